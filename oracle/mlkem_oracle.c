@@ -1,0 +1,689 @@
+/*
+ * oracle/mlkem_oracle.c -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+ *
+ * A plain-C, CPU-only restatement of the algorithm implemented by the
+ * reference rsjahnige/CRYSTALS-Kyber (`ml_kem.c`, `sha3.c`).  It exists so
+ * the CUDA path can be checked bit-for-bit on large batches, which the
+ * reference itself (0.03-0.15 s per KEM operation) is too slow for.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+ * --impl reference legs may load this library.  The shipped library
+ * (libmlkem_b200.so) never links, loads or calls anything in oracle/.
+ *
+ * Parity status: PINNED.  tests/test_oracle.py checks every function in this
+ * file against (a) the golden vectors of the reference's own Test_Archive
+ * drivers and (b) outputs of the reference itself, compiled from
+ * /root/reference by oracle/Makefile into oracle/_ref/ (fixtures committed
+ * under tests/golden/ so the check also runs where /root/reference is absent).
+ *
+ * Data layout differs from the reference on purpose: the reference stores one
+ * byte / one coefficient per 4-byte union (ml_kem.h:35-38, ml_kem.c:20-23);
+ * here bytes are uint8_t and coefficients uint16_t.  Values are identical.
+ *
+ * Deliberate deviations of the reference from FIPS 203 that are reproduced
+ * here because parity is defined against ml_kem.c:
+ *   D1  PRF = SHAKE128 (capacity 256)      ml_kem.c:508 with sha3.c:263
+ *   D2  J   = SHAKE128 (capacity 256)      ml_kem.c:546
+ *   D4  ByteDecode_12 does not reduce mod q ml_kem.c:162-171
+ */
+#include <stdint.h>
+#include <stddef.h>
+#include <string.h>
+
+#define ORC_N 256
+#define ORC_Q 3329
+
+#if defined(__GNUC__)
+#define ORC_API __attribute__((visibility("default")))
+#else
+#define ORC_API
+#endif
+
+/* ------------------------------------------------------------------ */
+/* Keccak-f[1600] on 25 little-endian 64-bit lanes.                     */
+/* Restates sha3.c:15-216 (Theta, Rho, Pi, Chi, rc, Iota, Keccak_f),    */
+/* which works on 1600 one-bit cells; for byte-aligned messages the     */
+/* two are the same function (FIPS 202 section 3).                      */
+/* ------------------------------------------------------------------ */
+
+/* Round constants: what sha3.c:148-205 (rc + Iota) recomputes by LFSR. */
+static uint64_t orc_rc_table[24];
+static int orc_rc_ready = 0;
+
+static void orc_rc_init(void) {
+    /* LFSR x^8+x^6+x^5+x^4+1, FIPS 202 Alg. 5 (sha3.c:148-180). */
+    uint8_t lfsr = 1;
+    for (int round = 0; round < 24; round++) {
+        uint64_t c = 0;
+        for (int j = 0; j <= 6; j++) {
+            if (lfsr & 1) c |= 1ULL << ((1u << j) - 1);
+            uint8_t hi = lfsr & 0x80;
+            lfsr <<= 1;
+            if (hi) lfsr ^= 0x71;
+        }
+        orc_rc_table[round] = c;
+    }
+    orc_rc_ready = 1;
+}
+
+static inline uint64_t orc_rotl(uint64_t v, unsigned n) {
+    return n ? (v << n) | (v >> (64 - n)) : v;
+}
+
+ORC_API void orc_keccak_f1600(uint64_t a[25]) {
+    static const unsigned rho[25] = {0,  1,  62, 28, 27, 36, 44, 6,  55, 20, 3,  10, 43,
+                                     25, 39, 41, 45, 15, 21, 8,  18, 2,  61, 56, 14};
+    if (!orc_rc_ready) orc_rc_init();
+    for (int round = 0; round < 24; round++) {
+        uint64_t c[5], b[25];
+        for (int x = 0; x < 5; x++) c[x] = a[x] ^ a[x + 5] ^ a[x + 10] ^ a[x + 15] ^ a[x + 20];
+        for (int x = 0; x < 5; x++) { /* theta, sha3.c:15 */
+            uint64_t d = c[(x + 4) % 5] ^ orc_rotl(c[(x + 1) % 5], 1);
+            for (int y = 0; y < 25; y += 5) a[y + x] ^= d;
+        }
+        for (int x = 0; x < 5; x++) /* rho + pi, sha3.c:53,88 */
+            for (int y = 0; y < 5; y++) b[y + 5 * ((2 * x + 3 * y) % 5)] = orc_rotl(a[x + 5 * y], rho[x + 5 * y]);
+        for (int y = 0; y < 25; y += 5) /* chi, sha3.c:116 */
+            for (int x = 0; x < 5; x++) a[y + x] = b[y + x] ^ (~b[y + (x + 1) % 5] & b[y + (x + 2) % 5]);
+        a[0] ^= orc_rc_table[round]; /* iota, sha3.c:182 */
+    }
+}
+
+/*
+ * Sponge over byte strings (sha3.c:257 Sponge, :226 pad, :408 sha3_b).
+ * `rate` in bytes (= (1600 - c)/8), `dsfx` = domain suffix bits followed by
+ * the first pad bit, little-endian in one byte: 0x06 for sfx {0,1} (hash),
+ * 0x1F for sfx {1,1,1,1} (XOF).
+ * Squeeze follows sha3.c:298-311: a permutation is applied only when more
+ * output is still needed after the current block.
+ */
+ORC_API void orc_sponge(unsigned rate, uint8_t dsfx, const uint8_t *in, size_t inlen, uint8_t *out,
+                        size_t outlen) {
+    uint64_t s[25];
+    uint8_t blk[200];
+    memset(s, 0, sizeof s);
+    while (inlen >= rate) {
+        for (unsigned i = 0; i < rate / 8; i++) {
+            uint64_t w;
+            memcpy(&w, in + 8 * i, 8);
+            s[i] ^= w;
+        }
+        orc_keccak_f1600(s);
+        in += rate;
+        inlen -= rate;
+    }
+    memset(blk, 0, rate);
+    memcpy(blk, in, inlen);
+    blk[inlen] ^= dsfx;
+    blk[rate - 1] ^= 0x80;
+    for (unsigned i = 0; i < rate / 8; i++) {
+        uint64_t w;
+        memcpy(&w, blk + 8 * i, 8);
+        s[i] ^= w;
+    }
+    orc_keccak_f1600(s);
+    while (outlen > 0) {
+        size_t take = outlen < rate ? outlen : rate;
+        memcpy(out, s, take); /* little-endian host assumed (x86-64, as the reference's probes) */
+        out += take;
+        outlen -= take;
+        if (outlen > 0) orc_keccak_f1600(s);
+    }
+}
+
+/* ml_kem.c:521  H(s) = SHA3-256(s)  (c = 512 -> rate 136, sfx 01) */
+ORC_API void orc_H(const uint8_t *in, size_t len, uint8_t out[32]) { orc_sponge(136, 0x06, in, len, out, 32); }
+/* ml_kem.c:559  G(c) = SHA3-512(c)  (c = 1024 -> rate 72, sfx 01) */
+ORC_API void orc_G(const uint8_t *in, size_t len, uint8_t out[64]) { orc_sponge(72, 0x06, in, len, out, 64); }
+/* ml_kem.c:540  J: sha3_b(..., c = N = 256, sfx 1111) => rate 168 => SHAKE128 (D2) */
+ORC_API void orc_J(const uint8_t *in, size_t len, uint8_t out[32]) { orc_sponge(168, 0x1F, in, len, out, 32); }
+/* ml_kem.c:496  PRF_eta(s,b): sha3_b(s||b, 8*64*eta, c = N = 256, sfx 1111) => SHAKE128 (D1) */
+ORC_API void orc_PRF(const uint8_t s[32], uint8_t b, unsigned eta, uint8_t *out) {
+    uint8_t seed[33];
+    memcpy(seed, s, 32);
+    seed[32] = b;
+    orc_sponge(168, 0x1F, seed, 33, out, 64 * eta);
+}
+/* Standard SHAKE256, used only by the optional FIPS-mode cross checks in tests. */
+ORC_API void orc_shake256(const uint8_t *in, size_t len, uint8_t *out, size_t outlen) {
+    orc_sponge(136, 0x1F, in, len, out, outlen);
+}
+ORC_API void orc_shake128(const uint8_t *in, size_t len, uint8_t *out, size_t outlen) {
+    orc_sponge(168, 0x1F, in, len, out, outlen);
+}
+
+/* ------------------------------------------------------------------ */
+/* L1 codec primitives (ml_kem.c:26-177)                                */
+/* ------------------------------------------------------------------ */
+
+/* ml_kem.c:26 BitRev7 */
+ORC_API uint8_t orc_bitrev7(uint8_t r) {
+    uint8_t o = 0;
+    for (int i = 0; i < 7; i++) o |= ((r >> i) & 1) << (6 - i);
+    return o;
+}
+
+/* ml_kem.c:83 Compress: quotient of 2^d*x by q, +1 when remainder > q/2, mod 2^d; identity for d = 12. */
+ORC_API uint16_t orc_compress(uint16_t x, unsigned d) {
+    x &= 0xFFF;
+    if (d < 12) {
+        uint32_t div = ((uint32_t)1 << d) * x;
+        uint32_t quo = div / ORC_Q, rem = div % ORC_Q;
+        if (rem > ORC_Q / 2) quo += 1;
+        x = (uint16_t)(quo % (1u << d));
+    }
+    return x;
+}
+
+/* ml_kem.c:104 Decompress: quotient of q*y by 2^d, +1 when remainder >= 2^(d-1); identity for d = 12. */
+ORC_API uint16_t orc_decompress(uint16_t y, unsigned d) {
+    y &= 0xFFF;
+    if (d < 12) {
+        uint32_t dsr = 1u << d;
+        uint32_t div = (uint32_t)ORC_Q * y;
+        uint32_t quo = div / dsr, rem = div % dsr;
+        if (rem >= dsr / 2) quo += 1;
+        y = (uint16_t)(quo & 0xFFF);
+    }
+    return y;
+}
+
+/* ml_kem.c:125 ByteEncode_d: 256 d-bit values, little-endian bit packing, 32*d bytes out. */
+ORC_API void orc_byte_encode(const uint16_t F[ORC_N], unsigned d, uint8_t *B) {
+    memset(B, 0, 32 * d);
+    for (unsigned i = 0; i < ORC_N; i++)
+        for (unsigned j = 0; j < d; j++) {
+            unsigned bit = (F[i] >> j) & 1, pos = i * d + j;
+            B[pos >> 3] |= (uint8_t)(bit << (pos & 7));
+        }
+}
+
+/* ml_kem.c:153 ByteDecode_d.  For d = 12 the reference applies `% q` to each single-bit term
+ * b*2^j (always < q), i.e. it never reduces: 12-bit values 3329..4095 pass through (D4). */
+ORC_API void orc_byte_decode(const uint8_t *B, unsigned d, uint16_t F[ORC_N]) {
+    for (unsigned i = 0; i < ORC_N; i++) {
+        uint16_t v = 0;
+        for (unsigned j = 0; j < d; j++) {
+            unsigned pos = i * d + j;
+            v |= (uint16_t)(((B[pos >> 3] >> (pos & 7)) & 1) << j);
+        }
+        F[i] = v;
+    }
+}
+
+/* ------------------------------------------------------------------ */
+/* L2 samplers (ml_kem.c:189-275)                                       */
+/* ------------------------------------------------------------------ */
+
+/*
+ * ml_kem.c:189 SampleNTT.  840 bytes of SHAKE128(B[0..33]) are squeezed up front (:201); at most 279
+ * three-byte groups are consumed (:221-227 -- the loop gives up after the 279th group even if that
+ * group completed the polynomial); on give-up B[32] and B[33] are incremented in the CALLER's buffer
+ * and the whole procedure restarts (:237-242).  Returns the number of restarts (0 in practice).
+ */
+ORC_API int orc_sample_ntt(uint8_t B[34], uint16_t a[ORC_N]) {
+    int restarts = 0;
+    for (;;) {
+        uint8_t S[840];
+        unsigned j = 0, grp = 0;
+        int gave_up = 0;
+        orc_sponge(168, 0x1F, B, 34, S, 840);
+        while (j < ORC_N) {
+            const uint8_t *C = S + 3 * grp;
+            uint16_t d1 = (uint16_t)(C[0] + 256 * (C[1] % 16));
+            uint16_t d2 = (uint16_t)((C[1] / 16) + 16 * C[2]);
+            if (d1 < ORC_Q) a[j++] = d1;
+            if (d2 < ORC_Q && j < ORC_N) a[j++] = d2;
+            grp++;
+            if (grp >= 279) {
+                gave_up = 1;
+                break;
+            }
+        }
+        if (!gave_up) return restarts;
+        B[32] = (uint8_t)(B[32] + 1);
+        B[33] = (uint8_t)(B[33] + 1);
+        restarts++;
+    }
+}
+
+/* ml_kem.c:253 SamplePolyCBD_eta over 64*eta bytes. */
+ORC_API void orc_sample_cbd(const uint8_t *B, unsigned eta, uint16_t f[ORC_N]) {
+    for (unsigned i = 0; i < ORC_N; i++) {
+        unsigned x = 0, y = 0;
+        for (unsigned j = 0; j < eta; j++) {
+            unsigned px = 2 * i * eta + j, py = 2 * i * eta + eta + j;
+            x += (B[px >> 3] >> (px & 7)) & 1;
+            y += (B[py >> 3] >> (py & 7)) & 1;
+        }
+        f[i] = (uint16_t)(x >= y ? x - y : ORC_Q - (y - x));
+    }
+}
+
+/* ------------------------------------------------------------------ */
+/* L3 ring arithmetic (ml_kem.c:287-442, 580-638)                       */
+/* ------------------------------------------------------------------ */
+
+static unsigned orc_pow17(unsigned e) {
+    unsigned z = 1;
+    while (e--) z = (z * 17) % ORC_Q;
+    return z;
+}
+
+/* zeta_i = 17^BitRev7(i) (ml_kem.c:300-307), gamma_i = 17^(2 BitRev7(i)+1) (ml_kem.c:424-433) */
+ORC_API void orc_zeta_table(uint16_t z[128]) {
+    for (unsigned i = 0; i < 128; i++) z[i] = (uint16_t)orc_pow17(orc_bitrev7((uint8_t)i));
+}
+ORC_API void orc_gamma_table(uint16_t g[128]) {
+    for (unsigned i = 0; i < 128; i++) g[i] = (uint16_t)orc_pow17(2 * orc_bitrev7((uint8_t)i) + 1);
+}
+
+/*
+ * ml_kem.c:287 NTT.  Inputs are 12-bit fields (`.t`); the reference's update is
+ *   t = zeta*f[j+len] % q;  f[j+len] = f[j] >= t ? f[j]-t : q-(t-f[j]);  f[j] = (f[j]+t) % q
+ * which is the textbook butterfly for canonical inputs, and is restated literally (including
+ * the 12-bit truncation) so that non-canonical inputs behave as in the reference too.
+ */
+ORC_API void orc_ntt(const uint16_t f[ORC_N], uint16_t fh[ORC_N]) {
+    uint16_t zt[128];
+    orc_zeta_table(zt);
+    for (int j = 0; j < ORC_N; j++) fh[j] = f[j] & 0xFFF;
+    unsigned i = 1;
+    for (int len = 128; len >= 2; len /= 2)
+        for (int start = 0; start < ORC_N; start += 2 * len) {
+            uint32_t zeta = zt[i++];
+            for (int j = start; j < start + len; j++) {
+                uint32_t t = (zeta * fh[j + len]) % ORC_Q;
+                uint32_t lo = fh[j];
+                fh[j + len] = (uint16_t)((lo >= t ? lo - t : ORC_Q - (t - lo)) & 0xFFF);
+                fh[j] = (uint16_t)((lo + t) % ORC_Q);
+            }
+        }
+}
+
+/* ml_kem.c:336 InverseNTT, then multiplication by 3303 = 128^-1 mod q (:378-381). */
+ORC_API void orc_intt(const uint16_t fh[ORC_N], uint16_t f[ORC_N]) {
+    uint16_t zt[128];
+    orc_zeta_table(zt);
+    for (int j = 0; j < ORC_N; j++) f[j] = fh[j] & 0xFFF;
+    unsigned i = 127;
+    for (int len = 2; len <= 128; len *= 2)
+        for (int start = 0; start < ORC_N; start += 2 * len) {
+            uint32_t zeta = zt[i--];
+            for (int j = start; j < start + len; j++) {
+                uint32_t t = f[j], u = f[j + len];
+                f[j] = (uint16_t)((t + u) % ORC_Q);
+                uint32_t diff = (u >= t ? u - t : ORC_Q - (t - u)) & 0xFFFFFF;
+                f[j + len] = (uint16_t)((zeta * diff) % ORC_Q);
+            }
+        }
+    for (int j = 0; j < ORC_N; j++) f[j] = (uint16_t)(((uint32_t)f[j] * 3303u) % ORC_Q);
+}
+
+/* ml_kem.c:395 BaseCaseMultiply (inputs may be any 12-bit value, D4; products fit 24 bits). */
+ORC_API void orc_basecase_multiply(uint16_t a0, uint16_t a1, uint16_t b0, uint16_t b1, uint16_t gamma,
+                                   uint16_t c[2]) {
+    uint32_t t;
+    t = ((uint32_t)a1 * b1) % ORC_Q;
+    t = (t * gamma) % ORC_Q;
+    t += ((uint32_t)a0 * b0) % ORC_Q;
+    c[0] = (uint16_t)(t % ORC_Q);
+    t = ((uint32_t)a0 * b1) % ORC_Q;
+    t += ((uint32_t)a1 * b0) % ORC_Q;
+    c[1] = (uint16_t)(t % ORC_Q);
+}
+
+/* ml_kem.c:415 MultiplyNTTs */
+ORC_API void orc_multiply_ntts(const uint16_t f[ORC_N], const uint16_t g[ORC_N], uint16_t h[ORC_N]) {
+    uint16_t gm[128];
+    orc_gamma_table(gm);
+    for (int i = 0; i < 128; i++)
+        orc_basecase_multiply(f[2 * i] & 0xFFF, f[2 * i + 1] & 0xFFF, g[2 * i] & 0xFFF, g[2 * i + 1] & 0xFFF,
+                              gm[i], h + 2 * i);
+}
+
+/* ml_kem.c:580 PolyAddition, :599 PolySubtraction */
+ORC_API void orc_poly_add(const uint16_t u[ORC_N], const uint16_t v[ORC_N], uint16_t z[ORC_N]) {
+    for (int i = 0; i < ORC_N; i++) z[i] = (uint16_t)(((uint32_t)(u[i] & 0xFFF) + (v[i] & 0xFFF)) % ORC_Q);
+}
+ORC_API void orc_poly_sub(const uint16_t u[ORC_N], const uint16_t v[ORC_N], uint16_t z[ORC_N]) {
+    for (int i = 0; i < ORC_N; i++) {
+        uint32_t a = u[i] & 0xFFF, b = v[i] & 0xFFF;
+        z[i] = (uint16_t)((a < b ? ORC_Q - (b - a) : a - b) & 0xFFF);
+    }
+}
+
+/* ml_kem.c:618 VectorMultiply: sum_i MultiplyNTTs(u[i], v[i]); u, v are k contiguous polynomials. */
+ORC_API void orc_vector_multiply(const uint16_t *u, const uint16_t *v, unsigned k, uint16_t w[ORC_N]) {
+    uint16_t z[ORC_N];
+    orc_multiply_ntts(u, v, w);
+    for (unsigned i = 1; i < k; i++) {
+        orc_multiply_ntts(u + i * ORC_N, v + i * ORC_N, z);
+        orc_poly_add(w, z, w);
+    }
+}
+
+/* ------------------------------------------------------------------ */
+/* Parameter sets (ml_kem.c:1363 init)                                  */
+/* ------------------------------------------------------------------ */
+typedef struct {
+    unsigned k, eta1, eta2, du, dv;
+} orc_params;
+
+ORC_API int orc_params_init(int set, orc_params *p) {
+    switch (set) {
+    case 512: *p = (orc_params){2, 3, 2, 10, 4}; return 0;
+    case 768: *p = (orc_params){3, 2, 2, 10, 4}; return 0;
+    case 1024: *p = (orc_params){4, 2, 2, 11, 5}; return 0;
+    default: return -1; /* ml_errno = -1, ml_kem.c:1391 */
+    }
+}
+ORC_API unsigned orc_ek_len(int set) { orc_params p; return orc_params_init(set, &p) ? 0 : 384 * p.k + 32; }
+ORC_API unsigned orc_dk_len(int set) { orc_params p; return orc_params_init(set, &p) ? 0 : 768 * p.k + 96; }
+ORC_API unsigned orc_c_len(int set) { orc_params p; return orc_params_init(set, &p) ? 0 : 32 * (p.du * p.k + p.dv); }
+
+#define ORC_KMAX 4
+
+/* ------------------------------------------------------------------ */
+/* L4 K-PKE (ml_kem.c:651-1023)                                         */
+/* ------------------------------------------------------------------ */
+
+/* ml_kem.c:651 PKE_KeyGen: ek = ByteEncode12(t^)||rho (384k+32 B), dk = ByteEncode12(s^) (384k B). */
+ORC_API int orc_pke_keygen(int set, const uint8_t d[32], uint8_t *ek, uint8_t *dk) {
+    orc_params p;
+    if (orc_params_init(set, &p)) return -1;
+    unsigned k = p.k;
+    uint8_t in[33], gout[64], rho[34], prf[192];
+    uint16_t A[ORC_KMAX][ORC_KMAX][ORC_N], s[ORC_KMAX][ORC_N], e[ORC_KMAX][ORC_N], t[ORC_N], tmp[ORC_N];
+    memcpy(in, d, 32);
+    in[32] = (uint8_t)k; /* :674-675 */
+    orc_G(in, 33, gout);
+    memcpy(rho, gout, 32);
+    const uint8_t *sigma = gout + 32;
+    for (unsigned i = 0; i < k; i++) /* :686-693; rho[32],rho[33] persist across calls as in the reference */
+        for (unsigned j = 0; j < k; j++) {
+            rho[32] = (uint8_t)j;
+            rho[33] = (uint8_t)i;
+            orc_sample_ntt(rho, A[i][j]);
+        }
+    uint8_t n = 0;
+    for (unsigned i = 0; i < k; i++) { /* :696-706 */
+        orc_PRF(sigma, n++, p.eta1, prf);
+        orc_sample_cbd(prf, p.eta1, tmp);
+        orc_ntt(tmp, s[i]);
+    }
+    for (unsigned i = 0; i < k; i++) { /* :710-720 */
+        orc_PRF(sigma, n++, p.eta1, prf);
+        orc_sample_cbd(prf, p.eta1, tmp);
+        orc_ntt(tmp, e[i]);
+    }
+    for (unsigned i = 0; i < k; i++) { /* :723-747 */
+        orc_vector_multiply(&A[i][0][0], &s[0][0], k, tmp);
+        orc_poly_add(tmp, e[i], t);
+        orc_byte_encode(t, 12, ek + 384 * i);
+    }
+    memcpy(ek + 384 * k, rho, 32);
+    for (unsigned i = 0; i < k; i++) orc_byte_encode(s[i], 12, dk + 384 * i); /* :750-756 */
+    return 0;
+}
+
+/* ml_kem.c:776 PKE_Encrypt */
+ORC_API int orc_pke_encrypt(int set, const uint8_t *ek, const uint8_t m[32], const uint8_t r[32], uint8_t *c) {
+    orc_params p;
+    if (orc_params_init(set, &p)) return -1;
+    unsigned k = p.k;
+    uint8_t rho[34], prf[192];
+    uint16_t t[ORC_KMAX][ORC_N], y[ORC_KMAX][ORC_N], e1[ORC_KMAX][ORC_N], e2[ORC_N], At[ORC_KMAX][ORC_KMAX][ORC_N];
+    uint16_t tmp1[ORC_N], tmp2[ORC_N], u[ORC_N], mu[ORC_N], v[ORC_N];
+    for (unsigned i = 0; i < k; i++) orc_byte_decode(ek + 384 * i, 12, t[i]); /* :806-808 */
+    memcpy(rho, ek + 384 * k, 32);
+    for (unsigned i = 0; i < k; i++) /* :817-823, stored transposed */
+        for (unsigned j = 0; j < k; j++) {
+            rho[32] = (uint8_t)j;
+            rho[33] = (uint8_t)i;
+            orc_sample_ntt(rho, At[j][i]);
+        }
+    uint8_t n = 0;
+    for (unsigned i = 0; i < k; i++) { /* :826-836 */
+        orc_PRF(r, n++, p.eta1, prf);
+        orc_sample_cbd(prf, p.eta1, tmp1);
+        orc_ntt(tmp1, y[i]);
+    }
+    for (unsigned i = 0; i < k; i++) { /* :839-846 */
+        orc_PRF(r, n++, p.eta2, prf);
+        orc_sample_cbd(prf, p.eta2, e1[i]);
+    }
+    orc_PRF(r, n, p.eta2, prf); /* :849-851 */
+    orc_sample_cbd(prf, p.eta2, e2);
+    for (unsigned i = 0; i < k; i++) { /* :854-864 and :886-896 */
+        orc_vector_multiply(&At[i][0][0], &y[0][0], k, tmp1);
+        orc_intt(tmp1, tmp2);
+        orc_poly_add(tmp2, e1[i], u);
+        for (int j = 0; j < ORC_N; j++) u[j] = orc_compress(u[j], p.du);
+        orc_byte_encode(u, p.du, c + 32 * p.du * i);
+    }
+    orc_byte_decode(m, 1, tmp1); /* :867-870 */
+    for (int j = 0; j < ORC_N; j++) mu[j] = orc_decompress(tmp1[j], 1);
+    orc_vector_multiply(&t[0][0], &y[0][0], k, tmp1); /* :874-880 */
+    orc_intt(tmp1, tmp2);
+    orc_poly_add(tmp2, e2, tmp1);
+    orc_poly_add(tmp1, mu, v);
+    for (int j = 0; j < ORC_N; j++) v[j] = orc_compress(v[j], p.dv); /* :899-904 */
+    orc_byte_encode(v, p.dv, c + 32 * p.du * k);
+    return 0;
+}
+
+/* ml_kem.c:942 PKE_Decrypt */
+ORC_API int orc_pke_decrypt(int set, const uint8_t *dk, const uint8_t *c, uint8_t m[32]) {
+    orc_params p;
+    if (orc_params_init(set, &p)) return -1;
+    unsigned k = p.k;
+    uint16_t u[ORC_KMAX][ORC_N], s[ORC_KMAX][ORC_N], v[ORC_N], tmp1[ORC_N], tmp2[ORC_N], w[ORC_N];
+    for (unsigned i = 0; i < k; i++) { /* :978-987 */
+        orc_byte_decode(c + 32 * p.du * i, p.du, tmp1);
+        for (int j = 0; j < ORC_N; j++) tmp1[j] = orc_decompress(tmp1[j], p.du);
+        orc_ntt(tmp1, u[i]);
+    }
+    orc_byte_decode(c + 32 * p.du * k, p.dv, v); /* :990-993 */
+    for (int j = 0; j < ORC_N; j++) v[j] = orc_decompress(v[j], p.dv);
+    for (unsigned i = 0; i < k; i++) orc_byte_decode(dk + 384 * i, 12, s[i]); /* :996-998 */
+    orc_vector_multiply(&s[0][0], &u[0][0], k, tmp1);                            /* :1001-1003 */
+    orc_intt(tmp1, tmp2);
+    orc_poly_sub(v, tmp2, w);
+    for (int j = 0; j < ORC_N; j++) w[j] = orc_compress(w[j], 1); /* :1009-1012 */
+    orc_byte_encode(w, 1, m);
+    return 0;
+}
+
+/* ------------------------------------------------------------------ */
+/* L5 ML-KEM internal (ml_kem.c:1034-1225)                              */
+/* ------------------------------------------------------------------ */
+
+/* ml_kem.c:1034 KeyGen_internal: dk = dk_pke || ek || H(ek) || z */
+ORC_API int orc_keygen_internal(int set, const uint8_t d[32], const uint8_t z[32], uint8_t *ek, uint8_t *dk) {
+    orc_params p;
+    if (orc_params_init(set, &p)) return -1;
+    unsigned k = p.k, ekl = 384 * k + 32;
+    orc_pke_keygen(set, d, ek, dk);
+    memcpy(dk + 384 * k, ek, ekl);
+    orc_H(ek, ekl, dk + 384 * k + ekl);
+    memcpy(dk + 384 * k + ekl + 32, z, 32);
+    return 0;
+}
+
+/* ml_kem.c:1093 Encaps_internal: (K, r) = G(m || H(ek)); c = PKE_Encrypt(ek, m, r) */
+ORC_API int orc_encaps_internal(int set, const uint8_t *ek, const uint8_t m[32], uint8_t *c, uint8_t K[32]) {
+    orc_params p;
+    if (orc_params_init(set, &p)) return -1;
+    uint8_t in[64], g[64];
+    memcpy(in, m, 32);
+    orc_H(ek, 384 * p.k + 32, in + 32);
+    orc_G(in, 64, g);
+    memcpy(K, g, 32);
+    return orc_pke_encrypt(set, ek, m, g + 32, c);
+}
+
+/* ml_kem.c:1136 Decaps_internal.  The reference compares c and c' with an early-exit loop (:1209-1215);
+ * the selected key is the same as with a full compare, which is what is done here. */
+ORC_API int orc_decaps_internal(int set, const uint8_t *dk, const uint8_t *c, uint8_t K[32]) {
+    orc_params p;
+    if (orc_params_init(set, &p)) return -1;
+    unsigned k = p.k, ekl = 384 * k + 32, cl = 32 * (p.du * k + p.dv);
+    const uint8_t *ek = dk + 384 * k, *h = ek + ekl, *z = h + 32;
+    uint8_t m[32], in[64], g[64], Kbar[32];
+    uint8_t jin[32 + 32 * (11 * 4 + 5)], c2[32 * (11 * 4 + 5)];
+    orc_pke_decrypt(set, dk, c, m);
+    memcpy(in, m, 32);
+    memcpy(in + 32, h, 32);
+    orc_G(in, 64, g);
+    memcpy(jin, z, 32);
+    memcpy(jin + 32, c, cl);
+    orc_J(jin, 32 + cl, Kbar);
+    orc_pke_encrypt(set, ek, m, g + 32, c2);
+    unsigned diff = 0;
+    for (unsigned i = 0; i < cl; i++) diff |= (unsigned)(c[i] ^ c2[i]);
+    memcpy(K, diff ? Kbar : g, 32);
+    return 0;
+}
+
+/* ------------------------------------------------------------------ */
+/* L6 input checks of the public wrappers (ml_kem.c:1257-1359).          */
+/* Return value = the ml_errno the reference would set (0 = accepted).   */
+/* ------------------------------------------------------------------ */
+ORC_API int orc_check_encaps_input(int set, const uint8_t *ek, unsigned ek_len) {
+    orc_params p;
+    if (orc_params_init(set, &p)) return -1;
+    if (384 * p.k + 32 != ek_len) return -3; /* :1267 */
+    for (unsigned i = 0; i < p.k; i++) {     /* :1274-1291: cannot fail, see D4 */
+        uint16_t t[ORC_N];
+        uint8_t back[384];
+        orc_byte_decode(ek + 384 * i, 12, t);
+        orc_byte_encode(t, 12, back);
+        if (memcmp(back, ek + 384 * i, 384)) return -4;
+    }
+    return 0;
+}
+ORC_API int orc_check_decaps_input(int set, const uint8_t *dk, unsigned dk_len, unsigned c_len) {
+    orc_params p;
+    if (orc_params_init(set, &p)) return -1;
+    if (c_len != 32 * (p.du * p.k + p.dv)) return -3; /* :1321 */
+    if (dk_len != 768 * p.k + 96) return -3;          /* :1329 */
+    uint8_t h[32];
+    orc_H(dk + 384 * p.k, 384 * p.k + 32, h); /* :1336-1350 */
+    if (memcmp(h, dk + 768 * p.k + 32, 32)) return -5;
+    return 0;
+}
+
+/* ------------------------------------------------------------------ */
+/* Batch drivers (dense, item-major), OpenMP over items when compiled   */
+/* with -fopenmp.  These exist so tests can check 2^16..2^20-item GPU    */
+/* batches in seconds and so bench.py can time a CPU port.              */
+/* ------------------------------------------------------------------ */
+ORC_API void orc_ntt_batch(size_t n, const uint16_t *f, uint16_t *fh) {
+#pragma omp parallel for schedule(static)
+    for (long long i = 0; i < (long long)n; i++) orc_ntt(f + i * ORC_N, fh + i * ORC_N);
+}
+ORC_API void orc_intt_batch(size_t n, const uint16_t *fh, uint16_t *f) {
+#pragma omp parallel for schedule(static)
+    for (long long i = 0; i < (long long)n; i++) orc_intt(fh + i * ORC_N, f + i * ORC_N);
+}
+ORC_API void orc_multiply_ntts_batch(size_t n, const uint16_t *f, const uint16_t *g, uint16_t *h) {
+#pragma omp parallel for schedule(static)
+    for (long long i = 0; i < (long long)n; i++) orc_multiply_ntts(f + i * ORC_N, g + i * ORC_N, h + i * ORC_N);
+}
+ORC_API void orc_sample_ntt_batch(size_t n, const uint8_t *seeds34, uint16_t *a) {
+#pragma omp parallel for schedule(static)
+    for (long long i = 0; i < (long long)n; i++) {
+        uint8_t B[34];
+        memcpy(B, seeds34 + 34 * i, 34);
+        orc_sample_ntt(B, a + i * ORC_N);
+    }
+}
+ORC_API void orc_prf_cbd_batch(size_t n, unsigned eta, const uint8_t *seeds32, const uint8_t *nonce, uint16_t *f) {
+#pragma omp parallel for schedule(static)
+    for (long long i = 0; i < (long long)n; i++) {
+        uint8_t prf[192];
+        orc_PRF(seeds32 + 32 * i, nonce[i], eta, prf);
+        orc_sample_cbd(prf, eta, f + i * ORC_N);
+    }
+}
+ORC_API void orc_cbd_batch(size_t n, unsigned eta, const uint8_t *bytes, uint16_t *f) {
+#pragma omp parallel for schedule(static)
+    for (long long i = 0; i < (long long)n; i++) orc_sample_cbd(bytes + 64 * eta * i, eta, f + i * ORC_N);
+}
+ORC_API void orc_byte_encode_batch(size_t n, unsigned d, const uint16_t *F, uint8_t *B) {
+#pragma omp parallel for schedule(static)
+    for (long long i = 0; i < (long long)n; i++) orc_byte_encode(F + i * ORC_N, d, B + 32 * d * i);
+}
+ORC_API void orc_byte_decode_batch(size_t n, unsigned d, const uint8_t *B, uint16_t *F) {
+#pragma omp parallel for schedule(static)
+    for (long long i = 0; i < (long long)n; i++) orc_byte_decode(B + 32 * d * i, d, F + i * ORC_N);
+}
+ORC_API void orc_compress_batch(size_t ncoef, unsigned d, const uint16_t *x, uint16_t *y) {
+#pragma omp parallel for schedule(static)
+    for (long long i = 0; i < (long long)ncoef; i++) y[i] = orc_compress(x[i], d);
+}
+ORC_API void orc_decompress_batch(size_t ncoef, unsigned d, const uint16_t *x, uint16_t *y) {
+#pragma omp parallel for schedule(static)
+    for (long long i = 0; i < (long long)ncoef; i++) y[i] = orc_decompress(x[i], d);
+}
+ORC_API void orc_hash_batch(int which, size_t n, size_t len, const uint8_t *in, uint8_t *out) {
+    /* which: 0 = H (32 B out), 1 = G (64 B out), 2 = J (32 B out) */
+    size_t ol = which == 1 ? 64 : 32;
+#pragma omp parallel for schedule(static)
+    for (long long i = 0; i < (long long)n; i++) {
+        if (which == 0) orc_H(in + len * i, len, out + ol * i);
+        else if (which == 1) orc_G(in + len * i, len, out + ol * i);
+        else orc_J(in + len * i, len, out + ol * i);
+    }
+}
+ORC_API int orc_keygen_batch(int set, size_t n, const uint8_t *d, const uint8_t *z, uint8_t *ek, uint8_t *dk) {
+    unsigned ekl = orc_ek_len(set), dkl = orc_dk_len(set);
+    if (!ekl) return -1;
+#pragma omp parallel for schedule(dynamic, 16)
+    for (long long i = 0; i < (long long)n; i++)
+        orc_keygen_internal(set, d + 32 * i, z + 32 * i, ek + (size_t)ekl * i, dk + (size_t)dkl * i);
+    return 0;
+}
+ORC_API int orc_encaps_batch(int set, size_t n, const uint8_t *ek, const uint8_t *m, uint8_t *c, uint8_t *K) {
+    unsigned ekl = orc_ek_len(set), cl = orc_c_len(set);
+    if (!ekl) return -1;
+#pragma omp parallel for schedule(dynamic, 16)
+    for (long long i = 0; i < (long long)n; i++)
+        orc_encaps_internal(set, ek + (size_t)ekl * i, m + 32 * i, c + (size_t)cl * i, K + 32 * i);
+    return 0;
+}
+ORC_API int orc_decaps_batch(int set, size_t n, const uint8_t *dk, const uint8_t *c, uint8_t *K) {
+    unsigned dkl = orc_dk_len(set), cl = orc_c_len(set);
+    if (!dkl) return -1;
+#pragma omp parallel for schedule(dynamic, 16)
+    for (long long i = 0; i < (long long)n; i++)
+        orc_decaps_internal(set, dk + (size_t)dkl * i, c + (size_t)cl * i, K + 32 * i);
+    return 0;
+}
+ORC_API int orc_pke_keygen_batch(int set, size_t n, const uint8_t *d, uint8_t *ek, uint8_t *dkpke) {
+    orc_params p;
+    if (orc_params_init(set, &p)) return -1;
+#pragma omp parallel for schedule(dynamic, 16)
+    for (long long i = 0; i < (long long)n; i++)
+        orc_pke_keygen(set, d + 32 * i, ek + (size_t)(384 * p.k + 32) * i, dkpke + (size_t)(384 * p.k) * i);
+    return 0;
+}
+ORC_API int orc_pke_encrypt_batch(int set, size_t n, const uint8_t *ek, const uint8_t *m, const uint8_t *r,
+                                  uint8_t *c) {
+    unsigned ekl = orc_ek_len(set), cl = orc_c_len(set);
+    if (!ekl) return -1;
+#pragma omp parallel for schedule(dynamic, 16)
+    for (long long i = 0; i < (long long)n; i++)
+        orc_pke_encrypt(set, ek + (size_t)ekl * i, m + 32 * i, r + 32 * i, c + (size_t)cl * i);
+    return 0;
+}
+ORC_API int orc_pke_decrypt_batch(int set, size_t n, size_t dk_stride, const uint8_t *dk, const uint8_t *c,
+                                  uint8_t *m) {
+    unsigned cl = orc_c_len(set);
+    if (!cl) return -1;
+#pragma omp parallel for schedule(dynamic, 16)
+    for (long long i = 0; i < (long long)n; i++)
+        orc_pke_decrypt(set, dk + dk_stride * i, c + (size_t)cl * i, m + 32 * i);
+    return 0;
+}
