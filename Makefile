@@ -1,0 +1,35 @@
+# Top-level build: the product library (CUDA, sm_100a), the INT32 microbenchmark and the checkers.
+#   make            -> crystals-kyber_b200/libmlkem_b200.so + build/microbench + oracle/
+#   make lib        -> only the product library
+NVCC    ?= /usr/local/cuda/bin/nvcc
+ARCH    := -gencode arch=compute_100a,code=sm_100a
+NVFLAGS := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC,-fvisibility=hidden -cudart static
+PKG     := crystals-kyber_b200
+CSRC    := $(PKG)/csrc
+LIB     := $(PKG)/libmlkem_b200.so
+
+all: lib tools oracle
+
+lib: $(LIB)
+
+$(LIB): $(CSRC)/mlkem_b200.cu $(CSRC)/mlkem_kernels.cuh $(CSRC)/mlkem_device.cuh $(CSRC)/ml_kem_compat.inl include/mlkem_b200.h include/ml_kem.h
+	$(NVCC) $(NVFLAGS) -shared -o $@ $(CSRC)/mlkem_b200.cu
+
+tools: build/microbench build/keccak_bench
+
+build/microbench: $(CSRC)/microbench.cu
+	mkdir -p build
+	$(NVCC) $(ARCH) -O3 -lineinfo -o $@ $<
+
+build/keccak_bench: $(CSRC)/keccak_bench.cu
+	mkdir -p build
+	$(NVCC) $(ARCH) -O3 -lineinfo -o $@ $<
+
+oracle:
+	$(MAKE) -C oracle
+
+clean:
+	rm -f $(LIB) build/microbench build/keccak_bench
+	$(MAKE) -C oracle clean
+
+.PHONY: all lib tools oracle clean

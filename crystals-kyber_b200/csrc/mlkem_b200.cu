@@ -1,0 +1,662 @@
+// mlkem_b200.cu -- host side of libmlkem_b200.so: the batched C ABI of include/mlkem_b200.h.
+//
+// Single translation unit: device code (mlkem_device.cuh, mlkem_kernels.cuh) + per-device context
+// (streams, workspace, staging buffers) + the pipelines that chain the kernels into KeyGen / Encaps /
+// Decaps / K-PKE, + the reference-signature API of include/ml_kem.h (ml_kem_compat.inl).
+//
+// There is no CPU implementation of any hot-path function in this library: if CUDA is unusable every entry
+// point fails with MLKEM_B200_ERR_CUDA.
+#include "mlkem_kernels.cuh"
+
+#include "../../include/mlkem_b200.h"
+
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+namespace {
+
+using namespace mlkem;
+
+thread_local char tl_error[512] = "";
+std::atomic<unsigned long long> g_launches{0};
+
+#define CU(call)                                                                                              \
+    do {                                                                                                      \
+        cudaError_t e_ = (call);                                                                              \
+        if (e_ != cudaSuccess) {                                                                              \
+            snprintf(tl_error, sizeof tl_error, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            return MLKEM_B200_ERR_CUDA;                                                                       \
+        }                                                                                                     \
+    } while (0)
+
+// kernel<<<...>>>(...) with launch accounting and error capture
+#define LAUNCH(kernel, grid, block, smem, stream, ...)           \
+    do {                                                         \
+        auto kern_ = kernel;                                     \
+        kern_<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__); \
+        g_launches.fetch_add(1, std::memory_order_relaxed);      \
+        CU(cudaGetLastError());                                  \
+    } while (0)
+
+inline unsigned cdiv(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
+
+// ------------------------------------------------------------------------------------------------
+// Tables
+// ------------------------------------------------------------------------------------------------
+unsigned bitrev7(unsigned r) {
+    unsigned o = 0;
+    for (int i = 0; i < 7; i++) o |= ((r >> i) & 1u) << (6 - i);
+    return o;
+}
+unsigned pow17(unsigned e) {
+    unsigned z = 1;
+    while (e--) z = (z * 17u) % kQ;
+    return z;
+}
+uint2 shoup_pair(unsigned w) { return make_uint2(w, (w << 16) / kQ); }
+
+void build_tables(TwiddleTables &t, uint2 rc[24]) {
+    for (unsigned i = 0; i < 128; i++) {
+        t.zeta[i] = shoup_pair(pow17(bitrev7(i)));           // ml_kem.c:300-307
+        t.gamma[i] = shoup_pair(pow17(2 * bitrev7(i) + 1));  // ml_kem.c:424-433
+    }
+    t.zeta_inv_last[0] = shoup_pair((t.zeta[1].x * 3303u) % kQ);  // ml_kem.c:378-381 folded into the last layer
+    t.zeta_inv_last[1] = shoup_pair(3303u);
+    // Keccak round constants from the LFSR of FIPS 202 Alg. 5 (what sha3.c:148-205 recomputes every round)
+    uint8_t lfsr = 1;
+    for (int round = 0; round < 24; round++) {
+        unsigned long long c = 0;
+        for (int j = 0; j <= 6; j++) {
+            if (lfsr & 1) c |= 1ULL << ((1u << j) - 1);
+            uint8_t hi = lfsr & 0x80;
+            lfsr = (uint8_t)(lfsr << 1);
+            if (hi) lfsr ^= 0x71;
+        }
+        rc[round] = make_uint2((unsigned)c, (unsigned)(c >> 32));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Per-device context
+// ------------------------------------------------------------------------------------------------
+constexpr int kSlots = 2;
+constexpr int kMaxDevices = 64;
+
+struct DeviceCtx {
+    bool ready = false;
+    cudaStream_t stream[kSlots] = {nullptr, nullptr};
+    void *ws[kSlots] = {nullptr, nullptr};  // kernel workspace (intermediates between kernels)
+    size_t ws_bytes[kSlots] = {0, 0};
+    void *io[kSlots] = {nullptr, nullptr};  // device staging of host-resident inputs / outputs
+    size_t io_bytes[kSlots] = {0, 0};
+};
+DeviceCtx g_ctx[kMaxDevices];
+std::mutex g_mutex;
+
+int ensure_buffer(void **p, size_t *have, size_t need) {
+    if (*have >= need) return 0;
+    if (*p) CU(cudaFree(*p));
+    *p = nullptr;
+    *have = 0;
+    size_t want = need + need / 8;
+    CU(cudaMalloc(p, want));
+    *have = want;
+    return 0;
+}
+
+template <class KernelT>
+int allow_smem(KernelT kernel, size_t bytes) {
+    CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    CU(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    return 0;
+}
+template <class P>
+int allow_smem_matvec() {
+    const size_t b = 32 * P::K * kSlotWords * 4;
+    if (int rc = allow_smem(k_sample_matvec<P, kModeKeyGen>, b)) return rc;
+    if (int rc = allow_smem(k_sample_matvec<P, kModeEncrypt>, b)) return rc;
+    if (int rc = allow_smem(k_sample_matvec<P, kModeEncryptCompare>, b)) return rc;
+    return 0;
+}
+
+// Select the device and make sure its context exists.  Returns the device ordinal through *dev.
+int acquire(const mlkem_b200_opts *o, int *dev, DeviceCtx **ctx) {
+    int d = o ? o->device : -1;
+    if (d < 0) CU(cudaGetDevice(&d));
+    if (d >= kMaxDevices) {
+        snprintf(tl_error, sizeof tl_error, "device ordinal %d out of range", d);
+        return MLKEM_B200_ERR_ARG;
+    }
+    CU(cudaSetDevice(d));
+    std::lock_guard<std::mutex> lock(g_mutex);
+    DeviceCtx &c = g_ctx[d];
+    if (!c.ready) {
+        TwiddleTables t;
+        uint2 rc[24];
+        build_tables(t, rc);
+        CU(cudaMemcpyToSymbol(c_tw, &t, sizeof t));
+        CU(cudaMemcpyToSymbol(c_keccak_rc, rc, sizeof rc));
+        for (int s = 0; s < kSlots; s++) CU(cudaStreamCreateWithFlags(&c.stream[s], cudaStreamNonBlocking));
+        if (int r = allow_smem_matvec<P512>()) return r;
+        if (int r = allow_smem_matvec<P768>()) return r;
+        if (int r = allow_smem_matvec<P1024>()) return r;
+        if (int r = allow_smem(k_sample_ntt_batch, 128 * kSlotWords * 4)) return r;
+        c.ready = true;
+    }
+    *dev = d;
+    *ctx = &c;
+    return 0;
+}
+
+// Bump allocator over a workspace buffer.
+struct Arena {
+    uint8_t *base;
+    size_t off = 0;
+    explicit Arena(void *p) : base(static_cast<uint8_t *>(p)) {}
+    template <class T>
+    T *take(size_t count) {
+        off = (off + 255) & ~size_t(255);
+        T *p = reinterpret_cast<T *>(base + off);
+        off += count * sizeof(T);
+        return p;
+    }
+};
+
+template <class P>
+constexpr size_t ws_bytes_per_item() {
+    // keygen: rs 64 + 2K polys ; encrypt: K polys + (K+1) code rows ; decaps adds m' 32 + K'r' 64 + flag 4
+    size_t kg = 64 + 2 * P::K * 512;
+    size_t enc = P::K * 512 + (P::K + 1) * 128 + 32;
+    size_t dec = enc + 32 + 64 + 4;
+    size_t m = kg > dec ? kg : dec;
+    return m + 64;
+}
+constexpr size_t kWsSlack = 16 * 256;
+
+// ------------------------------------------------------------------------------------------------
+// Pipelines on device pointers.  Every function only enqueues work on `st`.
+// ------------------------------------------------------------------------------------------------
+
+// K-PKE.Encrypt (ml_kem.c:776) for n items; `seed` = 32-byte PRF key r per item.
+// Stores c, or (cmp != nullptr) ORs the mismatch of the re-encryption against cmp into flags.
+template <class P>
+int enqueue_encrypt(cudaStream_t st, Arena &ws, int n, const uint8_t *ek, size_t ek_stride, const uint8_t *m,
+                    const uint8_t *seed, size_t seed_stride, uint8_t *c, const uint8_t *cmp, uint32_t *flags, int group_limit) {
+    constexpr int K = P::K;
+    uint16_t *yhat = ws.take<uint16_t>((size_t)n * K * 256);
+    uint32_t *codes = ws.take<uint32_t>((size_t)n * (K + 1) * 32);
+    // y^ = NTT(CBD_eta1(PRF(r, 0..K-1)))            ml_kem.c:826-836
+    LAUNCH((k_noise<P::ETA1, true>), dim3(cdiv(n, kNoiseTPB), K), kNoiseTPB, 0, st, n, seed, seed_stride, 0, yhat, (size_t)K * 256,
+           (uint32_t *)nullptr, (size_t)0);
+    // e1, e2 = CBD_eta2(PRF(r, K..2K))               ml_kem.c:839-851
+    LAUNCH((k_noise<P::ETA2, false>), dim3(cdiv(n, kNoiseTPB), K + 1), kNoiseTPB, 0, st, n, seed, seed_stride, K, (uint16_t *)nullptr,
+           (size_t)0, codes, (size_t)(K + 1) * 32);
+    MatvecArgs a{};
+    a.n = n;
+    a.group_limit = group_limit;
+    a.rho = ek + 384 * K;
+    a.rho_stride = ek_stride;
+    a.vec = yhat;
+    a.vec_stride = (size_t)K * 256;
+    a.addc = codes;
+    a.addc_stride = (size_t)(K + 1) * 32;
+    a.out = c;
+    a.out_stride = P::C;
+    a.cmp = cmp;
+    a.flags = flags;
+    const unsigned grid = cdiv((size_t)n * K, 32);
+    const size_t smem = 32 * K * kSlotWords * 4;
+    EncVArgs v{};
+    v.n = n;
+    v.ek = ek;
+    v.ek_stride = ek_stride;
+    v.yhat = yhat;
+    v.yhat_stride = (size_t)K * 256;
+    v.addc = codes;
+    v.addc_stride = (size_t)(K + 1) * 32;
+    v.m = m;
+    v.c = c;
+    v.c_stride = P::C;
+    v.cmp = cmp;
+    v.flags = flags;
+    if (cmp) {
+        LAUNCH((k_sample_matvec<P, kModeEncryptCompare>), grid, 32 * K, smem, st, a);
+        LAUNCH((k_encrypt_v<P, true>), cdiv(n, kWarpTPB / 32), kWarpTPB, 0, st, v);
+    } else {
+        LAUNCH((k_sample_matvec<P, kModeEncrypt>), grid, 32 * K, smem, st, a);
+        LAUNCH((k_encrypt_v<P, false>), cdiv(n, kWarpTPB / 32), kWarpTPB, 0, st, v);
+    }
+    return 0;
+}
+
+// KeyGen_internal (ml_kem.c:1034) when z != nullptr, PKE_KeyGen (ml_kem.c:651) otherwise.
+template <class P>
+int enqueue_keygen(cudaStream_t st, Arena &ws, int n, const uint8_t *d, const uint8_t *z, uint8_t *ek, uint8_t *dk, int group_limit) {
+    constexpr int K = P::K;
+    const bool full = z != nullptr;
+    const size_t dk_stride = full ? P::DK : P::DKPKE;
+    uint8_t *rs = ws.take<uint8_t>((size_t)n * 64);
+    uint16_t *se = ws.take<uint16_t>((size_t)n * 2 * K * 256);
+    LAUNCH(k_keygen_G, cdiv(n, kHashTPB), kHashTPB, 0, st, n, d, (uint32_t)K, rs);
+    // s^ (nonces 0..K-1) and e^ (nonces K..2K-1), ml_kem.c:696-720; sigma = rs + 32
+    LAUNCH((k_noise<P::ETA1, true>), dim3(cdiv(n, kNoiseTPB), 2 * K), kNoiseTPB, 0, st, n, rs + 32, (size_t)64, 0, se, (size_t)2 * K * 256,
+           (uint32_t *)nullptr, (size_t)0);
+    MatvecArgs a{};
+    a.n = n;
+    a.group_limit = group_limit;
+    a.rho = rs;
+    a.rho_stride = 64;
+    a.vec = se;
+    a.vec_stride = (size_t)2 * K * 256;
+    a.add16 = se + K * 256;
+    a.add16_stride = (size_t)2 * K * 256;
+    a.out = ek;
+    a.out_stride = P::EK;
+    a.out2 = full ? dk + 384 * K : nullptr;
+    a.out2_stride = dk_stride;
+    LAUNCH((k_sample_matvec<P, kModeKeyGen>), cdiv((size_t)n * K, 32), 32 * K, 32 * K * kSlotWords * 4, st, a);
+    LAUNCH((k_keygen_encode_s<P>), cdiv((size_t)n * K, kWarpTPB / 32), kWarpTPB, 0, st, n, se, (size_t)2 * K * 256, rs, ek, dk, dk_stride, full);
+    if (full) LAUNCH((k_keygen_H<P>), cdiv(n, kHashTPB), kHashTPB, 0, st, n, ek, z, dk);
+    return 0;
+}
+
+template <class P>
+int enqueue_encaps(cudaStream_t st, Arena &ws, int n, const uint8_t *ek, const uint8_t *m, uint8_t *c, uint8_t *Kout, int group_limit) {
+    uint8_t *r = ws.take<uint8_t>((size_t)n * 32);
+    LAUNCH((k_encaps_HG<P>), cdiv(n, kHashTPB), kHashTPB, 0, st, n, ek, m, Kout, r);
+    return enqueue_encrypt<P>(st, ws, n, ek, P::EK, m, r, 32, c, nullptr, nullptr, group_limit);
+}
+
+template <class P>
+int enqueue_decaps(cudaStream_t st, Arena &ws, int n, const uint8_t *dk, const uint8_t *c, uint8_t *Kout, int group_limit) {
+    constexpr int K = P::K;
+    uint8_t *mp = ws.take<uint8_t>((size_t)n * 32);
+    uint8_t *Kr = ws.take<uint8_t>((size_t)n * 64);
+    uint32_t *flags = ws.take<uint32_t>((size_t)n);
+    CU(cudaMemsetAsync(flags, 0, (size_t)n * 4, st));
+    LAUNCH((k_decrypt<P>), cdiv(n, kWarpTPB / 32), kWarpTPB, 0, st, n, dk, (size_t)P::DK, c, mp);
+    LAUNCH((k_decaps_G<P>), cdiv(n, kHashTPB), kHashTPB, 0, st, n, mp, dk, Kr);
+    // c' = K-PKE.Encrypt(ek_pke, m', r') compared on the fly (ml_kem.c:1206-1215)
+    if (int rc = enqueue_encrypt<P>(st, ws, n, dk + 384 * K, P::DK, mp, Kr + 32, 64, nullptr, c, flags, group_limit)) return rc;
+    LAUNCH((k_decaps_J_select<P>), cdiv(n, kHashTPB), kHashTPB, 0, st, n, dk, c, Kr, flags, Kout);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Generic batched driver: handles host / device memory, chunking and the two-slot pipeline.
+// ------------------------------------------------------------------------------------------------
+struct Buf {
+    const void *in;   // non-null for inputs
+    void *out;        // non-null for outputs
+    size_t item_bytes;
+};
+
+bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// run(stream, arena, n_chunk, ptrs[]) where ptrs[i] is the device address of buffer i for this chunk.
+template <class Run>
+int drive(const mlkem_b200_opts *o, size_t n, size_t ws_per_item, std::vector<Buf> bufs, Run run) {
+    if (n == 0) return MLKEM_B200_OK;
+    if (n > 0x7FFFFFFFull / 8) {
+        snprintf(tl_error, sizeof tl_error, "batch too large");
+        return MLKEM_B200_ERR_ARG;
+    }
+    for (auto &b : bufs)
+        if (!b.in && !b.out) {
+            snprintf(tl_error, sizeof tl_error, "NULL buffer");
+            return MLKEM_B200_ERR_ARG;
+        }
+    int dev;
+    DeviceCtx *ctx;
+    if (int rc = acquire(o, &dev, &ctx)) return rc;
+    const bool on_device = o && o->mem == MLKEM_B200_MEM_DEVICE;
+    size_t chunk = (o && o->chunk_items > 0) ? (size_t)o->chunk_items : (on_device ? (size_t)1 << 18 : (size_t)1 << 16);
+    if (chunk > n) chunk = n;
+    const size_t nchunks = (n + chunk - 1) / chunk;
+    std::vector<void *> ptrs(bufs.size());
+
+    if (on_device) {
+        for (auto &b : bufs)
+            if (!aligned16(b.in ? b.in : b.out)) {
+                snprintf(tl_error, sizeof tl_error, "device pointers must be 16-byte aligned");
+                return MLKEM_B200_ERR_ARG;
+            }
+        cudaStream_t st = o->stream ? static_cast<cudaStream_t>(o->stream) : ctx->stream[0];
+        {
+            std::lock_guard<std::mutex> lock(g_mutex);
+            if (int rc = ensure_buffer(&ctx->ws[0], &ctx->ws_bytes[0], chunk * ws_per_item + kWsSlack)) return rc;
+        }
+        for (size_t ci = 0; ci < nchunks; ci++) {
+            size_t i0 = ci * chunk, cn = (i0 + chunk <= n) ? chunk : n - i0;
+            for (size_t b = 0; b < bufs.size(); b++) {
+                const uint8_t *base = static_cast<const uint8_t *>(bufs[b].in ? bufs[b].in : bufs[b].out);
+                ptrs[b] = const_cast<uint8_t *>(base) + i0 * bufs[b].item_bytes;
+            }
+            Arena arena(ctx->ws[0]);
+            if (int rc = run(st, arena, (int)cn, ptrs.data())) return rc;
+        }
+        return MLKEM_B200_OK;
+    }
+
+    // host memory: stage each chunk through device buffers, alternate between two streams so that the
+    // copies of one chunk overlap the kernels of the other
+    size_t io_per_item = 0;
+    for (auto &b : bufs) io_per_item += (b.item_bytes + 15) & ~size_t(15);
+    {
+        std::lock_guard<std::mutex> lock(g_mutex);
+        const int nslots = nchunks > 1 ? kSlots : 1;
+        for (int s = 0; s < nslots; s++) {
+            if (int rc = ensure_buffer(&ctx->ws[s], &ctx->ws_bytes[s], chunk * ws_per_item + kWsSlack)) return rc;
+            if (int rc = ensure_buffer(&ctx->io[s], &ctx->io_bytes[s], chunk * io_per_item + 256 * bufs.size())) return rc;
+        }
+    }
+    for (size_t ci = 0; ci < nchunks; ci++) {
+        const int s = (int)(ci % kSlots);
+        cudaStream_t st = ctx->stream[s];
+        size_t i0 = ci * chunk, cn = (i0 + chunk <= n) ? chunk : n - i0;
+        Arena io(ctx->io[s]);
+        for (size_t b = 0; b < bufs.size(); b++) {
+            ptrs[b] = io.take<uint8_t>(chunk * bufs[b].item_bytes);
+            if (bufs[b].in)
+                CU(cudaMemcpyAsync(ptrs[b], static_cast<const uint8_t *>(bufs[b].in) + i0 * bufs[b].item_bytes, cn * bufs[b].item_bytes,
+                                   cudaMemcpyHostToDevice, st));
+        }
+        Arena arena(ctx->ws[s]);
+        if (int rc = run(st, arena, (int)cn, ptrs.data())) return rc;
+        for (size_t b = 0; b < bufs.size(); b++)
+            if (bufs[b].out)
+                CU(cudaMemcpyAsync(static_cast<uint8_t *>(bufs[b].out) + i0 * bufs[b].item_bytes, ptrs[b], cn * bufs[b].item_bytes,
+                                   cudaMemcpyDeviceToHost, st));
+    }
+    for (int s = 0; s < kSlots; s++) CU(cudaStreamSynchronize(ctx->stream[s]));
+    return MLKEM_B200_OK;
+}
+
+int group_limit_of(const mlkem_b200_opts *o) { return (o && o->sample_group_limit > 0) ? o->sample_group_limit : 278; }
+
+#define DISPATCH_SET(param_set, CALL)                   \
+    switch (param_set) {                                \
+    case 512: { using P = P512; CALL; } break;          \
+    case 768: { using P = P768; CALL; } break;          \
+    case 1024: { using P = P1024; CALL; } break;        \
+    default: return MLKEM_B200_ERR_PARAM;               \
+    }
+
+inline unsigned prim_grid(size_t n_polys) {
+    size_t blocks = (n_polys + (kPrimTPB / 32) - 1) / (kPrimTPB / 32);
+    size_t cap = 148 * 8 * 4;  // a few waves of 8 resident blocks per SM; the kernels grid-stride
+    return (unsigned)(blocks < cap ? blocks : cap);
+}
+
+}  // namespace
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+extern "C" {
+
+const char *mlkem_b200_version(void) { return "mlkem_b200 0.1 (sm_100a)"; }
+const char *mlkem_b200_last_error(void) { return tl_error; }
+unsigned long long mlkem_b200_launch_count(void) { return g_launches.load(); }
+int mlkem_b200_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+int mlkem_b200_synchronize(int device, void *stream) {
+    if (device >= 0) CU(cudaSetDevice(device));
+    if (stream) CU(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+    else CU(cudaDeviceSynchronize());
+    return 0;
+}
+void *mlkem_b200_host_alloc(size_t bytes) {
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) return nullptr;
+    return p;
+}
+void mlkem_b200_host_free(void *p) {
+    if (p) cudaFreeHost(p);
+}
+void mlkem_b200_release(int device) {
+    if (device < 0 || device >= kMaxDevices) return;
+    std::lock_guard<std::mutex> lock(g_mutex);
+    DeviceCtx &c = g_ctx[device];
+    if (!c.ready) return;
+    cudaSetDevice(device);
+    for (int s = 0; s < kSlots; s++) {
+        if (c.ws[s]) cudaFree(c.ws[s]);
+        if (c.io[s]) cudaFree(c.io[s]);
+        c.ws[s] = c.io[s] = nullptr;
+        c.ws_bytes[s] = c.io_bytes[s] = 0;
+    }
+}
+
+static unsigned k_of(int set) { return set == 512 ? 2 : set == 768 ? 3 : set == 1024 ? 4 : 0; }
+unsigned mlkem_b200_ek_bytes(int set) { unsigned k = k_of(set); return k ? 384 * k + 32 : 0; }
+unsigned mlkem_b200_dk_bytes(int set) { unsigned k = k_of(set); return k ? 768 * k + 96 : 0; }
+unsigned mlkem_b200_dkpke_bytes(int set) { unsigned k = k_of(set); return k ? 384 * k : 0; }
+unsigned mlkem_b200_ct_bytes(int set) {
+    switch (set) {
+    case 512: return P512::C;
+    case 768: return P768::C;
+    case 1024: return P1024::C;
+    default: return 0;
+    }
+}
+
+int mlkem_b200_keygen_batch(int set, size_t n, const uint8_t *d, const uint8_t *z, uint8_t *ek, uint8_t *dk, const mlkem_b200_opts *o) {
+    const int gl = group_limit_of(o);
+    DISPATCH_SET(set, return drive(o, n, ws_bytes_per_item<P>(), {{d, nullptr, 32}, {z, nullptr, 32}, {nullptr, ek, P::EK}, {nullptr, dk, P::DK}},
+                                   [=](cudaStream_t st, Arena &ws, int cn, void **p) {
+                                       return enqueue_keygen<P>(st, ws, cn, (const uint8_t *)p[0], (const uint8_t *)p[1], (uint8_t *)p[2], (uint8_t *)p[3], gl);
+                                   }));
+    return MLKEM_B200_ERR_PARAM;
+}
+
+int mlkem_b200_pke_keygen_batch(int set, size_t n, const uint8_t *d, uint8_t *ek, uint8_t *dkpke, const mlkem_b200_opts *o) {
+    const int gl = group_limit_of(o);
+    DISPATCH_SET(set, return drive(o, n, ws_bytes_per_item<P>(), {{d, nullptr, 32}, {nullptr, ek, P::EK}, {nullptr, dkpke, P::DKPKE}},
+                                   [=](cudaStream_t st, Arena &ws, int cn, void **p) {
+                                       return enqueue_keygen<P>(st, ws, cn, (const uint8_t *)p[0], nullptr, (uint8_t *)p[1], (uint8_t *)p[2], gl);
+                                   }));
+    return MLKEM_B200_ERR_PARAM;
+}
+
+int mlkem_b200_encaps_batch(int set, size_t n, const uint8_t *ek, const uint8_t *m, uint8_t *c, uint8_t *K, const mlkem_b200_opts *o) {
+    const int gl = group_limit_of(o);
+    DISPATCH_SET(set, return drive(o, n, ws_bytes_per_item<P>(), {{ek, nullptr, P::EK}, {m, nullptr, 32}, {nullptr, c, P::C}, {nullptr, K, 32}},
+                                   [=](cudaStream_t st, Arena &ws, int cn, void **p) {
+                                       return enqueue_encaps<P>(st, ws, cn, (const uint8_t *)p[0], (const uint8_t *)p[1], (uint8_t *)p[2], (uint8_t *)p[3], gl);
+                                   }));
+    return MLKEM_B200_ERR_PARAM;
+}
+
+int mlkem_b200_decaps_batch(int set, size_t n, const uint8_t *dk, const uint8_t *c, uint8_t *K, const mlkem_b200_opts *o) {
+    const int gl = group_limit_of(o);
+    DISPATCH_SET(set, return drive(o, n, ws_bytes_per_item<P>(), {{dk, nullptr, P::DK}, {c, nullptr, P::C}, {nullptr, K, 32}},
+                                   [=](cudaStream_t st, Arena &ws, int cn, void **p) {
+                                       return enqueue_decaps<P>(st, ws, cn, (const uint8_t *)p[0], (const uint8_t *)p[1], (uint8_t *)p[2], gl);
+                                   }));
+    return MLKEM_B200_ERR_PARAM;
+}
+
+int mlkem_b200_check_dk_batch(int set, size_t n, const uint8_t *dk, int32_t *status, const mlkem_b200_opts *o) {
+    DISPATCH_SET(set, return drive(o, n, 0, {{dk, nullptr, P::DK}, {nullptr, status, 4}}, [=](cudaStream_t st, Arena &, int cn, void **p) {
+                     LAUNCH((k_check_dk_hash<P>), cdiv(cn, kHashTPB), kHashTPB, 0, st, cn, (const uint8_t *)p[0], (int *)p[1]);
+                     return 0;
+                 }));
+    return MLKEM_B200_ERR_PARAM;
+}
+
+int mlkem_b200_pke_encrypt_batch(int set, size_t n, const uint8_t *ek, const uint8_t *m, const uint8_t *r, uint8_t *c, const mlkem_b200_opts *o) {
+    const int gl = group_limit_of(o);
+    DISPATCH_SET(set, return drive(o, n, ws_bytes_per_item<P>(), {{ek, nullptr, P::EK}, {m, nullptr, 32}, {r, nullptr, 32}, {nullptr, c, P::C}},
+                                   [=](cudaStream_t st, Arena &ws, int cn, void **p) {
+                                       return enqueue_encrypt<P>(st, ws, cn, (const uint8_t *)p[0], P::EK, (const uint8_t *)p[1], (const uint8_t *)p[2], 32,
+                                                                 (uint8_t *)p[3], nullptr, nullptr, gl);
+                                   }));
+    return MLKEM_B200_ERR_PARAM;
+}
+
+int mlkem_b200_pke_decrypt_batch(int set, size_t n, const uint8_t *dk, size_t dk_stride, const uint8_t *c, uint8_t *m, const mlkem_b200_opts *o) {
+    if (dk_stride % 16 != 0) {
+        snprintf(tl_error, sizeof tl_error, "dk_stride must be a multiple of 16");
+        return MLKEM_B200_ERR_ARG;
+    }
+    DISPATCH_SET(set, {
+        if (dk_stride < (size_t)P::DKPKE) return MLKEM_B200_ERR_LENGTH;
+        return drive(o, n, 0, {{dk, nullptr, dk_stride}, {c, nullptr, P::C}, {nullptr, m, 32}}, [=](cudaStream_t st, Arena &, int cn, void **p) {
+            LAUNCH((k_decrypt<P>), cdiv(cn, kWarpTPB / 32), kWarpTPB, 0, st, cn, (const uint8_t *)p[0], dk_stride, (const uint8_t *)p[1], (uint8_t *)p[2]);
+            return 0;
+        });
+    });
+    return MLKEM_B200_ERR_PARAM;
+}
+
+int mlkem_b200_ntt_batch(size_t n, const uint16_t *f, uint16_t *fh, const mlkem_b200_opts *o) {
+    return drive(o, n, 0, {{f, nullptr, 512}, {nullptr, fh, 512}}, [=](cudaStream_t st, Arena &, int cn, void **p) {
+        LAUNCH(k_ntt_batch, prim_grid(cn), kPrimTPB, 0, st, cn, (const uint16_t *)p[0], (uint16_t *)p[1]);
+        return 0;
+    });
+}
+int mlkem_b200_intt_batch(size_t n, const uint16_t *fh, uint16_t *f, const mlkem_b200_opts *o) {
+    return drive(o, n, 0, {{fh, nullptr, 512}, {nullptr, f, 512}}, [=](cudaStream_t st, Arena &, int cn, void **p) {
+        LAUNCH(k_intt_batch, prim_grid(cn), kPrimTPB, 0, st, cn, (const uint16_t *)p[0], (uint16_t *)p[1]);
+        return 0;
+    });
+}
+int mlkem_b200_multiply_ntts_batch(size_t n, const uint16_t *f, const uint16_t *g, uint16_t *h, const mlkem_b200_opts *o) {
+    return drive(o, n, 0, {{f, nullptr, 512}, {g, nullptr, 512}, {nullptr, h, 512}}, [=](cudaStream_t st, Arena &, int cn, void **p) {
+        LAUNCH(k_mulntt_batch, prim_grid(cn), kPrimTPB, 0, st, cn, (const uint16_t *)p[0], (const uint16_t *)p[1], (uint16_t *)p[2]);
+        return 0;
+    });
+}
+
+int mlkem_b200_sample_ntt_batch(size_t n, const uint8_t *seeds, uint16_t *a, uint8_t *seeds_after, const mlkem_b200_opts *o) {
+    const int gl = group_limit_of(o);
+    std::vector<Buf> bufs = {{seeds, nullptr, 34}, {nullptr, a, 512}};
+    if (seeds_after) bufs.push_back({nullptr, seeds_after, 34});
+    const bool has_after = seeds_after != nullptr;
+    // 34-byte items are not 16-byte multiples: the chunk size must keep chunk starts aligned
+    mlkem_b200_opts oo = o ? *o : mlkem_b200_opts{-1, MLKEM_B200_MEM_HOST, nullptr, 0, 0};
+    if (oo.chunk_items <= 0) oo.chunk_items = 1 << 16;
+    oo.chunk_items = (oo.chunk_items + 7) & ~7;
+    return drive(&oo, n, 0, bufs, [=](cudaStream_t st, Arena &, int cn, void **p) {
+        LAUNCH(k_sample_ntt_batch, cdiv(cn, 128), 128, 128 * kSlotWords * 4, st, cn, (const uint8_t *)p[0], (uint16_t *)p[1],
+               has_after ? (uint8_t *)p[2] : (uint8_t *)nullptr, gl);
+        return 0;
+    });
+}
+
+int mlkem_b200_cbd_batch(int eta, size_t n, const uint8_t *bytes, uint16_t *f, const mlkem_b200_opts *o) {
+    if (eta != 2 && eta != 3) return MLKEM_B200_ERR_ARG;
+    return drive(o, n, 0, {{bytes, nullptr, (size_t)64 * eta}, {nullptr, f, 512}}, [=](cudaStream_t st, Arena &, int cn, void **p) {
+        if (eta == 2) LAUNCH((k_cbd_batch<2>), prim_grid(cn), kPrimTPB, 0, st, cn, (const uint8_t *)p[0], (uint16_t *)p[1]);
+        else LAUNCH((k_cbd_batch<3>), prim_grid(cn), kPrimTPB, 0, st, cn, (const uint8_t *)p[0], (uint16_t *)p[1]);
+        return 0;
+    });
+}
+int mlkem_b200_prf_cbd_batch(int eta, size_t n, const uint8_t *seeds, const uint8_t *nonces, uint16_t *f, const mlkem_b200_opts *o) {
+    if (eta != 2 && eta != 3) return MLKEM_B200_ERR_ARG;
+    mlkem_b200_opts oo = o ? *o : mlkem_b200_opts{-1, MLKEM_B200_MEM_HOST, nullptr, 0, 0};
+    if (oo.chunk_items <= 0) oo.chunk_items = 1 << 16;
+    oo.chunk_items = (oo.chunk_items + 15) & ~15;  // 1-byte nonces: keep chunk starts 16-byte aligned
+    return drive(&oo, n, 0, {{seeds, nullptr, 32}, {nonces, nullptr, 1}, {nullptr, f, 512}}, [=](cudaStream_t st, Arena &, int cn, void **p) {
+        if (eta == 2) LAUNCH((k_prf_cbd_batch<2>), cdiv(cn, kNoiseTPB), kNoiseTPB, 0, st, cn, (const uint8_t *)p[0], (const uint8_t *)p[1], (uint16_t *)p[2]);
+        else LAUNCH((k_prf_cbd_batch<3>), cdiv(cn, kNoiseTPB), kNoiseTPB, 0, st, cn, (const uint8_t *)p[0], (const uint8_t *)p[1], (uint16_t *)p[2]);
+        return 0;
+    });
+}
+
+#define DISPATCH_D(d, CALL)                    \
+    switch (d) {                               \
+    case 1: { constexpr int D = 1; CALL; } break;   \
+    case 4: { constexpr int D = 4; CALL; } break;   \
+    case 5: { constexpr int D = 5; CALL; } break;   \
+    case 10: { constexpr int D = 10; CALL; } break; \
+    case 11: { constexpr int D = 11; CALL; } break; \
+    case 12: { constexpr int D = 12; CALL; } break; \
+    default: return MLKEM_B200_ERR_ARG;        \
+    }
+
+static int encode_impl(int d, size_t n, const uint16_t *F, uint8_t *B, const mlkem_b200_opts *o, bool comp) {
+    return drive(o, n, 0, {{F, nullptr, 512}, {nullptr, B, (size_t)32 * d}}, [=](cudaStream_t st, Arena &, int cn, void **p) {
+        DISPATCH_D(d, {
+            if (comp) LAUNCH((k_encode_batch<D, true>), prim_grid(cn), kPrimTPB, 0, st, cn, (const uint16_t *)p[0], (uint8_t *)p[1]);
+            else LAUNCH((k_encode_batch<D, false>), prim_grid(cn), kPrimTPB, 0, st, cn, (const uint16_t *)p[0], (uint8_t *)p[1]);
+        });
+        return 0;
+    });
+}
+static int decode_impl(int d, size_t n, const uint8_t *B, uint16_t *F, const mlkem_b200_opts *o, bool decomp) {
+    return drive(o, n, 0, {{B, nullptr, (size_t)32 * d}, {nullptr, F, 512}}, [=](cudaStream_t st, Arena &, int cn, void **p) {
+        DISPATCH_D(d, {
+            if (decomp) LAUNCH((k_decode_batch<D, true>), prim_grid(cn), kPrimTPB, 0, st, cn, (const uint8_t *)p[0], (uint16_t *)p[1]);
+            else LAUNCH((k_decode_batch<D, false>), prim_grid(cn), kPrimTPB, 0, st, cn, (const uint8_t *)p[0], (uint16_t *)p[1]);
+        });
+        return 0;
+    });
+}
+int mlkem_b200_byte_encode_batch(int d, size_t n, const uint16_t *F, uint8_t *B, const mlkem_b200_opts *o) { return encode_impl(d, n, F, B, o, false); }
+int mlkem_b200_compress_encode_batch(int d, size_t n, const uint16_t *F, uint8_t *B, const mlkem_b200_opts *o) { return encode_impl(d, n, F, B, o, true); }
+int mlkem_b200_byte_decode_batch(int d, size_t n, const uint8_t *B, uint16_t *F, const mlkem_b200_opts *o) { return decode_impl(d, n, B, F, o, false); }
+int mlkem_b200_decode_decompress_batch(int d, size_t n, const uint8_t *B, uint16_t *F, const mlkem_b200_opts *o) { return decode_impl(d, n, B, F, o, true); }
+
+static int compress_impl(int d, size_t ncoef, const uint16_t *x, uint16_t *y, const mlkem_b200_opts *o, bool decomp) {
+    if (ncoef % 8 != 0) return MLKEM_B200_ERR_ARG;
+    if (d < 1 || d > 12) return MLKEM_B200_ERR_ARG;
+    return drive(o, ncoef / 8, 0, {{x, nullptr, 16}, {nullptr, y, 16}}, [=](cudaStream_t st, Arena &, int cn, void **p) {
+        unsigned grid = cdiv(cn, kPrimTPB);
+        if (grid > 148 * 32) grid = 148 * 32;
+#define CASE_D(DD)                                                                                                                        \
+    case DD:                                                                                                                              \
+        if (decomp) LAUNCH((k_compress_batch<DD, true>), grid, kPrimTPB, 0, st, (long long)cn, (const uint4 *)p[0], (uint4 *)p[1]);        \
+        else LAUNCH((k_compress_batch<DD, false>), grid, kPrimTPB, 0, st, (long long)cn, (const uint4 *)p[0], (uint4 *)p[1]);              \
+        break;
+        switch (d) {
+            CASE_D(1) CASE_D(2) CASE_D(3) CASE_D(4) CASE_D(5) CASE_D(6) CASE_D(7) CASE_D(8) CASE_D(9) CASE_D(10) CASE_D(11) CASE_D(12)
+        }
+#undef CASE_D
+        return 0;
+    });
+}
+int mlkem_b200_compress_batch(int d, size_t ncoef, const uint16_t *x, uint16_t *y, const mlkem_b200_opts *o) { return compress_impl(d, ncoef, x, y, o, false); }
+int mlkem_b200_decompress_batch(int d, size_t ncoef, const uint16_t *y, uint16_t *x, const mlkem_b200_opts *o) { return compress_impl(d, ncoef, y, x, o, true); }
+
+int mlkem_b200_hash_batch(int which, size_t n, size_t len, const uint8_t *in, uint8_t *out, const mlkem_b200_opts *o) {
+    if (len % 8 != 0 || which < 0 || which > 2) return MLKEM_B200_ERR_ARG;
+    if (len % 16 != 0 && !(o && o->mem == MLKEM_B200_MEM_DEVICE)) {
+        // chunk starts stay 16-byte aligned when the chunk size is even
+    }
+    mlkem_b200_opts oo = o ? *o : mlkem_b200_opts{-1, MLKEM_B200_MEM_HOST, nullptr, 0, 0};
+    if (oo.chunk_items <= 0) oo.chunk_items = 1 << 16;
+    oo.chunk_items = (oo.chunk_items + 1) & ~1;
+    const int nw = (int)(len / 8);
+    return drive(&oo, n, 0, {{in, nullptr, len ? len : 1}, {nullptr, out, which == 1 ? (size_t)64 : (size_t)32}}, [=](cudaStream_t st, Arena &, int cn, void **p) {
+        if (which == 0) LAUNCH((k_hash_words<kRateSha3_256, 4>), cdiv(cn, kHashTPB), kHashTPB, 0, st, cn, (const uint8_t *)p[0], nw, kSfxHash, (uint8_t *)p[1]);
+        else if (which == 1) LAUNCH((k_hash_words<kRateSha3_512, 8>), cdiv(cn, kHashTPB), kHashTPB, 0, st, cn, (const uint8_t *)p[0], nw, kSfxHash, (uint8_t *)p[1]);
+        else LAUNCH((k_hash_words<kRateShake128, 4>), cdiv(cn, kHashTPB), kHashTPB, 0, st, cn, (const uint8_t *)p[0], nw, kSfxXof, (uint8_t *)p[1]);
+        return 0;
+    });
+}
+
+int mlkem_b200_tables(uint16_t zeta[128], uint16_t gamma[128]) {
+    int dev;
+    DeviceCtx *ctx;
+    if (int rc = acquire(nullptr, &dev, &ctx)) return rc;
+    TwiddleTables t;
+    CU(cudaMemcpyFromSymbol(&t, c_tw, sizeof t));
+    for (int i = 0; i < 128; i++) {
+        zeta[i] = (uint16_t)t.zeta[i].x;
+        gamma[i] = (uint16_t)t.gamma[i].x;
+    }
+    return 0;
+}
+
+}  // extern "C"
+
+#include "ml_kem_compat.inl"

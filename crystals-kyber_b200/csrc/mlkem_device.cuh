@@ -1,0 +1,411 @@
+// mlkem_device.cuh -- device-side building blocks of the B200 batched ML-KEM engine (sm_100a).
+//
+// Everything here is integer work on the 32-bit ALU/FMA pipes; there is no dense contraction on this
+// path, so no tensor cores.  Three families of routines:
+//
+//   1. field arithmetic mod q = 3329 (Shoup multiplication by constants, Barrett for products),
+//   2. Keccak-f[1600] with one sponge per THREAD (25 lanes as 50 x 32-bit registers, funnel-shift
+//      rotates), plus absorb/squeeze helpers for SHA3-256 / SHA3-512 / SHAKE128,
+//   3. polynomial routines with one polynomial per WARP: NTT / inverse NTT (8 coefficients per lane,
+//      register butterflies + one shared-memory transpose + one shuffle layer), NTT-domain
+//      multiply-accumulate, Compress/Decompress and ByteEncode/ByteDecode.
+//
+// Bit-exactness contract: results equal the reference rsjahnige/CRYSTALS-Kyber `ml_kem.c`
+// (see SURVEY.md section 0 for where it differs from FIPS 203).  File:line citations below refer to
+// /root/reference/ml_kem.c unless stated otherwise.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace mlkem {
+
+constexpr int kN = 256;
+constexpr uint32_t kQ = 3329;
+constexpr uint32_t kFullMask = 0xFFFFFFFFu;
+
+// ------------------------------------------------------------------------------------------------
+// Constant tables (filled once per device by the host, see mlkem_tables.cu)
+// ------------------------------------------------------------------------------------------------
+// zeta_i = 17^BitRev7(i) mod q (ml_kem.c:300-307) as {w, floor(w * 2^16 / q)} for Shoup multiplication.
+// gamma_i = 17^(2 BitRev7(i) + 1) mod q (ml_kem.c:424-433), same packing.
+// The inverse transform walks the same table downwards (ml_kem.c:345-357: i = 127 .. 1); its last layer
+// is pre-multiplied by 3303 = 128^-1 (ml_kem.c:378-381).
+struct TwiddleTables {
+    uint2 zeta[128];
+    uint2 zeta_inv_last[2];  // {zeta[1] * 3303 mod q, 3303}
+    uint2 gamma[128];
+};
+// The library is a single translation unit (mlkem_b200.cu), so the tables are defined right here.
+__constant__ TwiddleTables c_tw;
+__constant__ uint2 c_keccak_rc[24];
+
+// ------------------------------------------------------------------------------------------------
+// 1. Field arithmetic
+// ------------------------------------------------------------------------------------------------
+
+// a * w mod q for a < 2^16 and a constant w given as {w, floor(w 2^16 / q)}; result in [0, 2q).
+__device__ __forceinline__ uint32_t mul_shoup(uint32_t a, uint2 w) {
+    uint32_t qh = (a * w.y) >> 16;
+    return a * w.x - qh * kQ;
+}
+// x mod q for x < 2^16, result in [0, q].
+__device__ __forceinline__ uint32_t barrett16(uint32_t x) {
+    uint32_t qh = (x * 40317u) >> 27;  // floor(2^27 / q) = 40317
+    return x - qh * kQ;
+}
+// x mod q for any x < 2^32, result in [0, 2q).
+__device__ __forceinline__ uint32_t barrett32(uint32_t x) {
+    uint32_t qh = __umulhi(x, 1290167u);  // floor(2^32 / q)
+    return x - qh * kQ;
+}
+// r in [0, 2q) -> [0, q)
+__device__ __forceinline__ uint32_t csubq(uint32_t r) { return min(r, r - kQ); }
+// canonical value of any x < 2^16
+__device__ __forceinline__ uint32_t canon16(uint32_t x) { return csubq(barrett16(x)); }
+// canonical value of any x < 2^32
+__device__ __forceinline__ uint32_t canon32(uint32_t x) { return csubq(barrett32(x)); }
+
+// ml_kem.c:83 Compress_d for canonical x: floor((2^d x + 1664) / q) mod 2^d  (closed form
+// verified exhaustively against the reference's quotient/remainder formulation).
+template <int D>
+__device__ __forceinline__ uint32_t compress(uint32_t x) {
+    if (D >= 12) return x;
+    uint32_t t = (x << D) + 1664u;  // < 2^23
+    uint32_t qh = __umulhi(t, 1290167u);
+    uint32_t r = t - qh * kQ;  // [0, 2q)
+    qh += (r >= kQ);
+    return qh & ((1u << D) - 1u);
+}
+// ml_kem.c:104 Decompress_d: (q y + 2^(d-1)) >> d.
+template <int D>
+__device__ __forceinline__ uint32_t decompress(uint32_t y) {
+    if (D >= 12) return y;
+    return (kQ * y + (1u << (D - 1))) >> D;
+}
+
+// ------------------------------------------------------------------------------------------------
+// 2. Keccak-f[1600], one sponge per thread
+// ------------------------------------------------------------------------------------------------
+// A lane is kept as two 32-bit halves so that rotates are single funnel shifts (SHF.L.W) and the
+// theta / chi steps are single three-input LOP3s: 122 LOP3 + 58 SHF = 180 instructions per round,
+// all on the alu pipe (profiles/: 99 % of the measured LOP3/SHF issue rate).
+struct Lane {
+    uint32_t lo, hi;
+};
+
+template <int R>
+__device__ __forceinline__ Lane rotl64(Lane x) {
+    Lane r = x;
+    if constexpr (R == 32) {
+        r.lo = x.hi;
+        r.hi = x.lo;
+    } else if constexpr (R > 0 && R < 32) {
+        r.hi = __funnelshift_l(x.lo, x.hi, R);
+        r.lo = __funnelshift_l(x.hi, x.lo, R);
+    } else if constexpr (R > 32) {
+        r.hi = __funnelshift_l(x.hi, x.lo, R - 32);
+        r.lo = __funnelshift_l(x.lo, x.hi, R - 32);
+    }
+    return r;
+}
+__device__ __forceinline__ Lane xor3(Lane a, Lane b, Lane c) { return Lane{a.lo ^ b.lo ^ c.lo, a.hi ^ b.hi ^ c.hi}; }
+__device__ __forceinline__ Lane xor5(Lane a, Lane b, Lane c, Lane d, Lane e) {
+    return Lane{a.lo ^ b.lo ^ c.lo ^ d.lo ^ e.lo, a.hi ^ b.hi ^ c.hi ^ d.hi ^ e.hi};
+}
+__device__ __forceinline__ Lane chi3(Lane a, Lane b, Lane c) { return Lane{a.lo ^ (~b.lo & c.lo), a.hi ^ (~b.hi & c.hi)}; }
+
+// sha3.c:207 Keccak_f = 24 x Iota(Chi(Pi(Rho(Theta(S))))) (sha3.c:15,53,88,116,182).
+// Kept as a rolled loop: 180 instructions per round fit the instruction cache even with several inlined
+// call sites, and ptxas renames registers across the back edge without moves.
+__device__ __forceinline__ void keccak_f1600(Lane a[25]) {
+#pragma unroll 1
+    for (int rnd = 0; rnd < 24; rnd++) {
+        Lane c0 = xor5(a[0], a[5], a[10], a[15], a[20]), c1 = xor5(a[1], a[6], a[11], a[16], a[21]),
+             c2 = xor5(a[2], a[7], a[12], a[17], a[22]), c3 = xor5(a[3], a[8], a[13], a[18], a[23]),
+             c4 = xor5(a[4], a[9], a[14], a[19], a[24]);
+        Lane r0 = rotl64<1>(c0), r1 = rotl64<1>(c1), r2 = rotl64<1>(c2), r3 = rotl64<1>(c3), r4 = rotl64<1>(c4);
+#define MLKEM_TH(x, cm, rp)             \
+    a[x] = xor3(a[x], cm, rp);          \
+    a[x + 5] = xor3(a[x + 5], cm, rp);  \
+    a[x + 10] = xor3(a[x + 10], cm, rp); \
+    a[x + 15] = xor3(a[x + 15], cm, rp); \
+    a[x + 20] = xor3(a[x + 20], cm, rp);
+        MLKEM_TH(0, c4, r1) MLKEM_TH(1, c0, r2) MLKEM_TH(2, c1, r3) MLKEM_TH(3, c2, r4) MLKEM_TH(4, c3, r0)
+#undef MLKEM_TH
+        Lane b[25];
+        b[0] = a[0];             b[10] = rotl64<1>(a[1]);   b[20] = rotl64<62>(a[2]);  b[5] = rotl64<28>(a[3]);   b[15] = rotl64<27>(a[4]);
+        b[16] = rotl64<36>(a[5]); b[1] = rotl64<44>(a[6]);   b[11] = rotl64<6>(a[7]);   b[21] = rotl64<55>(a[8]);  b[6] = rotl64<20>(a[9]);
+        b[7] = rotl64<3>(a[10]);  b[17] = rotl64<10>(a[11]); b[2] = rotl64<43>(a[12]);  b[12] = rotl64<25>(a[13]); b[22] = rotl64<39>(a[14]);
+        b[23] = rotl64<41>(a[15]); b[8] = rotl64<45>(a[16]); b[18] = rotl64<15>(a[17]); b[3] = rotl64<21>(a[18]);  b[13] = rotl64<8>(a[19]);
+        b[14] = rotl64<18>(a[20]); b[24] = rotl64<2>(a[21]); b[9] = rotl64<61>(a[22]);  b[19] = rotl64<56>(a[23]); b[4] = rotl64<14>(a[24]);
+#pragma unroll
+        for (int y = 0; y < 25; y += 5) {
+#pragma unroll
+            for (int x = 0; x < 5; x++) a[y + x] = chi3(b[y + x], b[y + (x + 1) % 5], b[y + (x + 2) % 5]);
+        }
+        uint2 rc = c_keccak_rc[rnd];
+        a[0].lo ^= rc.x;
+        a[0].hi ^= rc.y;
+    }
+}
+
+__device__ __forceinline__ void keccak_zero(Lane a[25]) {
+#pragma unroll
+    for (int i = 0; i < 25; i++) a[i] = Lane{0u, 0u};
+}
+
+// Domain-suffix bytes (suffix bits followed by the first pad bit, sha3.c:408-431 + sha3.c:226):
+constexpr uint32_t kSfxHash = 0x06;  // sfx {0,1}      SHA3-256 / SHA3-512
+constexpr uint32_t kSfxXof = 0x1F;   // sfx {1,1,1,1}  SHAKE
+constexpr int kRateShake128 = 21;    // lanes: c = 256  (PRF, J and the matrix XOF -- D1, D2)
+constexpr int kRateSha3_256 = 17;    // lanes: c = 512  (H)
+constexpr int kRateSha3_512 = 9;     // lanes: c = 1024 (G)
+
+// Absorb a message given as 64-bit little-endian words (all ML-KEM hash inputs except G(d||k) are
+// multiples of 8 bytes) and apply pad10*1 (sha3.c:226,257-291).  `word(i)` returns message word i as a
+// Lane; `nwords` is uniform across the warp.  Leaves the state after the last absorbing permutation,
+// i.e. ready to read the first output block.
+template <int RATE, typename F>
+__device__ __forceinline__ void sponge_absorb_words(Lane a[25], int nwords, uint32_t sfx, F word) {
+    keccak_zero(a);
+    int base = 0;
+    for (; base + RATE <= nwords; base += RATE) {
+#pragma unroll
+        for (int i = 0; i < RATE; i++) {
+            Lane w = word(base + i);
+            a[i].lo ^= w.lo;
+            a[i].hi ^= w.hi;
+        }
+        keccak_f1600(a);
+    }
+    int rem = nwords - base;  // 0 .. RATE-1 words in the final block
+#pragma unroll
+    for (int i = 0; i < RATE; i++) {
+        if (i < rem) {
+            Lane w = word(base + i);
+            a[i].lo ^= w.lo;
+            a[i].hi ^= w.hi;
+        } else if (i == rem) {
+            a[i].lo ^= sfx;
+        }
+    }
+    a[RATE - 1].hi ^= 0x80000000u;
+    keccak_f1600(a);
+}
+
+__device__ __forceinline__ Lane load_lane(const uint8_t *p) {  // p must be 8-byte aligned
+    uint2 v = *reinterpret_cast<const uint2 *>(p);
+    return Lane{v.x, v.y};
+}
+__device__ __forceinline__ void store_lane(uint8_t *p, Lane v) { *reinterpret_cast<uint2 *>(p) = make_uint2(v.lo, v.hi); }
+
+// ------------------------------------------------------------------------------------------------
+// 3. Polynomials, one per warp
+// ------------------------------------------------------------------------------------------------
+// Register layouts for the 256 coefficients of one polynomial held by a warp, 8 per lane:
+//   layout A: x[r] = f[lane + 32 r]                               (index bits: r = b7 b6 b5, lane = b4..b0)
+//   layout B: x[r] = f[32 (lane >> 2) + 4 r + (lane & 3)]         (r = b4 b3 b2, lane = b7 b6 b5 b1 b0)
+// The forward transform consumes A (layers len = 128, 64, 32 are register-local), transposes to B through
+// the warp's shared-memory scratch (layers 16, 8, 4 local) and finishes len = 2 with one shuffle layer.
+// The inverse transform runs the same steps backwards: B in, A out.
+//
+// Scratch polynomials in shared memory use a padded index so that both layouts are bank-conflict free:
+//   coefficient c lives at uint16 index c + 2 (c >> 5)  (one 32-bit pad word per 32 coefficients).
+constexpr int kScratchU16 = 272;  // 256 + 16 pad
+__device__ __forceinline__ int pidx(int c) { return c + ((c >> 5) << 1); }
+__device__ __forceinline__ int idxA(int lane, int r) { return lane + 32 * r; }
+__device__ __forceinline__ int idxB(int lane, int r) { return ((lane >> 2) << 5) | (r << 2) | (lane & 3); }
+
+// Per-lane twiddles for the layers whose zeta depends on the lane (layout B + the shuffle layer).
+struct LaneTwiddles {
+    uint2 z16;     // len 16: zeta[8 + (lane>>2)]
+    uint2 z8[2];   // len 8 : zeta[16 + 2 (lane>>2) + (r>>2)]
+    uint2 z4[4];   // len 4 : zeta[32 + 4 (lane>>2) + (r>>1)]
+    uint2 z2[8];   // len 2 : zeta[64 + 8 (lane>>2) + r]
+};
+__device__ __forceinline__ void load_lane_twiddles(LaneTwiddles &t, int lane) {
+    int g = lane >> 2;
+    t.z16 = c_tw.zeta[8 + g];
+#pragma unroll
+    for (int i = 0; i < 2; i++) t.z8[i] = c_tw.zeta[16 + 2 * g + i];
+#pragma unroll
+    for (int i = 0; i < 4; i++) t.z4[i] = c_tw.zeta[32 + 4 * g + i];
+#pragma unroll
+    for (int i = 0; i < 8; i++) t.z2[i] = c_tw.zeta[64 + 8 * g + i];
+}
+
+// Inverse transform: block `blk` of the layer with n blocks uses zeta[2n - 1 - blk] (i counts down from 127).
+__device__ __forceinline__ void load_lane_twiddles_inv(LaneTwiddles &t, int lane) {
+    int g = lane >> 2;
+    t.z16 = c_tw.zeta[15 - g];
+#pragma unroll
+    for (int i = 0; i < 2; i++) t.z8[i] = c_tw.zeta[31 - (2 * g + i)];
+#pragma unroll
+    for (int i = 0; i < 4; i++) t.z4[i] = c_tw.zeta[63 - (4 * g + i)];
+#pragma unroll
+    for (int i = 0; i < 8; i++) t.z2[i] = c_tw.zeta[127 - (8 * g + i)];
+}
+
+// Cooley-Tukey butterfly, lazy: inputs < 2^16 - 2q, outputs grow by at most 2q.
+__device__ __forceinline__ void ct_bfly(uint32_t &a, uint32_t &b, uint2 z) {
+    uint32_t t = mul_shoup(b, z);
+    b = a - t + 2 * kQ;
+    a = a + t;
+}
+
+// ml_kem.c:287 NTT.  x in layout A, canonical (< q; any value < 4096 also works and gives the same
+// residues).  Returns the transform in layout B, canonical.  `scratch` = this warp's padded scratch.
+__device__ __forceinline__ void ntt_warp(uint32_t x[8], uint16_t *scratch, int lane, const LaneTwiddles &tw) {
+    // len = 128, 64, 32: register index bits 2, 1, 0
+#pragma unroll
+    for (int r = 0; r < 4; r++) ct_bfly(x[r], x[r + 4], c_tw.zeta[1]);
+#pragma unroll
+    for (int h = 0; h < 2; h++)
+#pragma unroll
+        for (int r = 0; r < 2; r++) ct_bfly(x[4 * h + r], x[4 * h + r + 2], c_tw.zeta[2 + h]);
+#pragma unroll
+    for (int h = 0; h < 4; h++) ct_bfly(x[2 * h], x[2 * h + 1], c_tw.zeta[4 + h]);
+    // transpose A -> B (values < q + 6q < 2^16 fit uint16)
+#pragma unroll
+    for (int r = 0; r < 8; r++) scratch[pidx(idxA(lane, r))] = (uint16_t)x[r];
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < 8; r++) x[r] = scratch[pidx(idxB(lane, r))];
+    __syncwarp();
+    // len = 16, 8, 4: register index bits 2, 1, 0 of layout B
+#pragma unroll
+    for (int r = 0; r < 4; r++) ct_bfly(x[r], x[r + 4], tw.z16);
+#pragma unroll
+    for (int h = 0; h < 2; h++)
+#pragma unroll
+        for (int r = 0; r < 2; r++) ct_bfly(x[4 * h + r], x[4 * h + r + 2], tw.z8[h]);
+#pragma unroll
+    for (int h = 0; h < 4; h++) ct_bfly(x[2 * h], x[2 * h + 1], tw.z4[h]);
+    // len = 2: partner lane differs in index bit b1 = lane bit 1.  The upper lane multiplies its own
+    // value, the lower lane sends its value; one shuffle per coefficient.
+    const bool up = lane & 2;
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        uint32_t t = mul_shoup(x[r], tw.z2[r]);          // only meaningful on the upper lane
+        uint32_t send = up ? t : x[r];
+        uint32_t got = __shfl_xor_sync(kFullMask, send, 2);
+        uint32_t v = up ? (got - t + 2 * kQ) : (x[r] + got);  // up: a - zeta b ; low: a + zeta b
+        x[r] = canon16(v);
+    }
+}
+
+// Gentleman-Sande butterfly for the inverse transform (ml_kem.c:359-373): a' = a + b, b' = zeta (b - a).
+// `bias` is a multiple of q not smaller than the bound of a.
+__device__ __forceinline__ void gs_bfly(uint32_t &a, uint32_t &b, uint2 z, uint32_t bias) {
+    uint32_t t = a;
+    a = t + b;
+    b = mul_shoup(b - t + bias, z);
+}
+
+// ml_kem.c:336 InverseNTT including the final multiplication by 3303 (:378-381).
+// x in layout B, values < q (or any 12-bit value).  Returns layout A, canonical.  `tw` must come from
+// load_lane_twiddles_inv.
+__device__ __forceinline__ void intt_warp(uint32_t x[8], uint16_t *scratch, int lane, const LaneTwiddles &tw) {
+    // len = 2
+    const bool up = lane & 2;
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        uint32_t got = __shfl_xor_sync(kFullMask, x[r], 2);
+        // low lane: a + b ; upper lane: zeta (b - a) with a = got, b = own.  Inputs < 4096 -> bias 2q.
+        uint32_t d = mul_shoup(x[r] - got + 2 * kQ, tw.z2[r]);
+        x[r] = up ? d : (x[r] + got);  // bounds: low < 8192, up < 2q
+    }
+    // len = 4, 8, 16 (layout B register bits 0, 1, 2).  All values are < 8192 here.
+    // len 4: a' < 16384; the bias must be a multiple of q that is >= the bound of a: 3q = 9987
+#pragma unroll
+    for (int h = 0; h < 4; h++) gs_bfly(x[2 * h], x[2 * h + 1], tw.z4[h], 3 * kQ);
+    // after len 4: a < 16384, b < 2q.  reduce a to keep the sums below 2^16 later on
+#pragma unroll
+    for (int h = 0; h < 4; h++) x[2 * h] = barrett16(x[2 * h]);  // <= q
+    // len 8: inputs < 2q (6658): a' < 4q ; bias 2q
+#pragma unroll
+    for (int h = 0; h < 2; h++)
+#pragma unroll
+        for (int r = 0; r < 2; r++) gs_bfly(x[4 * h + r], x[4 * h + r + 2], tw.z8[h], 2 * kQ);
+    // len 16: inputs < 4q: a' < 8q ; bias 4q
+#pragma unroll
+    for (int r = 0; r < 4; r++) gs_bfly(x[r], x[r + 4], tw.z16, 4 * kQ);
+    // values < 8q = 26632 < 2^16: transpose B -> A
+#pragma unroll
+    for (int r = 0; r < 8; r++) scratch[pidx(idxB(lane, r))] = (uint16_t)x[r];
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < 8; r++) x[r] = scratch[pidx(idxA(lane, r))];
+    __syncwarp();
+    // len = 32: inputs < 8q: a' < 16q = 53264 < 2^16, bias 8q ; then reduce the sums
+#pragma unroll
+    for (int h = 0; h < 4; h++) {
+        gs_bfly(x[2 * h], x[2 * h + 1], c_tw.zeta[7 - h], 8 * kQ);
+        x[2 * h] = barrett16(x[2 * h]);  // <= q
+    }
+    // len = 64: inputs < 2q: a' < 4q, bias 2q
+#pragma unroll
+    for (int h = 0; h < 2; h++)
+#pragma unroll
+        for (int r = 0; r < 2; r++) gs_bfly(x[4 * h + r], x[4 * h + r + 2], c_tw.zeta[3 - h], 2 * kQ);
+    // len = 128 with the 128^-1 scaling folded in: a' = 3303 (a + b), b' = 3303 zeta (b - a); inputs < 4q
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        uint32_t t = x[r];
+        x[r] = csubq(mul_shoup(t + x[r + 4], c_tw.zeta_inv_last[1]));
+        x[r + 4] = csubq(mul_shoup(x[r + 4] - t + 4 * kQ, c_tw.zeta_inv_last[0]));
+    }
+}
+
+// ml_kem.c:395 BaseCaseMultiply + :415 MultiplyNTTs + :618 VectorMultiply, accumulated lazily.
+// (a0 + a1 X)(b0 + b1 X) mod (X^2 - gamma) added into (acc0, acc1); operands may be any 12-bit value
+// (D4: ByteDecode12 does not reduce), each term is < 3 * 4096^2 so four terms fit 32 bits.
+__device__ __forceinline__ void basemul_acc(uint32_t &acc0, uint32_t &acc1, uint32_t a0, uint32_t a1, uint32_t b0,
+                                            uint32_t b1, uint2 gamma) {
+    uint32_t a1g = mul_shoup(a1, gamma);  // < 2q
+    acc0 += a0 * b0 + a1g * b1;
+    acc1 += a0 * b1 + a1 * b0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Bit packing.  ByteEncode_d / ByteDecode_d (ml_kem.c:125,153) are little-endian bit strings:
+// coefficient i occupies bits [d i, d i + d).  A lane that owns 8 consecutive coefficients therefore
+// owns exactly d consecutive bytes.
+// ------------------------------------------------------------------------------------------------
+// Pack 8 d-bit values into d bytes at `dst` (shared memory, byte granular).
+template <int D>
+__device__ __forceinline__ void pack8(const uint32_t v[8], uint8_t *dst) {
+    uint64_t lo = 0;  // bits 0..63
+    uint32_t hi = 0;  // bits 64..95
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const int off = D * i;
+        if (off < 64) {
+            lo |= (uint64_t)v[i] << off;
+            if (off + D > 64) hi |= v[i] >> (64 - off);
+        } else {
+            hi |= v[i] << (off - 64);
+        }
+    }
+#pragma unroll
+    for (int b = 0; b < D; b++) dst[b] = (uint8_t)(b < 8 ? (lo >> (8 * b)) : (hi >> (8 * (b - 8))));
+}
+// Extract the d-bit value of coefficient c from a little-endian packed byte string (shared or global).
+template <int D>
+__device__ __forceinline__ uint32_t unpack1(const uint8_t *src, int c) {
+    if (D == 1) return (src[c >> 3] >> (c & 7)) & 1u;
+    if (D == 4) return (src[c >> 1] >> ((c & 1) * 4)) & 15u;
+    const int bit = D * c, byte = bit >> 3, sh = bit & 7;
+    uint32_t w = (uint32_t)src[byte];
+    if (sh + D > 8) w |= (uint32_t)src[byte + 1] << 8;  // never reads past the last byte of the string
+    if (D > 9 && sh + D > 16) w |= (uint32_t)src[byte + 2] << 16;
+    return (w >> sh) & ((1u << D) - 1u);
+}
+
+// Noise polynomials travel between kernels as 4-bit codes (coefficient + 3), 8 per 32-bit word.
+__device__ __forceinline__ uint32_t noise_code_to_coeff(uint32_t code) {  // code in 0..6 -> canonical
+    int32_t c = (int32_t)code - 3;
+    return (uint32_t)(c + ((c >> 31) & (int32_t)kQ));
+}
+
+}  // namespace mlkem

@@ -1,0 +1,953 @@
+// mlkem_kernels.cuh -- the CUDA kernels of the batched ML-KEM engine (sm_100a).
+//
+// Work decomposition (DESIGN.md has the full picture):
+//   * every Keccak sponge is run by ONE THREAD (state in registers); a warp therefore runs 32 sponges of
+//     the same kind in lock step.  Kernels are split by sponge kind so warps never mix roles.
+//   * every polynomial operation (NTT, inverse NTT, multiply-accumulate, compress, pack) is run by ONE
+//     WARP per polynomial, 8 coefficients per lane.
+//   * the matrix expansion is fused with its consumer: k_sample_matvec samples the k entries of one matrix
+//     row with k threads straight into shared memory and the owning warp immediately multiplies them with
+//     the vector, accumulates, (inverse-)transforms, adds the noise, compresses and packs -- the matrix
+//     never exists in HBM.
+//
+// All byte buffers are dense and item-major (item i of an array with per-item size S starts at i*S);
+// every per-item size on this path is a multiple of 16 bytes, so with 16-byte aligned bases every item,
+// row and hash input is 8-byte aligned.
+#pragma once
+#include "mlkem_device.cuh"
+
+namespace mlkem {
+
+template <int K_, int ETA1_, int ETA2_, int DU_, int DV_>
+struct ParamSet {  // ml_kem.c:1363 init()
+    static constexpr int K = K_, ETA1 = ETA1_, ETA2 = ETA2_, DU = DU_, DV = DV_;
+    static constexpr int EK = 384 * K + 32;            // encapsulation key bytes (ml_kem.c:730)
+    static constexpr int DKPKE = 384 * K;              // K-PKE decryption key bytes (ml_kem.c:731)
+    static constexpr int DK = 768 * K + 96;            // decapsulation key bytes (ml_kem.c:1050)
+    static constexpr int C1ROW = 32 * DU;              // bytes of one compressed u row
+    static constexpr int C2 = 32 * DV;                 // bytes of compressed v
+    static constexpr int C = C1ROW * K + C2;           // ciphertext bytes (ml_kem.c:1105)
+};
+using P512 = ParamSet<2, 3, 2, 10, 4>;
+using P768 = ParamSet<3, 2, 2, 10, 4>;
+using P1024 = ParamSet<4, 2, 2, 11, 5>;
+
+constexpr int kHashTPB = 128;   // threads per block of the thread-per-item hash kernels
+constexpr int kNoiseTPB = 128;  // threads (= sponges) per block of k_noise
+constexpr int kSlotWords = 137; // shared-memory words per sampled polynomial slot (odd: conflict-free per-thread writes)
+
+// =================================================================================================
+// Hash kernels: one item per thread
+// =================================================================================================
+
+// (rho, sigma) = G(d || k)   (ml_kem.c:674-681).  33-byte message, SHA3-512: one permutation.
+__global__ void __launch_bounds__(kHashTPB) k_keygen_G(int n, const uint8_t *__restrict__ d, uint32_t kbyte,
+                                                       uint8_t *__restrict__ rs) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Lane a[25];
+    keccak_zero(a);
+#pragma unroll
+    for (int w = 0; w < 4; w++) a[w] = load_lane(d + 32 * (size_t)i + 8 * w);
+    a[4].lo = kbyte | (kSfxHash << 8);
+    a[kRateSha3_512 - 1].hi ^= 0x80000000u;
+    keccak_f1600(a);
+#pragma unroll
+    for (int w = 0; w < 8; w++) store_lane(rs + 64 * (size_t)i + 8 * w, a[w]);
+}
+
+// SHA3-256 over `P::EK` bytes at `ek`; result in h[0..3].
+template <class P>
+__device__ __forceinline__ void hash_H_ek(const uint8_t *ek, Lane h[4]) {
+    Lane a[25];
+    sponge_absorb_words<kRateSha3_256>(a, P::EK / 8, kSfxHash, [&](int w) { return load_lane(ek + 8 * w); });
+#pragma unroll
+    for (int w = 0; w < 4; w++) h[w] = a[w];
+}
+
+// SHA3-512 over the 64-byte message x || y; output lanes 0..7 left in a[].
+__device__ __forceinline__ void hash_G_64(Lane a[25], const Lane x[4], const Lane y[4]) {
+    keccak_zero(a);
+#pragma unroll
+    for (int w = 0; w < 4; w++) {
+        a[w] = x[w];
+        a[4 + w] = y[w];
+    }
+    a[8].lo = kSfxHash;
+    a[8].hi = 0x80000000u;
+    keccak_f1600(a);
+}
+
+// KeyGen tail (ml_kem.c:1064-1077): dk[768k+32 .. +32) = H(ek), dk[768k+64 .. +32) = z.
+template <class P>
+__global__ void __launch_bounds__(kHashTPB) k_keygen_H(int n, const uint8_t *__restrict__ ek, const uint8_t *__restrict__ z,
+                                                       uint8_t *__restrict__ dk) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Lane h[4];
+    hash_H_ek<P>(ek + (size_t)P::EK * i, h);
+    uint8_t *tail = dk + (size_t)P::DK * i + 768 * P::K + 32;
+#pragma unroll
+    for (int w = 0; w < 4; w++) {
+        store_lane(tail + 8 * w, h[w]);
+        store_lane(tail + 32 + 8 * w, load_lane(z + 32 * (size_t)i + 8 * w));
+    }
+}
+
+// Encaps front (ml_kem.c:1108-1124): h = H(ek); (K, r) = G(m || h).
+template <class P>
+__global__ void __launch_bounds__(kHashTPB) k_encaps_HG(int n, const uint8_t *__restrict__ ek, const uint8_t *__restrict__ m,
+                                                        uint8_t *__restrict__ Kout, uint8_t *__restrict__ r) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Lane h[4], mm[4], a[25];
+    hash_H_ek<P>(ek + (size_t)P::EK * i, h);
+#pragma unroll
+    for (int w = 0; w < 4; w++) mm[w] = load_lane(m + 32 * (size_t)i + 8 * w);
+    hash_G_64(a, mm, h);
+#pragma unroll
+    for (int w = 0; w < 4; w++) {
+        store_lane(Kout + 32 * (size_t)i + 8 * w, a[w]);
+        store_lane(r + 32 * (size_t)i + 8 * w, a[4 + w]);
+    }
+}
+
+// Plain H over ek (used by the public-wrapper hash check, ml_kem.c:1336-1350): status[i] = -5 on mismatch.
+template <class P>
+__global__ void __launch_bounds__(kHashTPB) k_check_dk_hash(int n, const uint8_t *__restrict__ dk, int *__restrict__ status) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint8_t *base = dk + (size_t)P::DK * i;
+    Lane h[4];
+    hash_H_ek<P>(base + 384 * P::K, h);
+    uint32_t diff = 0;
+#pragma unroll
+    for (int w = 0; w < 4; w++) {
+        Lane s = load_lane(base + 768 * P::K + 32 + 8 * w);
+        diff |= (s.lo ^ h[w].lo) | (s.hi ^ h[w].hi);
+    }
+    status[i] = diff ? -5 : 0;
+}
+
+// Decaps (ml_kem.c:1181-1193): (K', r') = G(m' || h), h = dk[768k+32 .. +32).
+template <class P>
+__global__ void __launch_bounds__(kHashTPB) k_decaps_G(int n, const uint8_t *__restrict__ mprime, const uint8_t *__restrict__ dk,
+                                                       uint8_t *__restrict__ Kr) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Lane h[4], mm[4], a[25];
+    const uint8_t *hp = dk + (size_t)P::DK * i + 768 * P::K + 32;
+#pragma unroll
+    for (int w = 0; w < 4; w++) {
+        mm[w] = load_lane(mprime + 32 * (size_t)i + 8 * w);
+        h[w] = load_lane(hp + 8 * w);
+    }
+    hash_G_64(a, mm, h);
+#pragma unroll
+    for (int w = 0; w < 8; w++) store_lane(Kr + 64 * (size_t)i + 8 * w, a[w]);
+}
+
+// Decaps tail (ml_kem.c:1196-1215): Kbar = J(z || c) -- SHAKE128 in the reference (D2) -- then a
+// branch-free select between K' and Kbar on the re-encryption mismatch flag.  The reference's compare is
+// an early-exit loop; the selected key is the same.
+template <class P>
+__global__ void __launch_bounds__(kHashTPB) k_decaps_J_select(int n, const uint8_t *__restrict__ dk, const uint8_t *__restrict__ c,
+                                                              const uint8_t *__restrict__ Kr, const uint32_t *__restrict__ flags,
+                                                              uint8_t *__restrict__ Kout) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint8_t *z = dk + (size_t)P::DK * i + 768 * P::K + 64;
+    const uint8_t *ci = c + (size_t)P::C * i;
+    Lane a[25];
+    sponge_absorb_words<kRateShake128>(a, 4 + P::C / 8, kSfxXof,
+                                       [&](int w) { return w < 4 ? load_lane(z + 8 * w) : load_lane(ci + 8 * (w - 4)); });
+    uint32_t mask = flags[i] ? 0xFFFFFFFFu : 0u;
+#pragma unroll
+    for (int w = 0; w < 4; w++) {
+        Lane kp = load_lane(Kr + 64 * (size_t)i + 8 * w);
+        Lane o{(a[w].lo & mask) | (kp.lo & ~mask), (a[w].hi & mask) | (kp.hi & ~mask)};
+        store_lane(Kout + 32 * (size_t)i + 8 * w, o);
+    }
+}
+
+// Generic batched hash (H / G / J) over equal-length messages, length a multiple of 8 bytes.
+// which: 0 = H (SHA3-256, 32 B out), 1 = G (SHA3-512, 64 B out), 2 = J (SHAKE128, 32 B out).
+template <int RATE, int OUTW>
+__global__ void __launch_bounds__(kHashTPB) k_hash_words(int n, const uint8_t *__restrict__ in, int nwords, uint32_t sfx,
+                                                         uint8_t *__restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint8_t *p = in + (size_t)nwords * 8 * i;
+    Lane a[25];
+    sponge_absorb_words<RATE>(a, nwords, sfx, [&](int w) { return load_lane(p + 8 * w); });
+#pragma unroll
+    for (int w = 0; w < OUTW; w++) store_lane(out + (size_t)OUTW * 8 * i + 8 * w, a[w]);
+}
+
+// =================================================================================================
+// Noise: PRF_eta(seed, nonce) = SHAKE128(seed || nonce) (D1) -> SamplePolyCBD_eta -> [NTT]
+// =================================================================================================
+
+// ml_kem.c:253 SamplePolyCBD on one 32-bit word of PRF output for eta = 2: 8 coefficients, returned as
+// 4-bit codes (coefficient + 3).
+__device__ __forceinline__ uint32_t cbd2_word(uint32_t w) {
+    uint32_t t = (w & 0x55555555u) + ((w >> 1) & 0x55555555u);
+    uint32_t x = t & 0x33333333u, y = (t >> 2) & 0x33333333u;
+    return x + (0x33333333u - y);
+}
+// eta = 3: 96 bits (w0,w1,w2) -> 16 coefficients -> two words of 4-bit codes.
+__device__ __forceinline__ uint32_t cbd3_chunk(uint32_t c24) {  // 4 coefficients -> 4 codes in the low 16 bits
+    uint32_t t = (c24 & 0x249249u) + ((c24 >> 1) & 0x249249u) + ((c24 >> 2) & 0x249249u);
+    uint32_t out = 0;
+#pragma unroll
+    for (int m = 0; m < 4; m++) {
+        uint32_t x = (t >> (6 * m)) & 7u, y = (t >> (6 * m + 3)) & 7u;
+        out |= (x + 3u - y) << (4 * m);
+    }
+    return out;
+}
+__device__ __forceinline__ void cbd3_words(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t &o0, uint32_t &o1) {
+    uint32_t c0 = w0 & 0xFFFFFFu, c1 = (w0 >> 24) | ((w1 & 0xFFFFu) << 8), c2 = (w1 >> 16) | ((w2 & 0xFFu) << 16), c3 = w2 >> 8;
+    o0 = cbd3_chunk(c0) | (cbd3_chunk(c1) << 16);
+    o1 = cbd3_chunk(c2) | (cbd3_chunk(c3) << 16);
+}
+
+// PRF + CBD for one (seed, nonce): 32 words of 4-bit codes written through `put(word_index, value)`.
+template <int ETA, typename PUT>
+__device__ __forceinline__ void prf_cbd_codes(const Lane seed[4], uint32_t nonce, PUT put) {
+    Lane a[25];
+    keccak_zero(a);
+#pragma unroll
+    for (int w = 0; w < 4; w++) a[w] = seed[w];
+    a[4].lo = nonce | (kSfxXof << 8);  // 33-byte message, then suffix 1111 + first pad bit
+    a[kRateShake128 - 1].hi ^= 0x80000000u;
+    keccak_f1600(a);
+    if (ETA == 2) {  // 128 bytes = lanes 0..15
+#pragma unroll
+        for (int l = 0; l < 16; l++) {
+            put(2 * l, cbd2_word(a[l].lo));
+            put(2 * l + 1, cbd2_word(a[l].hi));
+        }
+    } else {  // 192 bytes = 21 lanes of this block + 3 lanes of the next (sha3.c:298-311)
+#pragma unroll
+        for (int g = 0; g < 7; g++) {  // 3 lanes = 6 words = two 96-bit groups
+            uint32_t o0, o1;
+            cbd3_words(a[3 * g].lo, a[3 * g].hi, a[3 * g + 1].lo, o0, o1);
+            put(4 * g, o0);
+            put(4 * g + 1, o1);
+            cbd3_words(a[3 * g + 1].hi, a[3 * g + 2].lo, a[3 * g + 2].hi, o0, o1);
+            put(4 * g + 2, o0);
+            put(4 * g + 3, o1);
+        }
+        keccak_f1600(a);
+        uint32_t o0, o1;
+        cbd3_words(a[0].lo, a[0].hi, a[1].lo, o0, o1);
+        put(28, o0);
+        put(29, o1);
+        cbd3_words(a[1].hi, a[2].lo, a[2].hi, o0, o1);
+        put(30, o0);
+        put(31, o1);
+    }
+}
+
+// Store a polynomial held in layout B as 128 coalesced 32-bit words (coefficient pairs) at `dst`.
+__device__ __forceinline__ void store_layoutB_global(const uint32_t x[8], uint16_t *scratch, int lane, uint32_t *dst) {
+#pragma unroll
+    for (int r = 0; r < 8; r++) scratch[pidx(idxB(lane, r))] = (uint16_t)x[r];
+    __syncwarp();
+    const uint32_t *sw = reinterpret_cast<const uint32_t *>(scratch);
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        int t = lane + 32 * r;  // pair index: coefficients 2t, 2t+1
+        dst[t] = sw[pidx(2 * t) >> 1];
+    }
+    __syncwarp();
+}
+// Same for layout A.
+__device__ __forceinline__ void store_layoutA_global(const uint32_t x[8], uint16_t *scratch, int lane, uint32_t *dst) {
+#pragma unroll
+    for (int r = 0; r < 8; r++) scratch[pidx(idxA(lane, r))] = (uint16_t)x[r];
+    __syncwarp();
+    const uint32_t *sw = reinterpret_cast<const uint32_t *>(scratch);
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        int t = lane + 32 * r;
+        dst[t] = sw[pidx(2 * t) >> 1];
+    }
+    __syncwarp();
+}
+// Load 128 coalesced words (coefficient pairs) from `src` into the padded scratch.
+__device__ __forceinline__ void load_global_to_scratch(const uint32_t *src, uint16_t *scratch, int lane) {
+    uint32_t *sw = reinterpret_cast<uint32_t *>(scratch);
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        int t = lane + 32 * r;
+        sw[pidx(2 * t) >> 1] = src[t];
+    }
+    __syncwarp();
+}
+
+// Grid: (ceil(n / kNoiseTPB), npoly).  Thread = one (item, nonce) sponge; blockIdx.y selects the nonce,
+// so a block is uniform in eta and in whether its polynomials get transformed.
+//   seeds       : 32-byte PRF key of item i at seeds + i*seed_stride
+//   NTT_OUT     : out16 + i*out16_stride + p*256   <- NTT(CBD(...)) as uint16, natural order  (s^, e^, y^)
+//   otherwise   : outc  + i*outc_stride  + p*32    <- 4-bit codes of CBD(...)                 (e1, e2)
+template <int ETA, bool NTT_OUT>
+__global__ void __launch_bounds__(kNoiseTPB) k_noise(int n, const uint8_t *__restrict__ seeds, size_t seed_stride, int nonce0,
+                                                     uint16_t *__restrict__ out16, size_t out16_stride,
+                                                     uint32_t *__restrict__ outc, size_t outc_stride) {
+    __shared__ uint32_t s_codes[NTT_OUT ? kNoiseTPB * 33 : 1];
+    __shared__ __align__(16) uint16_t s_scratch[NTT_OUT ? (kNoiseTPB / 32) * kScratchU16 : 2];
+    const int p = blockIdx.y;
+    const int item = blockIdx.x * kNoiseTPB + threadIdx.x;
+    Lane seed[4];
+#pragma unroll
+    for (int w = 0; w < 4; w++) seed[w] = item < n ? load_lane(seeds + seed_stride * item + 8 * w) : Lane{0u, 0u};
+    if (NTT_OUT) {
+        uint32_t *mine = s_codes + 33 * threadIdx.x;
+        prf_cbd_codes<ETA>(seed, (uint32_t)(nonce0 + p), [&](int w, uint32_t v) { mine[w] = v; });
+        __syncwarp();  // a warp only ever reads the 32 slots its own lanes wrote
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        uint16_t *scratch = s_scratch + warp * kScratchU16;
+        LaneTwiddles tw;
+        load_lane_twiddles(tw, lane);
+        for (int t = 0; t < 32; t++) {
+            int it = blockIdx.x * kNoiseTPB + warp * 32 + t;
+            if (it >= n) break;
+            const uint32_t *codes = s_codes + 33 * (warp * 32 + t);
+            uint32_t x[8];
+#pragma unroll
+            for (int r = 0; r < 8; r++) {
+                int c = idxA(lane, r);
+                x[r] = noise_code_to_coeff((codes[c >> 3] >> (4 * (c & 7))) & 15u);
+            }
+            ntt_warp(x, scratch, lane, tw);
+            store_layoutB_global(x, scratch, lane, reinterpret_cast<uint32_t *>(out16 + out16_stride * it + 256 * p));
+        }
+    } else {
+        if (item >= n) return;
+        uint32_t buf[32];
+        prf_cbd_codes<ETA>(seed, (uint32_t)(nonce0 + p), [&](int w, uint32_t v) { buf[w] = v; });
+        uint4 *dst = reinterpret_cast<uint4 *>(outc + outc_stride * item + 32 * p);
+#pragma unroll
+        for (int v = 0; v < 8; v++) dst[v] = make_uint4(buf[4 * v], buf[4 * v + 1], buf[4 * v + 2], buf[4 * v + 3]);
+    }
+}
+
+// =================================================================================================
+// SampleNTT (ml_kem.c:189), one sponge per thread, output into a shared-memory slot
+// =================================================================================================
+// The reference squeezes 840 bytes (5 blocks) up front, consumes three-byte groups until it has 256
+// coefficients, gives up after the 279th group (even when that group completed the polynomial) and then
+// restarts with B[32] and B[33] incremented.  Here blocks are squeezed on demand (3 suffice 99.1 % of the
+// time); the accepted coefficients, the give-up rule and the restart are identical.  `group_limit` is 278
+// (= groups that may be consumed by a successful run); tests lower it to exercise the restart path.
+//
+// Returns with 256 canonical coefficients in slot[0..255]; b32/b33 are updated like the caller's buffer.
+__device__ __forceinline__ void sample_ntt_thread(const Lane rho[4], uint32_t &b32, uint32_t &b33, uint16_t *slot, bool active,
+                                                  int group_limit) {
+    Lane a[25];
+    int j = active ? 0 : kN;  // inactive lanes (beyond the batch) just follow along
+    int groups_left = 0;
+    bool need_init = true;
+    // Loop until every lane of the warp holds a full polynomial.
+    while (__any_sync(kFullMask, j < kN)) {
+        if (need_init) {  // XOF.Init + Absorb(rho || b32 || b33), ml_kem.c:200-201
+            keccak_zero(a);
+#pragma unroll
+            for (int w = 0; w < 4; w++) a[w] = rho[w];
+            a[4].lo = (b32 & 0xFFu) | ((b33 & 0xFFu) << 8) | (kSfxXof << 16);
+            a[kRateShake128 - 1].hi ^= 0x80000000u;
+            groups_left = group_limit;
+            need_init = false;
+        }
+        keccak_f1600(a);
+        // one 168-byte block = 56 three-byte groups = 7 chunks of 3 lanes (16 candidates each)
+#pragma unroll
+        for (int ch = 0; ch < 7; ch++) {
+            uint32_t w[6] = {a[3 * ch].lo, a[3 * ch].hi, a[3 * ch + 1].lo, a[3 * ch + 1].hi, a[3 * ch + 2].lo, a[3 * ch + 2].hi};
+#pragma unroll
+            for (int g = 0; g < 8; g++) {  // group g of the chunk = 24 bits at bit offset 24 g
+                const int bit = 24 * g, wi = bit >> 5, sh = bit & 31;
+                uint32_t v = sh <= 8 ? (w[wi] >> sh) : __funnelshift_r(w[wi], w[wi + (wi < 5 ? 1 : 0)], sh);
+                uint32_t d1 = v & 0xFFFu, d2 = (v >> 12) & 0xFFFu;  // ml_kem.c:208-209
+                bool live = groups_left > 0;
+                if (live && d1 < kQ && j < kN) slot[j++] = (uint16_t)d1;  // :211-214
+                if (live && d2 < kQ && j < kN) slot[j++] = (uint16_t)d2;  // :216-219
+                groups_left -= 1;
+            }
+        }
+        // give-up rule (:221-227,237-242): out of groups without a full polynomial -> bump the seed, restart
+        if (groups_left <= 0 && j < kN) {
+            b32 = (b32 + 1) & 0xFFu;
+            b33 = (b33 + 1) & 0xFFu;
+            j = 0;
+            need_init = true;
+        }
+    }
+}
+
+// =================================================================================================
+// Fused matrix expansion + matrix-vector product (the heavy kernel of KeyGen and Encrypt)
+// =================================================================================================
+enum MatvecMode { kModeKeyGen = 0, kModeEncrypt = 1, kModeEncryptCompare = 2 };
+
+struct MatvecArgs {
+    int n;
+    int group_limit;
+    const uint8_t *rho;      // 32-byte matrix seed of item i at rho + i*rho_stride
+    size_t rho_stride;
+    const uint16_t *vec;     // s^ (KeyGen) or y^ (Encrypt): item i, polynomial j at vec + i*vec_stride + 256 j
+    size_t vec_stride;
+    const uint16_t *add16;   // KeyGen: e^ as uint16, same addressing as vec (polynomial index = row)
+    size_t add16_stride;
+    const uint32_t *addc;    // Encrypt: e1 as 4-bit codes, row r of item i at addc + i*addc_stride + 32 r
+    size_t addc_stride;
+    uint8_t *out;            // KeyGen: ek (row r at +384 r); Encrypt: c (row r at +32 du r)
+    size_t out_stride;
+    uint8_t *out2;           // KeyGen: second copy of the row inside dk (dk + 384k), or nullptr
+    size_t out2_stride;
+    const uint8_t *cmp;      // EncryptCompare: the received ciphertext, addressed like out
+    uint32_t *flags;         // EncryptCompare: flags[i] |= 1 when a re-encrypted row differs
+};
+
+// Block = 32 K threads = 32 (item,row) groups x K matrix columns.  Phase 1: each thread samples one matrix
+// entry into its slot.  Phase 2: each warp takes groups round-robin and finishes the row.
+template <class P, int MODE>
+__global__ void __launch_bounds__(32 * P::K) k_sample_matvec(MatvecArgs g) {
+    constexpr int K = P::K;
+    extern __shared__ __align__(16) uint32_t s_slots[];  // 32 K slots of kSlotWords words
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    {
+        const int grp = tid / K, col = tid - grp * K;
+        const long long gg = (long long)blockIdx.x * 32 + grp;
+        const int item = (int)(gg / K), row = (int)(gg - (long long)item * K);
+        const bool active = item < g.n;
+        Lane rho[4];
+#pragma unroll
+        for (int w = 0; w < 4; w++) rho[w] = active ? load_lane(g.rho + g.rho_stride * item + 8 * w) : Lane{0u, 0u};
+        // KeyGen: A[row][col] = SampleNTT(rho || col || row)      (ml_kem.c:686-693)
+        // Encrypt: At[row][col] = SampleNTT(rho || row || col)    (ml_kem.c:817-823, stored transposed)
+        uint32_t b32 = MODE == kModeKeyGen ? col : row, b33 = MODE == kModeKeyGen ? row : col;
+        sample_ntt_thread(rho, b32, b33, reinterpret_cast<uint16_t *>(s_slots + kSlotWords * tid), active, g.group_limit);
+    }
+    __syncthreads();
+
+    uint2 gam[4];
+#pragma unroll
+    for (int r = 0; r < 4; r++) gam[r] = c_tw.gamma[lane + 32 * r];
+    LaneTwiddles tw;
+    if (MODE != kModeKeyGen) load_lane_twiddles_inv(tw, lane);
+    uint32_t diff = 0;
+
+    for (int grp = warp; grp < 32; grp += K) {
+        const long long gg = (long long)blockIdx.x * 32 + grp;
+        const int item = (int)(gg / K), row = (int)(gg - (long long)item * K);
+        if (item >= g.n) break;  // groups are ordered by item
+        uint32_t *slot0 = s_slots + kSlotWords * (grp * K);
+        // ---- row . vector in the NTT domain (ml_kem.c:618 VectorMultiply), lazily accumulated
+        uint32_t acc[8];
+#pragma unroll
+        for (int r = 0; r < 8; r++) acc[r] = 0;
+        const uint32_t *vec = reinterpret_cast<const uint32_t *>(g.vec + g.vec_stride * item);
+#pragma unroll
+        for (int j = 0; j < K; j++) {
+            const uint32_t *aw = slot0 + kSlotWords * j;
+#pragma unroll
+            for (int r = 0; r < 4; r++) {
+                int t = lane + 32 * r;
+                uint32_t a = aw[t], b = __ldg(vec + 128 * j + t);
+                basemul_acc(acc[2 * r], acc[2 * r + 1], a & 0xFFFFu, a >> 16, b & 0xFFFFu, b >> 16, gam[r]);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < 8; r++) acc[r] = canon32(acc[r]);
+        __syncwarp();  // every lane is done reading the group's slots: they become scratch from here on
+        uint8_t *stage = reinterpret_cast<uint8_t *>(slot0 + kSlotWords);  // slot 1 of the group: packed bytes
+        int nwords;
+        if (MODE == kModeKeyGen) {
+            // t^[row] = A[row] . s^ + e^[row]   (ml_kem.c:723-727), then ByteEncode12 (:736-742)
+            const uint32_t *ev = reinterpret_cast<const uint32_t *>(g.add16 + g.add16_stride * item + 256 * row);
+#pragma unroll
+            for (int r = 0; r < 4; r++) {
+                int t = lane + 32 * r;
+                uint32_t e = __ldg(ev + t);
+                uint32_t c0 = csubq(acc[2 * r] + (e & 0xFFFFu)), c1 = csubq(acc[2 * r + 1] + (e >> 16));
+                uint32_t v = c0 | (c1 << 12);
+                stage[3 * t] = (uint8_t)v;
+                stage[3 * t + 1] = (uint8_t)(v >> 8);
+                stage[3 * t + 2] = (uint8_t)(v >> 16);
+            }
+            nwords = 96;
+        } else {
+            // u[row] = InverseNTT(At[row] . y^) + e1[row]  (ml_kem.c:854-864); Compress_du + ByteEncode_du (:886-896)
+            uint16_t *scratch = reinterpret_cast<uint16_t *>(slot0);
+            uint32_t *sw = slot0;
+#pragma unroll
+            for (int r = 0; r < 4; r++) {
+                int t = lane + 32 * r;
+                sw[pidx(2 * t) >> 1] = acc[2 * r] | (acc[2 * r + 1] << 16);
+            }
+            __syncwarp();
+            uint32_t x[8];
+#pragma unroll
+            for (int r = 0; r < 8; r++) x[r] = scratch[pidx(idxB(lane, r))];
+            __syncwarp();
+            intt_warp(x, scratch, lane, tw);
+            const uint32_t *codes = g.addc + g.addc_stride * item + 32 * row;
+#pragma unroll
+            for (int r = 0; r < 8; r++) {
+                uint32_t e = noise_code_to_coeff((__ldg(codes + (lane >> 3) + 4 * r) >> (4 * (lane & 7))) & 15u);
+                x[r] = compress<P::DU>(csubq(x[r] + e));
+                scratch[pidx(idxA(lane, r))] = (uint16_t)x[r];
+            }
+            __syncwarp();
+            uint32_t v8[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) v8[i] = scratch[pidx(8 * lane + i)];
+            pack8<P::DU>(v8, stage + P::DU * lane);
+            nwords = 8 * P::DU;
+        }
+        __syncwarp();
+        const uint32_t *stw = reinterpret_cast<const uint32_t *>(stage);
+        const size_t row_off = (MODE == kModeKeyGen ? 384 : P::C1ROW) * (size_t)row;
+        if (MODE == kModeEncryptCompare) {
+            const uint32_t *cw = reinterpret_cast<const uint32_t *>(g.cmp + g.out_stride * item + row_off);
+            uint32_t d = 0;
+            for (int w = lane; w < nwords; w += 32) d |= stw[w] ^ __ldg(cw + w);
+            d = __any_sync(kFullMask, d != 0) ? 1u : 0u;
+            if (lane == 0) atomicOr(g.flags + item, d);  // unconditional: no data-dependent control flow
+            diff |= d;
+        } else {
+            uint32_t *ow = reinterpret_cast<uint32_t *>(g.out + g.out_stride * item + row_off);
+            for (int w = lane; w < nwords; w += 32) ow[w] = stw[w];
+            if (MODE == kModeKeyGen && g.out2) {
+                uint32_t *ow2 = reinterpret_cast<uint32_t *>(g.out2 + g.out2_stride * item + row_off);
+                for (int w = lane; w < nwords; w += 32) ow2[w] = stw[w];
+            }
+        }
+        __syncwarp();
+    }
+    (void)diff;
+}
+
+// =================================================================================================
+// Remaining K-PKE pieces, one item per warp
+// =================================================================================================
+constexpr int kWarpTPB = 128;  // 4 items per block
+
+struct EncVArgs {
+    int n;
+    const uint8_t *ek;      // item i at ek + i*ek_stride: ByteEncode12(t^) (384 K bytes) || rho
+    size_t ek_stride;
+    const uint16_t *yhat;   // y^ polynomials, item stride in uint16
+    size_t yhat_stride;
+    const uint32_t *addc;   // noise codes, e2 is row K
+    size_t addc_stride;
+    const uint8_t *m;       // 32-byte message of item i at m + 32 i
+    uint8_t *c;             // ciphertext base (c2 is written at + 32 du K)
+    size_t c_stride;
+    const uint8_t *cmp;
+    uint32_t *flags;
+};
+
+// v = InverseNTT(t^ . y^) + e2 + Decompress_1(m)  (ml_kem.c:867-880); c2 = ByteEncode_dv(Compress_dv(v)) (:899-904).
+// Also copies rho into nothing: purely the v row.  COMPARE: OR the mismatch into flags instead of storing.
+template <class P, bool COMPARE>
+__global__ void __launch_bounds__(kWarpTPB) k_encrypt_v(EncVArgs g) {
+    constexpr int K = P::K;
+    __shared__ __align__(16) uint16_t s_scratch[(kWarpTPB / 32) * kScratchU16];
+    __shared__ __align__(16) uint8_t s_stage[(kWarpTPB / 32) * 32 * P::DV];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int item = blockIdx.x * (kWarpTPB / 32) + warp;
+    if (item >= g.n) return;
+    uint16_t *scratch = s_scratch + warp * kScratchU16;
+    uint8_t *stage = s_stage + warp * 32 * P::DV;
+    uint2 gam[4];
+#pragma unroll
+    for (int r = 0; r < 4; r++) gam[r] = c_tw.gamma[lane + 32 * r];
+    LaneTwiddles tw;
+    load_lane_twiddles_inv(tw, lane);
+
+    const uint8_t *ek = g.ek + g.ek_stride * item;
+    const uint32_t *yv = reinterpret_cast<const uint32_t *>(g.yhat + g.yhat_stride * item);
+    uint32_t acc[8];
+#pragma unroll
+    for (int r = 0; r < 8; r++) acc[r] = 0;
+#pragma unroll
+    for (int j = 0; j < K; j++) {
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            int t = lane + 32 * r;
+            const uint8_t *p = ek + 384 * j + 3 * t;  // ByteDecode12 without reduction (ml_kem.c:806-808, D4)
+            uint32_t v = (uint32_t)__ldg(p) | ((uint32_t)__ldg(p + 1) << 8) | ((uint32_t)__ldg(p + 2) << 16);
+            uint32_t b = __ldg(yv + 128 * j + t);
+            basemul_acc(acc[2 * r], acc[2 * r + 1], v & 0xFFFu, v >> 12, b & 0xFFFFu, b >> 16, gam[r]);
+        }
+    }
+    uint32_t *sw = reinterpret_cast<uint32_t *>(scratch);
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        int t = lane + 32 * r;
+        sw[pidx(2 * t) >> 1] = canon32(acc[2 * r]) | (canon32(acc[2 * r + 1]) << 16);
+    }
+    __syncwarp();
+    uint32_t x[8];
+#pragma unroll
+    for (int r = 0; r < 8; r++) x[r] = scratch[pidx(idxB(lane, r))];
+    __syncwarp();
+    intt_warp(x, scratch, lane, tw);
+    const uint32_t *codes = g.addc + g.addc_stride * item + 32 * K;
+    const uint32_t *mw = reinterpret_cast<const uint32_t *>(g.m + 32 * (size_t)item);
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        uint32_t e = noise_code_to_coeff((__ldg(codes + (lane >> 3) + 4 * r) >> (4 * (lane & 7))) & 15u);
+        uint32_t mu = ((__ldg(mw + r) >> lane) & 1u) * 1665u;  // Decompress_1(bit) = 1665 bit (ml_kem.c:867-870)
+        uint32_t v = csubq(csubq(x[r] + e) + mu);
+        scratch[pidx(idxA(lane, r))] = (uint16_t)compress<P::DV>(v);
+    }
+    __syncwarp();
+    uint32_t v8[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) v8[i] = scratch[pidx(8 * lane + i)];
+    pack8<P::DV>(v8, stage + P::DV * lane);
+    __syncwarp();
+    const uint32_t *stw = reinterpret_cast<const uint32_t *>(stage);
+    const size_t off = (size_t)P::C1ROW * K;
+    if (COMPARE) {
+        const uint32_t *cw = reinterpret_cast<const uint32_t *>(g.cmp + g.c_stride * item + off);
+        uint32_t d = 0;
+        for (int w = lane; w < 8 * P::DV; w += 32) d |= stw[w] ^ __ldg(cw + w);
+        d = __any_sync(kFullMask, d != 0) ? 1u : 0u;
+        if (lane == 0) atomicOr(g.flags + item, d);
+    } else {
+        uint32_t *ow = reinterpret_cast<uint32_t *>(g.c + g.c_stride * item + off);
+        for (int w = lane; w < 8 * P::DV; w += 32) ow[w] = stw[w];
+    }
+}
+
+// ml_kem.c:942 PKE_Decrypt: m' = ByteEncode_1(Compress_1(v - InverseNTT(s^ . NTT(u)))).
+template <class P>
+__global__ void __launch_bounds__(kWarpTPB) k_decrypt(int n, const uint8_t *__restrict__ dk, size_t dk_stride,
+                                                      const uint8_t *__restrict__ c, uint8_t *__restrict__ mout) {
+    constexpr int K = P::K;
+    __shared__ __align__(16) uint16_t s_scratch[(kWarpTPB / 32) * kScratchU16];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int item = blockIdx.x * (kWarpTPB / 32) + warp;
+    if (item >= n) return;
+    uint16_t *scratch = s_scratch + warp * kScratchU16;
+    const uint32_t *sw = reinterpret_cast<const uint32_t *>(scratch);
+    uint2 gam[4];
+#pragma unroll
+    for (int r = 0; r < 4; r++) gam[r] = c_tw.gamma[lane + 32 * r];
+    LaneTwiddles tw;
+    load_lane_twiddles(tw, lane);
+    const uint8_t *ci = c + (size_t)P::C * item;
+    const uint8_t *sk = dk + dk_stride * item;
+    uint32_t acc[8];
+#pragma unroll
+    for (int r = 0; r < 8; r++) acc[r] = 0;
+    for (int i = 0; i < K; i++) {
+        // u^[i] = NTT(Decompress_du(ByteDecode_du(c1[i])))   (ml_kem.c:978-987)
+        uint32_t x[8];
+#pragma unroll
+        for (int r = 0; r < 8; r++) x[r] = decompress<P::DU>(unpack1<P::DU>(ci + P::C1ROW * i, idxA(lane, r)));
+        ntt_warp(x, scratch, lane, tw);
+#pragma unroll
+        for (int r = 0; r < 8; r++) scratch[pidx(idxB(lane, r))] = (uint16_t)x[r];
+        __syncwarp();
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            int t = lane + 32 * r;
+            const uint8_t *p = sk + 384 * i + 3 * t;  // s^[i] = ByteDecode12(dk_pke[i]) (ml_kem.c:996-998)
+            uint32_t s = (uint32_t)__ldg(p) | ((uint32_t)__ldg(p + 1) << 8) | ((uint32_t)__ldg(p + 2) << 16);
+            uint32_t u = sw[pidx(2 * t) >> 1];
+            basemul_acc(acc[2 * r], acc[2 * r + 1], s & 0xFFFu, s >> 12, u & 0xFFFFu, u >> 16, gam[r]);
+        }
+        __syncwarp();
+    }
+    uint32_t *sww = reinterpret_cast<uint32_t *>(scratch);
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        int t = lane + 32 * r;
+        sww[pidx(2 * t) >> 1] = canon32(acc[2 * r]) | (canon32(acc[2 * r + 1]) << 16);
+    }
+    __syncwarp();
+    uint32_t x[8];
+#pragma unroll
+    for (int r = 0; r < 8; r++) x[r] = scratch[pidx(idxB(lane, r))];
+    __syncwarp();
+    load_lane_twiddles_inv(tw, lane);
+    intt_warp(x, scratch, lane, tw);
+    // w = v - x (ml_kem.c:1001-1003), m' bit = Compress_1(w) (:1009-1012); coefficient lane+32r is bit lane of word r
+    uint32_t myword = 0;
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        uint32_t v = decompress<P::DV>(unpack1<P::DV>(ci + P::C1ROW * K, idxA(lane, r)));
+        uint32_t w = csubq(v + kQ - x[r]);
+        uint32_t word = __ballot_sync(kFullMask, compress<1>(w) & 1u);
+        if (lane == r) myword = word;
+    }
+    if (lane < 8) reinterpret_cast<uint32_t *>(mout + 32 * (size_t)item)[lane] = myword;
+}
+
+// KeyGen: dk_pke rows = ByteEncode12(s^[i]) (ml_kem.c:750-756), plus the rho / ek-tail copies.
+// One warp per (item, row); s^ as uint16 at shat + item*stride + 256 row.
+template <class P>
+__global__ void __launch_bounds__(kWarpTPB) k_keygen_encode_s(int n, const uint16_t *__restrict__ shat, size_t shat_stride,
+                                                              const uint8_t *__restrict__ rs, uint8_t *__restrict__ ek,
+                                                              uint8_t *__restrict__ dk, size_t dk_stride, bool full_dk) {
+    constexpr int K = P::K;
+    __shared__ __align__(16) uint8_t s_stage[(kWarpTPB / 32) * 384];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long gg = (long long)blockIdx.x * (kWarpTPB / 32) + warp;
+    const int item = (int)(gg / K), row = (int)(gg - (long long)item * K);
+    if (item >= n) return;
+    uint8_t *stage = s_stage + warp * 384;
+    const uint32_t *sv = reinterpret_cast<const uint32_t *>(shat + shat_stride * item + 256 * row);
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        int t = lane + 32 * r;
+        uint32_t s = __ldg(sv + t);
+        uint32_t v = (s & 0xFFFFu) | ((s >> 16) << 12);
+        stage[3 * t] = (uint8_t)v;
+        stage[3 * t + 1] = (uint8_t)(v >> 8);
+        stage[3 * t + 2] = (uint8_t)(v >> 16);
+    }
+    __syncwarp();
+    const uint32_t *stw = reinterpret_cast<const uint32_t *>(stage);
+    uint32_t *ow = reinterpret_cast<uint32_t *>(dk + dk_stride * item + 384 * row);
+    for (int w = lane; w < 96; w += 32) ow[w] = stw[w];
+    if (row == 0 && lane < 8) {  // rho -> ek tail (ml_kem.c:745-747) and its copy inside dk (:1058-1062)
+        uint32_t v = reinterpret_cast<const uint32_t *>(rs + 64 * (size_t)item)[lane];
+        reinterpret_cast<uint32_t *>(ek + (size_t)P::EK * item + 384 * K)[lane] = v;
+        if (full_dk) reinterpret_cast<uint32_t *>(dk + dk_stride * item + 384 * K + 384 * K)[lane] = v;
+    }
+}
+
+// =================================================================================================
+// Stand-alone batched primitives (the C-ABI's mlkem_*_batch entry points; BASELINE config 2)
+// =================================================================================================
+constexpr int kPrimTPB = 256;  // 8 polynomials per block
+
+// ml_kem.c:287 NTT over n polynomials of 256 uint16 (natural order in, natural order out).
+__global__ void __launch_bounds__(kPrimTPB) k_ntt_batch(int n, const uint16_t *__restrict__ in, uint16_t *__restrict__ out) {
+    __shared__ __align__(16) uint16_t s_scratch[(kPrimTPB / 32) * kScratchU16];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint16_t *scratch = s_scratch + warp * kScratchU16;
+    LaneTwiddles tw;
+    load_lane_twiddles(tw, lane);
+    for (long long p = (long long)blockIdx.x * (kPrimTPB / 32) + warp; p < n; p += (long long)gridDim.x * (kPrimTPB / 32)) {
+        load_global_to_scratch(reinterpret_cast<const uint32_t *>(in + 256 * p), scratch, lane);
+        uint32_t x[8];
+#pragma unroll
+        for (int r = 0; r < 8; r++) x[r] = scratch[pidx(idxA(lane, r))] & 0xFFFu;
+        __syncwarp();
+        ntt_warp(x, scratch, lane, tw);
+        store_layoutB_global(x, scratch, lane, reinterpret_cast<uint32_t *>(out + 256 * p));
+    }
+}
+// ml_kem.c:336 InverseNTT.
+__global__ void __launch_bounds__(kPrimTPB) k_intt_batch(int n, const uint16_t *__restrict__ in, uint16_t *__restrict__ out) {
+    __shared__ __align__(16) uint16_t s_scratch[(kPrimTPB / 32) * kScratchU16];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint16_t *scratch = s_scratch + warp * kScratchU16;
+    LaneTwiddles tw;
+    load_lane_twiddles_inv(tw, lane);
+    for (long long p = (long long)blockIdx.x * (kPrimTPB / 32) + warp; p < n; p += (long long)gridDim.x * (kPrimTPB / 32)) {
+        load_global_to_scratch(reinterpret_cast<const uint32_t *>(in + 256 * p), scratch, lane);
+        uint32_t x[8];
+#pragma unroll
+        for (int r = 0; r < 8; r++) x[r] = scratch[pidx(idxB(lane, r))] & 0xFFFu;
+        __syncwarp();
+        intt_warp(x, scratch, lane, tw);
+        store_layoutA_global(x, scratch, lane, reinterpret_cast<uint32_t *>(out + 256 * p));
+    }
+}
+// ml_kem.c:415 MultiplyNTTs (operands may be any 12-bit value, D4).
+__global__ void __launch_bounds__(kPrimTPB) k_mulntt_batch(int n, const uint16_t *__restrict__ f, const uint16_t *__restrict__ gq,
+                                                           uint16_t *__restrict__ h) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint2 gam[4];
+#pragma unroll
+    for (int r = 0; r < 4; r++) gam[r] = c_tw.gamma[lane + 32 * r];
+    for (long long p = (long long)blockIdx.x * (kPrimTPB / 32) + warp; p < n; p += (long long)gridDim.x * (kPrimTPB / 32)) {
+        const uint32_t *fw = reinterpret_cast<const uint32_t *>(f + 256 * p), *gw = reinterpret_cast<const uint32_t *>(gq + 256 * p);
+        uint32_t *hw = reinterpret_cast<uint32_t *>(h + 256 * p);
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            int t = lane + 32 * r;
+            uint32_t a = __ldg(fw + t), b = __ldg(gw + t), c0 = 0, c1 = 0;
+            basemul_acc(c0, c1, a & 0xFFFu, (a >> 16) & 0xFFFu, b & 0xFFFu, (b >> 16) & 0xFFFu, gam[r]);
+            hw[t] = canon32(c0) | (canon32(c1) << 16);
+        }
+    }
+}
+
+// ml_kem.c:189 SampleNTT over n 34-byte seeds; out = n x 256 uint16; seeds_after (optional) receives the
+// caller-visible B after the call (only bytes 32, 33 can change).
+__global__ void __launch_bounds__(128) k_sample_ntt_batch(int n, const uint8_t *__restrict__ seeds, uint16_t *__restrict__ out,
+                                                          uint8_t *__restrict__ seeds_after, int group_limit) {
+    extern __shared__ __align__(16) uint32_t s_slots[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int item = blockIdx.x * 128 + tid;
+    const bool active = item < n;
+    Lane rho[4];
+    uint32_t b32 = 0, b33 = 0;
+    if (active) {
+        const uint8_t *s = seeds + 34 * (size_t)item;  // 34-byte stride: byte loads
+#pragma unroll
+        for (int w = 0; w < 4; w++) {
+            uint32_t lo = 0, hi = 0;
+#pragma unroll
+            for (int b = 0; b < 4; b++) {
+                lo |= (uint32_t)s[8 * w + b] << (8 * b);
+                hi |= (uint32_t)s[8 * w + 4 + b] << (8 * b);
+            }
+            rho[w] = Lane{lo, hi};
+        }
+        b32 = s[32];
+        b33 = s[33];
+    } else {
+#pragma unroll
+        for (int w = 0; w < 4; w++) rho[w] = Lane{0u, 0u};
+    }
+    sample_ntt_thread(rho, b32, b33, reinterpret_cast<uint16_t *>(s_slots + kSlotWords * tid), active, group_limit);
+    if (active && seeds_after) {
+        uint8_t *sa = seeds_after + 34 * (size_t)item;
+        const uint8_t *s = seeds + 34 * (size_t)item;
+        for (int b = 0; b < 32; b++) sa[b] = s[b];
+        sa[32] = (uint8_t)b32;
+        sa[33] = (uint8_t)b33;
+    }
+    __syncwarp();
+    for (int t = 0; t < 32; t++) {  // coalesced copy-out, one polynomial at a time
+        int it = blockIdx.x * 128 + warp * 32 + t;
+        if (it >= n) break;
+        const uint32_t *src = s_slots + kSlotWords * (warp * 32 + t);
+        uint32_t *dst = reinterpret_cast<uint32_t *>(out + 256 * (size_t)it);
+#pragma unroll
+        for (int r = 0; r < 4; r++) dst[lane + 32 * r] = src[lane + 32 * r];
+    }
+}
+
+// ml_kem.c:253 SamplePolyCBD over n byte strings of 64 eta bytes (no PRF); one polynomial per warp.
+template <int ETA>
+__global__ void __launch_bounds__(kPrimTPB) k_cbd_batch(int n, const uint8_t *__restrict__ in, uint16_t *__restrict__ out) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (long long p = (long long)blockIdx.x * (kPrimTPB / 32) + warp; p < n; p += (long long)gridDim.x * (kPrimTPB / 32)) {
+        const uint8_t *src = in + (size_t)64 * ETA * p;
+        uint32_t *dst = reinterpret_cast<uint32_t *>(out + 256 * p);
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            int t = lane + 32 * r;  // coefficients 2t, 2t+1 = 4 eta bits starting at bit 4 eta t
+            uint32_t c[2];
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                int bit = 2 * ETA * (2 * t + h);
+                uint32_t w = (uint32_t)src[bit >> 3] | ((uint32_t)src[min((bit >> 3) + 1, 64 * ETA - 1)] << 8);
+                w >>= (bit & 7);
+                uint32_t x = __popc(w & ((1u << ETA) - 1u)), y = __popc((w >> ETA) & ((1u << ETA) - 1u));
+                c[h] = x >= y ? x - y : kQ - (y - x);
+            }
+            dst[t] = c[0] | (c[1] << 16);
+        }
+    }
+}
+
+// PRF + CBD (+ optional NTT) exposed as a primitive: n (seed, nonce) pairs -> uint16 polynomials.
+template <int ETA>
+__global__ void __launch_bounds__(kNoiseTPB) k_prf_cbd_batch(int n, const uint8_t *__restrict__ seeds, const uint8_t *__restrict__ nonces,
+                                                             uint16_t *__restrict__ out) {
+    __shared__ uint32_t s_codes[kNoiseTPB * 33];
+    const int item = blockIdx.x * kNoiseTPB + threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    Lane seed[4];
+#pragma unroll
+    for (int w = 0; w < 4; w++) seed[w] = item < n ? load_lane(seeds + 32 * (size_t)item + 8 * w) : Lane{0u, 0u};
+    uint32_t nonce = item < n ? nonces[item] : 0u;
+    uint32_t *mine = s_codes + 33 * threadIdx.x;
+    prf_cbd_codes<ETA>(seed, nonce, [&](int w, uint32_t v) { mine[w] = v; });
+    __syncwarp();
+    for (int t = 0; t < 32; t++) {
+        int it = blockIdx.x * kNoiseTPB + warp * 32 + t;
+        if (it >= n) break;
+        const uint32_t *codes = s_codes + 33 * (warp * 32 + t);
+        uint32_t *dst = reinterpret_cast<uint32_t *>(out + 256 * (size_t)it);
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            int tt = lane + 32 * r;  // coefficients 2tt, 2tt+1
+            uint32_t wd = codes[tt >> 2] >> (8 * (tt & 3));
+            dst[tt] = noise_code_to_coeff(wd & 15u) | (noise_code_to_coeff((wd >> 4) & 15u) << 16);
+        }
+    }
+}
+
+// ByteEncode_d(Compress_d(.)) and Decompress_d(ByteDecode_d(.)) (ml_kem.c:83-177), HBM-bound:
+// one polynomial per warp, 128-bit loads of 8 coefficients per lane, bytes staged in shared memory and
+// written back with 128-bit stores.  COMPRESS=false gives the plain codec (for d = 12: no reduction, D4).
+template <int D, bool COMPRESS>
+__global__ void __launch_bounds__(kPrimTPB) k_encode_batch(int n, const uint16_t *__restrict__ in, uint8_t *__restrict__ out) {
+    __shared__ __align__(16) uint8_t s_stage[(kPrimTPB / 32) * 32 * D];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint8_t *stage = s_stage + warp * 32 * D;
+    for (long long p = (long long)blockIdx.x * (kPrimTPB / 32) + warp; p < n; p += (long long)gridDim.x * (kPrimTPB / 32)) {
+        uint4 q4 = __ldg(reinterpret_cast<const uint4 *>(in + 256 * p) + lane);  // coefficients 8 lane .. 8 lane + 7
+        uint32_t w[4] = {q4.x, q4.y, q4.z, q4.w}, v[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            uint32_t c = (w[i >> 1] >> (16 * (i & 1))) & 0xFFFu;
+            v[i] = (COMPRESS ? compress<D>(c) : c) & ((1u << D) - 1u);
+        }
+        pack8<D>(v, stage + D * lane);
+        __syncwarp();
+        const uint4 *sv = reinterpret_cast<const uint4 *>(stage);
+        uint4 *ov = reinterpret_cast<uint4 *>(out + (size_t)32 * D * p);
+        for (int i = lane; i < 2 * D; i += 32) ov[i] = sv[i];
+        __syncwarp();
+    }
+}
+template <int D, bool DECOMPRESS>
+__global__ void __launch_bounds__(kPrimTPB) k_decode_batch(int n, const uint8_t *__restrict__ in, uint16_t *__restrict__ out) {
+    __shared__ __align__(16) uint8_t s_stage[(kPrimTPB / 32) * 32 * D];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint8_t *stage = s_stage + warp * 32 * D;
+    for (long long p = (long long)blockIdx.x * (kPrimTPB / 32) + warp; p < n; p += (long long)gridDim.x * (kPrimTPB / 32)) {
+        const uint4 *iv = reinterpret_cast<const uint4 *>(in + (size_t)32 * D * p);
+        uint4 *sv = reinterpret_cast<uint4 *>(stage);
+        for (int i = lane; i < 2 * D; i += 32) sv[i] = __ldg(iv + i);
+        __syncwarp();
+        uint32_t v[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            uint32_t c = unpack1<D>(stage, 8 * lane + i);
+            v[i] = DECOMPRESS ? decompress<D>(c) : c;
+        }
+        reinterpret_cast<uint4 *>(out + 256 * p)[lane] =
+            make_uint4(v[0] | (v[1] << 16), v[2] | (v[3] << 16), v[4] | (v[5] << 16), v[6] | (v[7] << 16));
+        __syncwarp();
+    }
+}
+// Element-wise Compress_d / Decompress_d on uint16 arrays (8 coefficients per thread).
+template <int D, bool DECOMPRESS>
+__global__ void __launch_bounds__(kPrimTPB) k_compress_batch(long long nvec, const uint4 *__restrict__ in, uint4 *__restrict__ out) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+        uint4 q4 = __ldg(in + i);
+        uint32_t w[4] = {q4.x, q4.y, q4.z, q4.w};
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            uint32_t lo = w[k] & 0xFFFu, hi = (w[k] >> 16) & 0xFFFu;
+            if (DECOMPRESS) {
+                lo = decompress<D>(lo & ((1u << D) - 1u));
+                hi = decompress<D>(hi & ((1u << D) - 1u));
+            } else {
+                lo = compress<D>(lo);
+                hi = compress<D>(hi);
+            }
+            w[k] = lo | (hi << 16);
+        }
+        out[i] = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+}
+
+}  // namespace mlkem

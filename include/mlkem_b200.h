@@ -1,0 +1,162 @@
+/*
+ * mlkem_b200.h -- C ABI of the B200-native batched ML-KEM engine (libmlkem_b200.so).
+ *
+ * This is the drop-in boundary for the hot path of rsjahnige/CRYSTALS-Kyber.  The reference has no
+ * plugin / FFI layer: its boundary is the C header ml_kem.h plus the symbols of ml_kem.o.  Two headers
+ * therefore describe this library:
+ *
+ *   include/ml_kem.h      the reference's own API (same unions, structs, enum and prototypes), each call a
+ *                         batch of one -- what an existing caller links against unchanged;
+ *   include/mlkem_b200.h  (this file) the batched entry points the reference-signature functions are
+ *                         built on, dense bytes / uint16 instead of the reference's 4-byte unions.
+ *
+ * Every function below names the reference function (file:line in /root/reference) whose results it
+ * reproduces bit for bit.  All arithmetic runs in CUDA kernels for sm_100a; there is no CPU fallback:
+ * without a usable CUDA device every call returns MLKEM_B200_ERR_CUDA.
+ *
+ * Layout conventions
+ *   - byte strings are dense uint8_t, item-major: item i of an array with per-item size S is at base + i*S;
+ *   - polynomials are 256 x uint16_t, natural coefficient order, item-major;
+ *   - keys and ciphertexts use the byte layouts of ml_kem.c: ek = ByteEncode12(t^)[384k] || rho[32]
+ *     (ml_kem.c:736-747), dk = dk_pke[384k] || ek || H(ek)[32] || z[32] (ml_kem.c:1050-1077),
+ *     c = c1[32 du k] || c2[32 dv] (ml_kem.c:907-918).
+ *
+ * Memory spaces (mlkem_b200_opts.mem)
+ *   MLKEM_B200_MEM_HOST    pointers are host memory (pinned memory from mlkem_b200_host_alloc gives the
+ *                          full PCIe rate).  The call stages chunks through device memory with copies and
+ *                          kernels overlapped on two streams and returns when the results are in place.
+ *   MLKEM_B200_MEM_DEVICE  pointers are device memory on opts.device, 16-byte aligned.  The call enqueues
+ *                          its kernels on opts.stream (NULL = the library's stream for that device) and
+ *                          returns without synchronising.
+ */
+#ifndef MLKEM_B200_H
+#define MLKEM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default) /* the library itself is built with -fvisibility=hidden */
+#endif
+
+#define MLKEM_B200_MEM_HOST 0
+#define MLKEM_B200_MEM_DEVICE 1
+
+/* Return codes.  -1, -3 and -5 keep the meaning of the reference's ml_errno (ml_kem.c:1243-1391). */
+#define MLKEM_B200_OK 0
+#define MLKEM_B200_ERR_PARAM (-1)     /* unknown parameter set (ml_errno -1, ml_kem.c:1391) */
+#define MLKEM_B200_ERR_LENGTH (-3)    /* length / type check failed (ml_errno -3, ml_kem.c:1269,1323,1331) */
+#define MLKEM_B200_ERR_HASH (-5)      /* dk hash check failed (ml_errno -5, ml_kem.c:1347) */
+#define MLKEM_B200_ERR_CUDA (-10)     /* CUDA runtime error or no device; see mlkem_b200_last_error() */
+#define MLKEM_B200_ERR_ARG (-11)      /* NULL / misaligned pointer, unsupported d or eta */
+
+typedef struct mlkem_b200_opts {
+    int device;             /* CUDA device ordinal, -1 = the calling thread's current device */
+    int mem;                /* MLKEM_B200_MEM_HOST or MLKEM_B200_MEM_DEVICE */
+    void *stream;           /* cudaStream_t for MEM_DEVICE calls; NULL = library stream */
+    int chunk_items;        /* items per internal chunk, 0 = default */
+    int sample_group_limit; /* test hook for the SampleNTT give-up rule (ml_kem.c:221-227); 0 = 278 (the reference) */
+} mlkem_b200_opts;
+/* A NULL opts pointer means {device -1, MEM_HOST, NULL, 0, 0}. */
+
+const char *mlkem_b200_version(void);
+const char *mlkem_b200_last_error(void);          /* text of the last CUDA error seen by this thread */
+unsigned long long mlkem_b200_launch_count(void); /* kernels launched by this library so far (all threads) */
+int mlkem_b200_device_count(void);
+int mlkem_b200_synchronize(int device, void *stream);
+void *mlkem_b200_host_alloc(size_t bytes);        /* pinned host memory (cudaHostAlloc) */
+void mlkem_b200_host_free(void *p);
+void mlkem_b200_release(int device);              /* drop the cached workspace of a device */
+
+/* Sizes of a parameter set (512 / 768 / 1024), 0 for an unknown set.  ml_kem.c:730-731,1050,1105 */
+unsigned mlkem_b200_ek_bytes(int param_set);
+unsigned mlkem_b200_dk_bytes(int param_set);
+unsigned mlkem_b200_dkpke_bytes(int param_set);
+unsigned mlkem_b200_ct_bytes(int param_set);
+
+/* ---- ML-KEM internal algorithms (FIPS 203 Alg. 16-18 as implemented by the reference) -------------- */
+
+/* KeyGen_internal, ml_kem.c:1034.  d, z: n x 32.  ek: n x (384k+32).  dk: n x (768k+96). */
+int mlkem_b200_keygen_batch(int param_set, size_t n, const uint8_t *d, const uint8_t *z, uint8_t *ek, uint8_t *dk,
+                            const mlkem_b200_opts *opts);
+/* Encaps_internal, ml_kem.c:1093.  ek: n x (384k+32), m: n x 32.  c: n x 32(du k + dv), K: n x 32. */
+int mlkem_b200_encaps_batch(int param_set, size_t n, const uint8_t *ek, const uint8_t *m, uint8_t *c, uint8_t *K,
+                            const mlkem_b200_opts *opts);
+/* Decaps_internal, ml_kem.c:1136, including FO re-encryption and implicit rejection on the device.
+ * dk: n x (768k+96), c: n x 32(du k + dv).  K: n x 32. */
+int mlkem_b200_decaps_batch(int param_set, size_t n, const uint8_t *dk, const uint8_t *c, uint8_t *K,
+                            const mlkem_b200_opts *opts);
+/* The dk hash check of KEM_Decaps, ml_kem.c:1336-1350: status[i] = 0 or -5.  status: n x int32. */
+int mlkem_b200_check_dk_batch(int param_set, size_t n, const uint8_t *dk, int32_t *status, const mlkem_b200_opts *opts);
+
+/* ---- K-PKE (FIPS 203 Alg. 13-15) -------------------------------------------------------------------- */
+
+/* PKE_KeyGen, ml_kem.c:651.  d: n x 32.  ek: n x (384k+32).  dk_pke: n x 384k. */
+int mlkem_b200_pke_keygen_batch(int param_set, size_t n, const uint8_t *d, uint8_t *ek, uint8_t *dk_pke,
+                                const mlkem_b200_opts *opts);
+/* PKE_Encrypt, ml_kem.c:776.  m, r: n x 32. */
+int mlkem_b200_pke_encrypt_batch(int param_set, size_t n, const uint8_t *ek, const uint8_t *m, const uint8_t *r,
+                                 uint8_t *c, const mlkem_b200_opts *opts);
+/* PKE_Decrypt, ml_kem.c:942.  dk_pke: item i at dk_pke + i*dk_stride (384k for bare keys, 768k+96 to read them
+ * out of decapsulation keys).  m: n x 32. */
+int mlkem_b200_pke_decrypt_batch(int param_set, size_t n, const uint8_t *dk_pke, size_t dk_stride, const uint8_t *c,
+                                 uint8_t *m, const mlkem_b200_opts *opts);
+
+/* ---- ring arithmetic ------------------------------------------------------------------------------- */
+
+/* NTT, ml_kem.c:287.  Coefficients must be < q (any 12-bit value is reduced mod q first; the reference's
+ * behaviour for values in [q, 4096) differs and is not reproduced -- it never occurs on the KEM path). */
+int mlkem_b200_ntt_batch(size_t n, const uint16_t *f, uint16_t *f_hat, const mlkem_b200_opts *opts);
+/* InverseNTT, ml_kem.c:336 (includes the multiplication by 3303). */
+int mlkem_b200_intt_batch(size_t n, const uint16_t *f_hat, uint16_t *f, const mlkem_b200_opts *opts);
+/* MultiplyNTTs, ml_kem.c:415 (128 BaseCaseMultiply, ml_kem.c:395).  Operands may be any 12-bit value. */
+int mlkem_b200_multiply_ntts_batch(size_t n, const uint16_t *f_hat, const uint16_t *g_hat, uint16_t *h_hat,
+                                   const mlkem_b200_opts *opts);
+
+/* ---- samplers -------------------------------------------------------------------------------------- */
+
+/* SampleNTT, ml_kem.c:189.  seeds: n x 34.  a_hat: n x 256.  seeds_after (may be NULL): n x 34, the caller's
+ * buffer B after the call (the reference bumps B[32], B[33] when it gives up and restarts, :237-242). */
+int mlkem_b200_sample_ntt_batch(size_t n, const uint8_t *seeds, uint16_t *a_hat, uint8_t *seeds_after,
+                                const mlkem_b200_opts *opts);
+/* SamplePolyCBD_eta, ml_kem.c:253.  bytes: n x 64 eta, eta in {2, 3}. */
+int mlkem_b200_cbd_batch(int eta, size_t n, const uint8_t *bytes, uint16_t *f, const mlkem_b200_opts *opts);
+/* SamplePolyCBD_eta(PRF_eta(s, b)), ml_kem.c:496 + :253 (PRF is SHAKE128 in the reference).
+ * seeds: n x 32, nonces: n x 1. */
+int mlkem_b200_prf_cbd_batch(int eta, size_t n, const uint8_t *seeds, const uint8_t *nonces, uint16_t *f,
+                             const mlkem_b200_opts *opts);
+
+/* ---- codec ----------------------------------------------------------------------------------------- */
+
+/* ByteEncode_d, ml_kem.c:125.  F: n x 256 (low d bits used).  B: n x 32 d.  d in {1,4,5,10,11,12}. */
+int mlkem_b200_byte_encode_batch(int d, size_t n, const uint16_t *F, uint8_t *B, const mlkem_b200_opts *opts);
+/* ByteDecode_d, ml_kem.c:153 (d = 12: no reduction mod q, like the reference). */
+int mlkem_b200_byte_decode_batch(int d, size_t n, const uint8_t *B, uint16_t *F, const mlkem_b200_opts *opts);
+/* Compress_d / Decompress_d, ml_kem.c:83 / :104, element-wise over n_coeffs values (multiple of 8). */
+int mlkem_b200_compress_batch(int d, size_t n_coeffs, const uint16_t *x, uint16_t *y, const mlkem_b200_opts *opts);
+int mlkem_b200_decompress_batch(int d, size_t n_coeffs, const uint16_t *y, uint16_t *x, const mlkem_b200_opts *opts);
+/* Fused ByteEncode_d(Compress_d(F)) and Decompress_d(ByteDecode_d(B)) as used at ml_kem.c:886-904, :978-993. */
+int mlkem_b200_compress_encode_batch(int d, size_t n, const uint16_t *F, uint8_t *B, const mlkem_b200_opts *opts);
+int mlkem_b200_decode_decompress_batch(int d, size_t n, const uint8_t *B, uint16_t *F, const mlkem_b200_opts *opts);
+
+/* ---- hashes ---------------------------------------------------------------------------------------- */
+
+/* which = 0: H = SHA3-256 (ml_kem.c:521), 32 B out.  1: G = SHA3-512 (:559), 64 B out.
+ * 2: J = SHAKE128 with 32 B out (:540 -- the reference uses capacity 256).
+ * in: n messages of `len` bytes each, len a multiple of 8 (true of every H/G/J input of ML-KEM except
+ * G(d||k), which only occurs inside KeyGen). */
+int mlkem_b200_hash_batch(int which, size_t n, size_t len, const uint8_t *in, uint8_t *out, const mlkem_b200_opts *opts);
+
+/* Read-only copies of the device twiddle tables: zeta_i = 17^BitRev7(i), gamma_i = 17^(2 BitRev7(i)+1). */
+int mlkem_b200_tables(uint16_t zeta[128], uint16_t gamma[128]);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* MLKEM_B200_H */

@@ -221,6 +221,13 @@ ORC_API void orc_byte_decode(const uint8_t *B, unsigned d, uint16_t F[ORC_N]) {
  * group completed the polynomial); on give-up B[32] and B[33] are incremented in the CALLER's buffer
  * and the whole procedure restarts (:237-242).  Returns the number of restarts (0 in practice).
  */
+static unsigned orc_group_limit = 279; /* ml_kem.c:224: k >= 280*8*3 - 8*3 after the 279th group */
+
+/* TEST HOOK: lower the give-up threshold so that the restart path (ml_kem.c:237-242), which is
+ * unreachable in practice with the reference's own limit, can be exercised against the CUDA kernel.
+ * `usable` = number of groups a successful run may consume (the reference: 278). */
+ORC_API void orc_set_sample_group_limit(unsigned usable) { orc_group_limit = usable ? usable + 1 : 279; }
+
 ORC_API int orc_sample_ntt(uint8_t B[34], uint16_t a[ORC_N]) {
     int restarts = 0;
     for (;;) {
@@ -235,7 +242,7 @@ ORC_API int orc_sample_ntt(uint8_t B[34], uint16_t a[ORC_N]) {
             if (d1 < ORC_Q) a[j++] = d1;
             if (d2 < ORC_Q && j < ORC_N) a[j++] = d2;
             grp++;
-            if (grp >= 279) {
+            if (grp >= orc_group_limit) {
                 gave_up = 1;
                 break;
             }

@@ -147,6 +147,18 @@ class Oracle(_Lib):
                                            out.ctypes.data_as(C.POINTER(C.c_uint16)))
         return out, s.tobytes(), int(r)
 
+    def set_sample_group_limit(self, usable):
+        """TEST HOOK, see orc_set_sample_group_limit (0 restores the reference's 278)."""
+        self.fn("set_sample_group_limit")(C.c_uint(usable))
+
+    def sample_ntt_with_seeds(self, seeds34):
+        s = np.array(np.ascontiguousarray(seeds34, dtype=np.uint8)).reshape(-1, 34)
+        out = np.empty((s.shape[0], 256), np.uint16)
+        f = self.fn("sample_ntt", C.c_int)
+        for i in range(s.shape[0]):
+            f(s[i].ctypes.data_as(C.POINTER(C.c_uint8)), out[i].ctypes.data_as(C.POINTER(C.c_uint16)))
+        return out, s
+
     def cbd(self, data, eta):
         b, pb = _u8(data)
         n = b.size // (64 * eta)
