@@ -1,0 +1,396 @@
+#!/usr/bin/env python3
+"""bench.py -- BASELINE.json's headline metric on B200: batched ML-KEM-768 Encaps + Decaps.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--log2-items L] [--impl reference]
+
+Workload (BASELINE.json configs[3]): 2^22 synthetic ML-KEM-768 items PER GPU; one step = Encaps_internal over
+all items followed by Decaps_internal over the resulting ciphertexts with 10 % of them tampered (FO
+re-encryption + implicit rejection on the device).  Inputs are derived on the device from the global item
+index (crystals-kyber_b200/workload.py), keys are generated on the device before the timed region.
+
+  value     encaps+decaps pairs per second, whole job, inputs and outputs resident in HBM
+  e2e       the same step through the C ABI with HOST buffers (pinned): H2D of ek, m, dk, c and D2H of
+            c, K, K' inside the timed region
+  roofline  the dominant kernel (fused matrix expansion + matrix-vector product) against the INT32
+            alu-pipe issue rate measured live on the same GPU (mlkem_b200_int32_peak)
+  cpu_baseline / --impl reference
+            the reference itself (oracle/_ref, compiled from /root/reference by oracle/Makefile) timed on
+            the box's host cores on a bounded sample of the same workload
+
+Multi-GPU: one process per GPU under torchrun; ranks take contiguous shards of the global index range, no
+collective on the data path; timing is the max over ranks.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+PS = 768
+METRIC = "ML-KEM-768 Encaps+Decaps ops/s"
+UNIT = "encaps+decaps pairs/s"
+
+
+def emit(obj):
+    print(json.dumps(obj), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the reference's own CPU code on the host cores
+# ----------------------------------------------------------------------------------------------------
+def reference_pairs_per_s(threads: int, pairs_per_thread: int, steps: int, warmup: int):
+    """Times oracle/_ref (the unmodified reference behind ref_shim.c) on `threads` host threads.
+    Falls back to the oracle port when the compiled reference did not travel.  Returns a dict."""
+    import numpy as np
+
+    from oracle.oracle import REF_G_SO, REF_SO, Oracle, Reference, build
+
+    build()
+    orc = Oracle()
+    n = threads * pairs_per_thread
+    rng = np.random.default_rng(20261018)
+    d, z, m = (rng.integers(0, 256, (n, 32), dtype=np.uint8) for _ in range(3))
+    ek, dk = orc.keygen(PS, d, z)  # setup only (not timed, not part of the measured path)
+    out = {"cores": threads, "sample": f"{n} ML-KEM-768 encaps+decaps pairs per step on {threads} threads"}
+    if os.path.exists(REF_SO):
+        ref = Reference(REF_SO)
+        for _ in range(warmup):
+            ref.time_pairs(PS, ek[:threads], dk[:threads], m[:threads], threads)
+        ts = [ref.time_pairs(PS, ek, dk, m, threads)[0] for _ in range(steps)]
+        t = sum(ts) / len(ts)
+        _, c, K = ref.time_pairs(PS, ek[:threads], dk[:threads], m[:threads], threads)
+        oc, oK = orc.encaps(PS, ek[:threads], m[:threads])
+        assert (c == oc).all() and (K == oK).all(), "reference and oracle disagree"
+        out.update(kind="reference", value=n / t, ms_per_step=1e3 * t,
+                   build="gcc -O2 of /root/reference/{ml_kem.c,sha3.c} via oracle/ref_shim.c")
+        if os.path.exists(REF_G_SO):  # the reference's own makefile flags (-Wall -g => -O0), one thread, for the record
+            rg = Reference(REF_G_SO)
+            tg, _, _ = rg.time_pairs(PS, ek[:2], dk[:2], m[:2], 1)
+            out["makefile_flags_1thread_pairs_per_s"] = 2 / tg
+    else:
+        import ctypes
+
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            c, K = orc.encaps(PS, ek, m)
+            orc.decaps(PS, dk, c)
+        t = (time.perf_counter() - t0) / steps
+        out.update(kind="port", value=n / t, ms_per_step=1e3 * t, build="oracle/mlkem_oracle.c (OpenMP), reference .so absent")
+    out["unit"] = UNIT
+    return out
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    r = reference_pairs_per_s(threads, 8, max(1, args.steps), max(0, min(args.warmup, 1)))
+    emit({
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u16/u64 integer", "data": "synthetic",
+        "config": {"workload": "ML-KEM-768 Encaps_internal + Decaps_internal, bounded sample on host cores", "sample": r["sample"]},
+        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"],
+                         "build": r["build"], "makefile_flags_1thread_pairs_per_s": r.get("makefile_flags_1thread_pairs_per_s")},
+        "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    })
+
+
+# ----------------------------------------------------------------------------------------------------
+# clocks
+# ----------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.idx)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+
+    def summary(self, t0, t1):
+        sm, mx, reasons, power = [], [], set(), []
+        for ts, line in self.lines:
+            if ts < t0 or ts > t1 + 0.2:
+                continue
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm), "power_w_max": max(power)}
+
+
+# ----------------------------------------------------------------------------------------------------
+# the GPU arm
+# ----------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--log2-items", type=int, default=22, help="items per GPU = 2^L (BASELINE config: 22)")
+    ap.add_argument("--e2e-log2-items", type=int, default=None, help="items per GPU for the host-buffer leg (default: same)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import numpy as np
+    import torch
+
+    import crystals_kyber_b200 as ck
+    from crystals_kyber_b200 import workload as wl
+    from crystals_kyber_b200.lib import MEM_DEVICE, MEM_HOST, Opts
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    kem = ck.MLKEM()
+    lib = kem.lib
+    sz = ck.sizes(PS)
+    n = 1 << args.log2_items
+    begin = rank * n  # weak scaling: every rank owns 2^L consecutive global items
+    steps, warmup = args.steps, max(args.warmup, 3)
+
+    # ---- setup (untimed): inputs from the global index, keys, the tampered ciphertexts
+    d, z, m = wl.derive_inputs(lambda msg, ln: kem.hash_batch(1, msg, ln), begin, begin + n, dev)
+    ek, dk = kem.keygen(PS, d, z)
+    c0, K0 = kem.encaps(PS, ek, m)
+    c_t = c0.clone()
+    tampered = wl.tamper_inplace(c_t, begin)
+    del d, z, c0
+    c = torch.empty((n, sz["c"]), dtype=torch.uint8, device=dev)
+    K = torch.empty((n, 32), dtype=torch.uint8, device=dev)
+    Kd = torch.empty((n, 32), dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream(dev)
+    o_dev = Opts(local, MEM_DEVICE, stream.cuda_stream, 0, 0)
+    P = lambda t: C.c_void_p(t.data_ptr())
+
+    def step_device():
+        rc = lib.mlkem_b200_encaps_batch(PS, n, P(ek), P(m), P(c), P(K), C.byref(o_dev))
+        rc |= lib.mlkem_b200_decaps_batch(PS, n, P(dk), P(c_t), P(Kd), C.byref(o_dev))
+        if rc:
+            raise RuntimeError(lib.mlkem_b200_last_error().decode())
+
+    for _ in range(warmup):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.3)
+    launches0 = lib.mlkem_b200_launch_count()
+    kem.profile(True)  # two event records per kernel launch (~300 launches per step): negligible
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_wall0 = time.time()
+    e0.record(stream)
+    for _ in range(steps):
+        step_device()
+    e1.record(stream)
+    barrier()
+    t_wall1 = time.time()
+    kem.profile(False)
+    launches = lib.mlkem_b200_launch_count() - launches0
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    clocks = sampler.summary(t_wall0, t_wall1)
+    prof = kem.profile_report()
+    value = world * n * steps / (ms * 1e-3)
+
+    # ---- correctness of what was just timed (outside the timed region)
+    ok = torch.ones(n, dtype=torch.bool, device=dev)
+    ok[tampered] = False
+    same = (Kd == K0).all(dim=1)
+    assert bool((K == K0).all()) and bool(same[ok].all()) and not bool(same[~ok].any()), "KEM round trip failed"
+
+    # ---- e2e: host buffers through the C ABI (H2D + kernels + D2H per step)
+    ne = 1 << (args.e2e_log2_items if args.e2e_log2_items is not None else args.log2_items)
+    ne = min(ne, n)
+    def pinned_copy(t):
+        h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        h.copy_(t)
+        return h
+
+    hek, hm, hdk, hct = (pinned_copy(t[:ne]) for t in (ek, m, dk, c_t))
+    hc = torch.empty((ne, sz["c"]), dtype=torch.uint8, pin_memory=True)
+    hK = torch.empty((ne, 32), dtype=torch.uint8, pin_memory=True)
+    hKd = torch.empty((ne, 32), dtype=torch.uint8, pin_memory=True)
+    o_host = Opts(local, MEM_HOST, None, 0, 0)
+
+    def step_host():
+        rc = lib.mlkem_b200_encaps_batch(PS, ne, P(hek), P(hm), P(hc), P(hK), C.byref(o_host))
+        rc |= lib.mlkem_b200_decaps_batch(PS, ne, P(hdk), P(hct), P(hKd), C.byref(o_host))
+        if rc:
+            raise RuntimeError(lib.mlkem_b200_last_error().decode())
+
+    step_host()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step_host()  # synchronous: returns when the results are in host memory
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    assert bool((hK == K0[:ne].cpu()).all()) and bool((hKd == Kd[:ne].cpu()).all()), "host-buffer path disagrees with device path"
+    e2e_value = world * ne * steps / e2e_s
+    h2d = ne * (sz["ek"] + 32 + sz["dk"] + sz["c"])
+    d2h = ne * (sz["c"] + 32 + 32)
+    sampler.stop()
+
+    # ---- roofline of the dominant kernel, INT32 alu pipe
+    peaks = kem.int32_peak()
+    k_, eta1, _, du, dv = ck.PARAMS[PS]
+    ops = wl.op_counts(k_, eta1, du, dv)
+    mv = [(name, v) for name, v in prof.items() if "k_sample_matvec" in name]
+    mv_ms = sum(v["ms"] for _, v in mv)
+    mv_launches = sum(v["launches"] for _, v in mv)
+    total_kernel_ms = sum(v["ms"] for v in prof.values())
+    items_per_launch = 2.0 * n * steps / max(mv_launches, 1)  # Encrypt runs once in Encaps and once in Decaps
+    achieved = ops["matvec_encrypt"] * items_per_launch / (mv_ms / max(mv_launches, 1) * 1e-3) if mv_ms else None
+    peak = max(peaks["lop3"], peaks["shf"])
+    roofline = {
+        "bound": "int32",
+        "kernel": "k_sample_matvec (SampleNTT x k^2 + MultiplyNTTs x k^2 + InverseNTT x k, fused)",
+        "achieved": achieved / 1e12 if achieved else None, "peak": peak / 1e12, "unit": "Tera int32 op/s",
+        "frac": achieved / peak if achieved else None,
+        "peak_source": "measured live: mlkem_b200_int32_peak (LOP3/SHF issue rate, alu pipe); MEASURED_PEAKS.json has no integer figure",
+        "algorithmic_ops_per_item": ops["matvec_encrypt"], "items_per_launch": items_per_launch,
+        "avg_launch_ms": mv_ms / max(mv_launches, 1), "share_of_step_kernel_time": mv_ms / total_kernel_ms if total_kernel_ms else None,
+        "traffic": None,
+        "whole_step": {"algorithmic_ops_per_pair": ops["encaps"] + ops["decaps"],
+                       "achieved": (ops["encaps"] + ops["decaps"]) * value / world / 1e12, "frac": (ops["encaps"] + ops["decaps"]) * value / world / peak},
+        "peaks_tera_ops": {k: v / 1e12 for k, v in peaks.items()},
+    }
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
+        "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u16/u64 integer", "data": "synthetic",
+        "config": {"workload": f"ML-KEM-768 Encaps_internal + Decaps_internal over 2^{args.log2_items} items per GPU, 10% of the ciphertexts tampered "
+                               "(BASELINE configs[3]); 1 op = 1 encaps + 1 decaps",
+                   "items_per_gpu": n, "distinct_keys": n, "tamper": "i % 10 == 3", "sharding": f"contiguous index shards x{world}, no collective",
+                   "cache": "working set 20 GB per GPU >> 126 MB L2, no flush needed"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "items_per_gpu": ne,
+                "ms_per_step": 1e3 * e2e_s / steps, "path": "mlkem_b200_encaps_batch + mlkem_b200_decaps_batch with MLKEM_B200_MEM_HOST (pinned buffers)"},
+        "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+        "kernel_ms_per_step": {k: v["ms"] / steps for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])},
+    }
+
+    # ---- extras: the other numbers BASELINE's metric names (NTT polys/s, codec GB/s, KeyGen/s), rank 0 only
+    if rank == 0 and not args.no_extras:
+        line["extra"] = extras(kem, torch, dev, peaks)
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        r = reference_pairs_per_s(os.cpu_count() or 1, 16, 1, 0)
+        line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "build") if k in r}
+        if "makefile_flags_1thread_pairs_per_s" in r:
+            line["cpu_baseline"]["makefile_flags_1thread_pairs_per_s"] = r["makefile_flags_1thread_pairs_per_s"]
+    if rank == 0:
+        emit(line)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def extras(kem, torch, dev, peaks):
+    """BASELINE config 2 (2^20 polynomials through NTT / InverseNTT / MultiplyNTTs) and the codec kernels,
+    device-resident, CUDA-event timed; working sets (0.5-1.5 GB) are far larger than L2."""
+    from crystals_kyber_b200 import workload as wl
+
+    out = {}
+    n = 1 << 20
+    g = torch.Generator(device=dev).manual_seed(20261018)
+    f = torch.randint(0, 3329, (n, 256), generator=g, device=dev, dtype=torch.int16).view(torch.uint16)
+    h = torch.randint(0, 3329, (n, 256), generator=g, device=dev, dtype=torch.int16).view(torch.uint16)
+
+    def timeit(fn, reps=5):
+        for _ in range(3):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps * 1e-3
+
+    hbm = None
+    try:
+        hbm = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+    except Exception:
+        pass
+    alu = max(peaks["lop3"], peaks["shf"])
+    for name, fn, opsn, bytesn in (("ntt", lambda: kem.ntt(f), wl.OPS_NTT, 1024), ("intt", lambda: kem.intt(f), wl.OPS_INTT, 1024),
+                                   ("multiply_ntts", lambda: kem.multiply_ntts(f, h), wl.OPS_MULNTT, 1536)):
+        t = timeit(fn)
+        out[name] = {"polys_per_s": n / t, "int32_frac_of_alu_pipe": opsn * n / t / alu, "gb_per_s": bytesn * n / t / 1e9,
+                     "hbm_frac": (bytesn * n / t / 1e9 / hbm) if hbm else None}
+    for d in (4, 10, 12):
+        t = timeit(lambda: kem.compress_encode(f, d))
+        b = (512 + 32 * d) * n
+        out[f"compress_encode_{d}"] = {"gb_per_s": b / t / 1e9, "hbm_frac": (b / t / 1e9 / hbm) if hbm else None}
+    nk = 1 << 20
+    seeds = torch.randint(0, 256, (2, nk, 32), generator=g, device=dev, dtype=torch.uint8)
+    for ps in (512, 768, 1024):
+        t = timeit(lambda: kem.keygen(ps, seeds[0], seeds[1]), reps=2)
+        out[f"keygen_{ps}_per_s"] = nk / t
+    out["hbm_peak_gbs"] = hbm
+    return out
+
+
+if __name__ == "__main__":
+    main()

@@ -240,3 +240,19 @@ class MLKEM:
 
     def launch_count(self):
         return int(self.lib.mlkem_b200_launch_count())
+
+    # ------------------------------------------------------------------ measurement hooks
+    def profile(self, enable: bool):
+        self.lib.mlkem_b200_profile(1 if enable else 0)
+
+    def profile_report(self):
+        import json
+
+        buf = C.create_string_buffer(1 << 16)
+        n = self.lib.mlkem_b200_profile_report(buf, len(buf))
+        return json.loads(buf.raw[:n].decode()) if n else {}
+
+    def int32_peak(self):
+        out = (C.c_double * 6)()
+        self._check(self.lib.mlkem_b200_int32_peak(out), "mlkem_b200_int32_peak")
+        return dict(zip(("lop3", "shf", "imad", "lop3+imad", "iadd3", "imad_hi"), [float(v) for v in out]))

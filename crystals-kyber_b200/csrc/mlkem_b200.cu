@@ -33,11 +33,40 @@ std::atomic<unsigned long long> g_launches{0};
         }                                                                                                     \
     } while (0)
 
-// kernel<<<...>>>(...) with launch accounting and error capture
+// Optional per-kernel timing (mlkem_b200_profile): CUDA events recorded on the launching stream around
+// every kernel, resolved when the report is read.  Off by default; costs two event records per launch.
+struct ProfEntry {
+    const char *name;
+    cudaEvent_t e0, e1;
+};
+std::atomic<int> g_profile{0};
+std::mutex g_prof_mutex;
+std::vector<ProfEntry> g_prof_entries;
+
+inline void prof_begin(const char *name, cudaStream_t st, ProfEntry &pe, bool &on) {
+    on = g_profile.load(std::memory_order_relaxed) != 0;
+    if (!on) return;
+    pe.name = name;
+    cudaEventCreate(&pe.e0);
+    cudaEventCreate(&pe.e1);
+    cudaEventRecord(pe.e0, st);
+}
+inline void prof_end(cudaStream_t st, ProfEntry &pe, bool on) {
+    if (!on) return;
+    cudaEventRecord(pe.e1, st);
+    std::lock_guard<std::mutex> lock(g_prof_mutex);
+    g_prof_entries.push_back(pe);
+}
+
+// kernel<<<...>>>(...) with launch accounting, optional timing and error capture
 #define LAUNCH(kernel, grid, block, smem, stream, ...)           \
     do {                                                         \
         auto kern_ = kernel;                                     \
+        ProfEntry pe_;                                           \
+        bool prof_on_;                                           \
+        prof_begin(#kernel, (stream), pe_, prof_on_);            \
         kern_<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__); \
+        prof_end((stream), pe_, prof_on_);                       \
         g_launches.fetch_add(1, std::memory_order_relaxed);      \
         CU(cudaGetLastError());                                  \
     } while (0)
@@ -325,7 +354,9 @@ int drive(const mlkem_b200_opts *o, size_t n, size_t ws_per_item, std::vector<Bu
                 snprintf(tl_error, sizeof tl_error, "device pointers must be 16-byte aligned");
                 return MLKEM_B200_ERR_ARG;
             }
-        cudaStream_t st = o->stream ? static_cast<cudaStream_t>(o->stream) : ctx->stream[0];
+        // NULL is the CUDA default stream (what torch hands over for its default stream), not a library stream:
+        // the caller orders its own work against ours through the stream it names.
+        cudaStream_t st = static_cast<cudaStream_t>(o->stream);
         {
             std::lock_guard<std::mutex> lock(g_mutex);
             if (int rc = ensure_buffer(&ctx->ws[0], &ctx->ws_bytes[0], chunk * ws_per_item + kWsSlack)) return rc;
@@ -659,4 +690,5 @@ int mlkem_b200_tables(uint16_t zeta[128], uint16_t gamma[128]) {
 
 }  // extern "C"
 
+#include "mlkem_profile.inl"
 #include "ml_kem_compat.inl"

@@ -26,8 +26,8 @@
  *                          full PCIe rate).  The call stages chunks through device memory with copies and
  *                          kernels overlapped on two streams and returns when the results are in place.
  *   MLKEM_B200_MEM_DEVICE  pointers are device memory on opts.device, 16-byte aligned.  The call enqueues
- *                          its kernels on opts.stream (NULL = the library's stream for that device) and
- *                          returns without synchronising.
+ *                          its kernels on opts.stream (NULL = the CUDA default stream) and returns
+ *                          without synchronising; the caller orders its own work through that stream.
  */
 #ifndef MLKEM_B200_H
 #define MLKEM_B200_H
@@ -56,7 +56,7 @@ extern "C" {
 typedef struct mlkem_b200_opts {
     int device;             /* CUDA device ordinal, -1 = the calling thread's current device */
     int mem;                /* MLKEM_B200_MEM_HOST or MLKEM_B200_MEM_DEVICE */
-    void *stream;           /* cudaStream_t for MEM_DEVICE calls; NULL = library stream */
+    void *stream;           /* cudaStream_t for MEM_DEVICE calls; NULL = the CUDA default stream */
     int chunk_items;        /* items per internal chunk, 0 = default */
     int sample_group_limit; /* test hook for the SampleNTT give-up rule (ml_kem.c:221-227); 0 = 278 (the reference) */
 } mlkem_b200_opts;
@@ -149,6 +149,21 @@ int mlkem_b200_decode_decompress_batch(int d, size_t n, const uint8_t *B, uint16
  * in: n messages of `len` bytes each, len a multiple of 8 (true of every H/G/J input of ML-KEM except
  * G(d||k), which only occurs inside KeyGen). */
 int mlkem_b200_hash_batch(int which, size_t n, size_t len, const uint8_t *in, uint8_t *out, const mlkem_b200_opts *opts);
+
+/* ---- measurement hooks (bench.py) -------------------------------------------------------------------- */
+
+/* Per-kernel timing: while enabled, every kernel launch of the library is bracketed by CUDA events on its
+ * stream.  mlkem_b200_profile_report() synchronises, writes up to `cap` bytes of JSON
+ * ({"kernel name": {"launches": L, "ms": total}, ...}) into buf, clears the records and returns the number of
+ * bytes written (0 when nothing was recorded). */
+void mlkem_b200_profile(int enable);
+int mlkem_b200_profile_report(char *buf, int cap);
+
+/* INT32 roofline denominators of the current device, measured now: sustained thread-operations per second
+ * of out[0] LOP3, out[1] SHF (alu pipe), out[2] IMAD (fma pipe), out[3] LOP3+IMAD interleaved (both pipes),
+ * out[4] IADD3, out[5] IMAD.HI.  MEASURED_PEAKS.json has no integer figure, and the ML-KEM kernels are bound by
+ * these pipes, not by HBM or the tensor cores. */
+int mlkem_b200_int32_peak(double out[6]);
 
 /* Read-only copies of the device twiddle tables: zeta_i = 17^BitRev7(i), gamma_i = 17^(2 BitRev7(i)+1). */
 int mlkem_b200_tables(uint16_t zeta[128], uint16_t gamma[128]);
