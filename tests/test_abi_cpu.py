@@ -1,0 +1,112 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads and exports every symbol the headers declare
+(no compute calls -- there is no GPU here), and refuses to compute without a device instead of falling back."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import crystals_kyber_b200 as ck
+
+    if not os.path.exists(ck.LIB_PATH):
+        import subprocess
+
+        subprocess.run(["make", "-C", ROOT, "lib"], check=True, stdout=subprocess.DEVNULL)
+    return ck.load()
+
+
+def declared_functions(header):
+    txt = open(os.path.join(ROOT, "include", header)).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b([A-Za-z_][A-Za-z0-9_]*)\s*\([^;{]*\)\s*;", txt)))
+
+
+def test_batched_header_symbols_exported(lib):
+    from crystals_kyber_b200.lib import SIGNATURES
+
+    names = [n for n in declared_functions("mlkem_b200.h") if n.startswith("mlkem_b200_")]
+    assert len(names) >= 30
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/mlkem_b200.h but not exported"
+        assert n in SIGNATURES, f"{n} has no ctypes signature in lib.py"
+    assert set(SIGNATURES) == set(names)
+
+
+def test_reference_header_symbols_exported(lib):
+    from crystals_kyber_b200.lib import COMPAT_SYMBOLS
+
+    names = declared_functions("ml_kem.h")
+    expect = {"init", "KEM_KeyGen", "KEM_Encaps", "KEM_Decaps", "SampleNTT", "SamplePolyCBD", "NTT", "InverseNTT", "BitRev7",
+              "BitsToBytes", "BytesToBits", "Compress", "Decompress", "ByteEncode", "ByteDecode", "BaseCaseMultiply",
+              "MultiplyNTTs", "PKE_KeyGen", "PKE_Encrypt", "PKE_Decrypt", "KeyGen_internal", "Encaps_internal", "Decaps_internal"}
+    assert expect <= set(names)
+    for n in expect:
+        assert hasattr(lib, n)
+    assert set(COMPAT_SYMBOLS) == expect | {"ml_errno"}
+    assert C.c_int.in_dll(lib, "ml_errno").value == 0
+
+
+def test_sizes_match_reference_formulas(lib):
+    for ps, (k, du, dv) in {512: (2, 10, 4), 768: (3, 10, 4), 1024: (4, 11, 5)}.items():
+        assert lib.mlkem_b200_ek_bytes(ps) == 384 * k + 32       # ml_kem.c:730
+        assert lib.mlkem_b200_dkpke_bytes(ps) == 384 * k         # ml_kem.c:731
+        assert lib.mlkem_b200_dk_bytes(ps) == 768 * k + 96       # ml_kem.c:1050
+        assert lib.mlkem_b200_ct_bytes(ps) == 32 * (du * k + dv)  # ml_kem.c:1105
+    assert lib.mlkem_b200_ek_bytes(999) == 0
+
+
+def test_host_side_helpers_without_gpu(lib):
+    """Pure layout helpers of the reference-signature API need no device."""
+    class U(C.Structure):
+        _fields_ = [("v", C.c_uint)]
+
+    lib.BitRev7.restype, lib.BitRev7.argtypes = U, [U]
+    assert [lib.BitRev7(U(i)).v & 0x7F for i in (0, 1, 2, 3, 64, 127)] == [0, 64, 32, 96, 1, 127]  # ml_kem.c:26
+    lib.BitsToBytes.restype, lib.BitsToBytes.argtypes = C.POINTER(C.c_uint), [C.POINTER(C.c_uint), C.c_uint]
+    bits = (C.c_uint * 8)(*[i % 2 for i in range(8)])  # BitsAndBytes_test02.c: 01010101 -> 170
+    out = lib.BitsToBytes(bits, 8)
+    assert out[0] & 0xFF == 170
+    C.CDLL(None).free(out)
+
+
+def test_no_cpu_fallback(lib):
+    """Without a CUDA device every compute entry point must fail loudly (MLKEM_B200_ERR_CUDA), never compute."""
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    f = np.zeros((1, 256), np.uint16)
+    out = np.full((1, 256), 0xABCD, np.uint16)
+    rc = lib.mlkem_b200_ntt_batch(1, C.c_void_p(f.ctypes.data), C.c_void_p(out.ctypes.data), None)
+    assert rc == -10 and (out == 0xABCD).all()
+    assert b"failed" in lib.mlkem_b200_last_error()
+    assert lib.mlkem_b200_device_count() == 0
+    import crystals_kyber_b200 as ck
+
+    with pytest.raises(ck.MlKemB200Error):
+        ck.MLKEM().keygen(768, np.zeros((1, 32), np.uint8), np.zeros((1, 32), np.uint8))
+
+
+def test_product_does_not_import_oracle():
+    """The shipped package must never import, include, link or dlopen anything under oracle/."""
+    pkg = os.path.join(ROOT, "crystals-kyber_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            path = os.path.join(dirpath, fn)
+            if fn.endswith(".py"):
+                for line in open(path):
+                    assert not re.match(r"\s*(from|import)\s+oracle\b", line), f"{path}: {line.strip()}"
+                    assert "libmlkem_oracle" not in line and "libref_mlkem" not in line, f"{path}: {line.strip()}"
+            if fn.endswith((".cu", ".cuh", ".inl", ".h")):
+                for line in open(path):
+                    if line.lstrip().startswith("#include"):
+                        assert "oracle" not in line and "reference" not in line, f"{path}: {line.strip()}"
+    mk = open(os.path.join(ROOT, "Makefile")).read()
+    lib_rule = mk[mk.index("$(LIB):"):].split("\n\n")[0]
+    assert "oracle" not in lib_rule
