@@ -72,6 +72,12 @@ inline void prof_end(cudaStream_t st, ProfEntry &pe, bool on) {
     } while (0)
 
 inline unsigned cdiv(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
+// grid of the persistent warp-per-item kernels: enough blocks to fill the machine several times over, then grid-stride
+inline unsigned warp_grid(size_t items, int warps_per_block) {
+    size_t blocks = (items + warps_per_block - 1) / warps_per_block;
+    const size_t cap = 148 * 16;
+    return (unsigned)(blocks < cap ? blocks : cap);
+}
 
 // ------------------------------------------------------------------------------------------------
 // Tables
@@ -145,7 +151,7 @@ int allow_smem(KernelT kernel, size_t bytes) {
 }
 template <class P>
 int allow_smem_matvec() {
-    const size_t b = 32 * P::K * kSlotWords * 4;
+    const size_t b = matvec_smem_bytes<P>();
     if (int rc = allow_smem(k_sample_matvec<P, kModeKeyGen>, b)) return rc;
     if (int rc = allow_smem(k_sample_matvec<P, kModeEncrypt>, b)) return rc;
     if (int rc = allow_smem(k_sample_matvec<P, kModeEncryptCompare>, b)) return rc;
@@ -168,6 +174,7 @@ int acquire(const mlkem_b200_opts *o, int *dev, DeviceCtx **ctx) {
         uint2 rc[24];
         build_tables(t, rc);
         CU(cudaMemcpyToSymbol(c_tw, &t, sizeof t));
+        CU(cudaMemcpyToSymbol(g_tw, &t, sizeof t));
         CU(cudaMemcpyToSymbol(c_keccak_rc, rc, sizeof rc));
         for (int s = 0; s < kSlots; s++) CU(cudaStreamCreateWithFlags(&c.stream[s], cudaStreamNonBlocking));
         if (int r = allow_smem_matvec<P512>()) return r;
@@ -238,7 +245,7 @@ int enqueue_encrypt(cudaStream_t st, Arena &ws, int n, const uint8_t *ek, size_t
     a.cmp = cmp;
     a.flags = flags;
     const unsigned grid = cdiv((size_t)n * K, 32);
-    const size_t smem = 32 * K * kSlotWords * 4;
+    const size_t smem = matvec_smem_bytes<P>();
     EncVArgs v{};
     v.n = n;
     v.ek = ek;
@@ -254,10 +261,10 @@ int enqueue_encrypt(cudaStream_t st, Arena &ws, int n, const uint8_t *ek, size_t
     v.flags = flags;
     if (cmp) {
         LAUNCH((k_sample_matvec<P, kModeEncryptCompare>), grid, 32 * K, smem, st, a);
-        LAUNCH((k_encrypt_v<P, true>), cdiv(n, kWarpTPB / 32), kWarpTPB, 0, st, v);
+        LAUNCH((k_encrypt_v<P, true>), warp_grid(n, kWarpTPB / 32), kWarpTPB, 0, st, v);
     } else {
         LAUNCH((k_sample_matvec<P, kModeEncrypt>), grid, 32 * K, smem, st, a);
-        LAUNCH((k_encrypt_v<P, false>), cdiv(n, kWarpTPB / 32), kWarpTPB, 0, st, v);
+        LAUNCH((k_encrypt_v<P, false>), warp_grid(n, kWarpTPB / 32), kWarpTPB, 0, st, v);
     }
     return 0;
 }
@@ -287,7 +294,7 @@ int enqueue_keygen(cudaStream_t st, Arena &ws, int n, const uint8_t *d, const ui
     a.out_stride = P::EK;
     a.out2 = full ? dk + 384 * K : nullptr;
     a.out2_stride = dk_stride;
-    LAUNCH((k_sample_matvec<P, kModeKeyGen>), cdiv((size_t)n * K, 32), 32 * K, 32 * K * kSlotWords * 4, st, a);
+    LAUNCH((k_sample_matvec<P, kModeKeyGen>), cdiv((size_t)n * K, 32), 32 * K, matvec_smem_bytes<P>(), st, a);
     LAUNCH((k_keygen_encode_s<P>), cdiv((size_t)n * K, kWarpTPB / 32), kWarpTPB, 0, st, n, se, (size_t)2 * K * 256, rs, ek, dk, dk_stride, full);
     if (full) LAUNCH((k_keygen_H<P>), cdiv(n, kHashTPB), kHashTPB, 0, st, n, ek, z, dk);
     return 0;
@@ -307,7 +314,7 @@ int enqueue_decaps(cudaStream_t st, Arena &ws, int n, const uint8_t *dk, const u
     uint8_t *Kr = ws.take<uint8_t>((size_t)n * 64);
     uint32_t *flags = ws.take<uint32_t>((size_t)n);
     CU(cudaMemsetAsync(flags, 0, (size_t)n * 4, st));
-    LAUNCH((k_decrypt<P>), cdiv(n, kWarpTPB / 32), kWarpTPB, 0, st, n, dk, (size_t)P::DK, c, mp);
+    LAUNCH((k_decrypt<P>), warp_grid(n, kWarpTPB / 32), kWarpTPB, 0, st, n, dk, (size_t)P::DK, c, mp);
     LAUNCH((k_decaps_G<P>), cdiv(n, kHashTPB), kHashTPB, 0, st, n, mp, dk, Kr);
     // c' = K-PKE.Encrypt(ek_pke, m', r') compared on the fly (ml_kem.c:1206-1215)
     if (int rc = enqueue_encrypt<P>(st, ws, n, dk + 384 * K, P::DK, mp, Kr + 32, 64, nullptr, c, flags, group_limit)) return rc;
@@ -541,7 +548,7 @@ int mlkem_b200_pke_decrypt_batch(int set, size_t n, const uint8_t *dk, size_t dk
     DISPATCH_SET(set, {
         if (dk_stride < (size_t)P::DKPKE) return MLKEM_B200_ERR_LENGTH;
         return drive(o, n, 0, {{dk, nullptr, dk_stride}, {c, nullptr, P::C}, {nullptr, m, 32}}, [=](cudaStream_t st, Arena &, int cn, void **p) {
-            LAUNCH((k_decrypt<P>), cdiv(cn, kWarpTPB / 32), kWarpTPB, 0, st, cn, (const uint8_t *)p[0], dk_stride, (const uint8_t *)p[1], (uint8_t *)p[2]);
+            LAUNCH((k_decrypt<P>), warp_grid(cn, kWarpTPB / 32), kWarpTPB, 0, st, cn, (const uint8_t *)p[0], dk_stride, (const uint8_t *)p[1], (uint8_t *)p[2]);
             return 0;
         });
     });

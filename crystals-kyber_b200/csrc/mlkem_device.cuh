@@ -36,8 +36,14 @@ struct TwiddleTables {
     uint2 gamma[128];
 };
 // The library is a single translation unit (mlkem_b200.cu), so the tables are defined right here.
+// c_tw (constant bank) serves the warp-uniform lookups; g_tw (global memory, read through L1 with __ldg) serves
+// the lane-dependent ones -- a constant-bank load with 8..32 distinct addresses per warp is replayed once per
+// address, which showed up as the top stall reason per instruction in the first ncu capture.
 __constant__ TwiddleTables c_tw;
+__device__ TwiddleTables g_tw;
 __constant__ uint2 c_keccak_rc[24];
+__device__ __forceinline__ uint2 lane_zeta(int i) { return __ldg(&g_tw.zeta[i]); }
+__device__ __forceinline__ uint2 lane_gamma(int i) { return __ldg(&g_tw.gamma[i]); }
 
 // ------------------------------------------------------------------------------------------------
 // 1. Field arithmetic
@@ -202,48 +208,86 @@ __device__ __forceinline__ void store_lane(uint8_t *p, Lane v) { *reinterpret_ca
 // ------------------------------------------------------------------------------------------------
 // 3. Polynomials, one per warp
 // ------------------------------------------------------------------------------------------------
-// Register layouts for the 256 coefficients of one polynomial held by a warp, 8 per lane:
-//   layout A: x[r] = f[lane + 32 r]                               (index bits: r = b7 b6 b5, lane = b4..b0)
-//   layout B: x[r] = f[32 (lane >> 2) + 4 r + (lane & 3)]         (r = b4 b3 b2, lane = b7 b6 b5 b1 b0)
-// The forward transform consumes A (layers len = 128, 64, 32 are register-local), transposes to B through
-// the warp's shared-memory scratch (layers 16, 8, 4 local) and finishes len = 2 with one shuffle layer.
-// The inverse transform runs the same steps backwards: B in, A out.
+// Register layouts for the 256 coefficients of one polynomial held by a warp, 8 per lane
+// (coefficient index bits b7..b0):
+//   layout A: x[r] = f[lane + 32 r]                        r = b7 b6 b5        lane = b4 b3 b2 b1 b0
+//   layout B: x[r] = f[32 (lane >> 2) + 4 r + (lane & 3)]  r = b4 b3 b2        lane = b7 b6 b5 b1 b0
+//   layout C: x[r] = f[8 lane + r]                         r = b2 b1 b0        lane = b7 b6 b5 b4 b3
+// The forward transform (layers len = 128 .. 2 act on index bits b7 .. b1) runs three register-local
+// passes, A: len 128/64/32, B: len 16/8/4, C: len 2, with two transposes through the warp's shared-memory
+// scratch in between; it consumes layout A and leaves layout C, i.e. every lane ends up owning 8
+// consecutive coefficients = one 16-byte vector of the natural-order output.  The inverse transform runs
+// the same passes backwards: C in, A out.  No shuffles, no redundant multiplications: 28 butterflies per lane.
 //
-// Scratch polynomials in shared memory use a padded index so that both layouts are bank-conflict free:
-//   coefficient c lives at uint16 index c + 2 (c >> 5)  (one 32-bit pad word per 32 coefficients).
-constexpr int kScratchU16 = 272;  // 256 + 16 pad
-__device__ __forceinline__ int pidx(int c) { return c + ((c >> 5) << 1); }
+// Scratch polynomials are 256 uint16 (512 B, 16-byte aligned) with an XOR swizzle that makes all three
+// access patterns bank-conflict free: coefficient c lives at uint16 index  c ^ (((c >> 6) & 3) << 3)
+// (index bits b4 b3 are XORed with b7 b6; 8-coefficient groups stay contiguous and 16-byte aligned).
+constexpr int kScratchU16 = 256;
+__device__ __forceinline__ int sidx(int c) { return c ^ (((c >> 6) & 3) << 3); }
 __device__ __forceinline__ int idxA(int lane, int r) { return lane + 32 * r; }
 __device__ __forceinline__ int idxB(int lane, int r) { return ((lane >> 2) << 5) | (r << 2) | (lane & 3); }
+__device__ __forceinline__ int idxC(int lane, int r) { return 8 * lane + r; }
 
-// Per-lane twiddles for the layers whose zeta depends on the lane (layout B + the shuffle layer).
+// Per-lane twiddles for the passes whose zeta depends on the lane.
 struct LaneTwiddles {
-    uint2 z16;     // len 16: zeta[8 + (lane>>2)]
-    uint2 z8[2];   // len 8 : zeta[16 + 2 (lane>>2) + (r>>2)]
-    uint2 z4[4];   // len 4 : zeta[32 + 4 (lane>>2) + (r>>1)]
-    uint2 z2[8];   // len 2 : zeta[64 + 8 (lane>>2) + r]
+    uint2 z16;    // len 16: block = lane >> 2                 (layout B)
+    uint2 z8[2];  // len 8 : block = 2 (lane >> 2) + (r >> 2)
+    uint2 z4[4];  // len 4 : block = 4 (lane >> 2) + (r >> 1)
+    uint2 z2[2];  // len 2 : block = 2 lane + (r >> 2)         (layout C)
 };
+// Forward: block `blk` of the layer with n blocks uses zeta[n + blk] (ml_kem.c:296-308, i counts up from 1).
 __device__ __forceinline__ void load_lane_twiddles(LaneTwiddles &t, int lane) {
     int g = lane >> 2;
-    t.z16 = c_tw.zeta[8 + g];
+    t.z16 = lane_zeta(8 + g);
 #pragma unroll
-    for (int i = 0; i < 2; i++) t.z8[i] = c_tw.zeta[16 + 2 * g + i];
+    for (int i = 0; i < 2; i++) t.z8[i] = lane_zeta(16 + 2 * g + i);
 #pragma unroll
-    for (int i = 0; i < 4; i++) t.z4[i] = c_tw.zeta[32 + 4 * g + i];
+    for (int i = 0; i < 4; i++) t.z4[i] = lane_zeta(32 + 4 * g + i);
 #pragma unroll
-    for (int i = 0; i < 8; i++) t.z2[i] = c_tw.zeta[64 + 8 * g + i];
+    for (int i = 0; i < 2; i++) t.z2[i] = lane_zeta(64 + 2 * lane + i);
 }
-
-// Inverse transform: block `blk` of the layer with n blocks uses zeta[2n - 1 - blk] (i counts down from 127).
+// Inverse: block `blk` of the layer with n blocks uses zeta[2n - 1 - blk] (ml_kem.c:345-357, i counts down from 127).
 __device__ __forceinline__ void load_lane_twiddles_inv(LaneTwiddles &t, int lane) {
     int g = lane >> 2;
-    t.z16 = c_tw.zeta[15 - g];
+    t.z16 = lane_zeta(15 - g);
 #pragma unroll
-    for (int i = 0; i < 2; i++) t.z8[i] = c_tw.zeta[31 - (2 * g + i)];
+    for (int i = 0; i < 2; i++) t.z8[i] = lane_zeta(31 - (2 * g + i));
 #pragma unroll
-    for (int i = 0; i < 4; i++) t.z4[i] = c_tw.zeta[63 - (4 * g + i)];
+    for (int i = 0; i < 4; i++) t.z4[i] = lane_zeta(63 - (4 * g + i));
 #pragma unroll
-    for (int i = 0; i < 8; i++) t.z2[i] = c_tw.zeta[127 - (8 * g + i)];
+    for (int i = 0; i < 2; i++) t.z2[i] = lane_zeta(127 - (2 * lane + i));
+}
+
+// Transposes between layouts through the swizzled scratch.  Values must be < 2^16.
+__device__ __forceinline__ void store_scratch_A(const uint32_t x[8], uint16_t *s, int lane) {
+#pragma unroll
+    for (int r = 0; r < 8; r++) s[sidx(idxA(lane, r))] = (uint16_t)x[r];
+}
+__device__ __forceinline__ void load_scratch_A(uint32_t x[8], const uint16_t *s, int lane) {
+#pragma unroll
+    for (int r = 0; r < 8; r++) x[r] = s[sidx(idxA(lane, r))];
+}
+__device__ __forceinline__ void store_scratch_B(const uint32_t x[8], uint16_t *s, int lane) {
+#pragma unroll
+    for (int r = 0; r < 8; r++) s[sidx(idxB(lane, r))] = (uint16_t)x[r];
+}
+__device__ __forceinline__ void load_scratch_B(uint32_t x[8], const uint16_t *s, int lane) {
+#pragma unroll
+    for (int r = 0; r < 8; r++) x[r] = s[sidx(idxB(lane, r))];
+}
+// Layout C is one 16-byte vector per lane (8 consecutive coefficients).
+__device__ __forceinline__ uint4 pack_pairs(const uint32_t x[8]) {
+    return make_uint4(x[0] | (x[1] << 16), x[2] | (x[3] << 16), x[4] | (x[5] << 16), x[6] | (x[7] << 16));
+}
+__device__ __forceinline__ void unpack_pairs(uint4 v, uint32_t x[8]) {
+    x[0] = v.x & 0xFFFFu; x[1] = v.x >> 16; x[2] = v.y & 0xFFFFu; x[3] = v.y >> 16;
+    x[4] = v.z & 0xFFFFu; x[5] = v.z >> 16; x[6] = v.w & 0xFFFFu; x[7] = v.w >> 16;
+}
+__device__ __forceinline__ void store_scratch_C(const uint32_t x[8], uint16_t *s, int lane) {
+    *reinterpret_cast<uint4 *>(s + sidx(8 * lane)) = pack_pairs(x);
+}
+__device__ __forceinline__ void load_scratch_C(uint32_t x[8], const uint16_t *s, int lane) {
+    unpack_pairs(*reinterpret_cast<const uint4 *>(s + sidx(8 * lane)), x);
 }
 
 // Cooley-Tukey butterfly, lazy: inputs < 2^16 - 2q, outputs grow by at most 2q.
@@ -253,10 +297,10 @@ __device__ __forceinline__ void ct_bfly(uint32_t &a, uint32_t &b, uint2 z) {
     a = a + t;
 }
 
-// ml_kem.c:287 NTT.  x in layout A, canonical (< q; any value < 4096 also works and gives the same
-// residues).  Returns the transform in layout B, canonical.  `scratch` = this warp's padded scratch.
+// ml_kem.c:287 NTT.  x in layout A with values < 4096 (values >= q are treated as residues).  Returns the
+// transform in layout C, canonical.  `scratch` = this warp's 512-byte scratch; tw from load_lane_twiddles.
 __device__ __forceinline__ void ntt_warp(uint32_t x[8], uint16_t *scratch, int lane, const LaneTwiddles &tw) {
-    // len = 128, 64, 32: register index bits 2, 1, 0
+    // pass A -- len = 128, 64, 32: register index bits 2, 1, 0
 #pragma unroll
     for (int r = 0; r < 4; r++) ct_bfly(x[r], x[r + 4], c_tw.zeta[1]);
 #pragma unroll
@@ -265,14 +309,11 @@ __device__ __forceinline__ void ntt_warp(uint32_t x[8], uint16_t *scratch, int l
         for (int r = 0; r < 2; r++) ct_bfly(x[4 * h + r], x[4 * h + r + 2], c_tw.zeta[2 + h]);
 #pragma unroll
     for (int h = 0; h < 4; h++) ct_bfly(x[2 * h], x[2 * h + 1], c_tw.zeta[4 + h]);
-    // transpose A -> B (values < q + 6q < 2^16 fit uint16)
-#pragma unroll
-    for (int r = 0; r < 8; r++) scratch[pidx(idxA(lane, r))] = (uint16_t)x[r];
+    store_scratch_A(x, scratch, lane);  // values < 4096 + 6q < 2^16
     __syncwarp();
-#pragma unroll
-    for (int r = 0; r < 8; r++) x[r] = scratch[pidx(idxB(lane, r))];
+    load_scratch_B(x, scratch, lane);
     __syncwarp();
-    // len = 16, 8, 4: register index bits 2, 1, 0 of layout B
+    // pass B -- len = 16, 8, 4
 #pragma unroll
     for (int r = 0; r < 4; r++) ct_bfly(x[r], x[r + 4], tw.z16);
 #pragma unroll
@@ -281,17 +322,17 @@ __device__ __forceinline__ void ntt_warp(uint32_t x[8], uint16_t *scratch, int l
         for (int r = 0; r < 2; r++) ct_bfly(x[4 * h + r], x[4 * h + r + 2], tw.z8[h]);
 #pragma unroll
     for (int h = 0; h < 4; h++) ct_bfly(x[2 * h], x[2 * h + 1], tw.z4[h]);
-    // len = 2: partner lane differs in index bit b1 = lane bit 1.  The upper lane multiplies its own
-    // value, the lower lane sends its value; one shuffle per coefficient.
-    const bool up = lane & 2;
+    store_scratch_B(x, scratch, lane);  // values < 4096 + 12q < 2^16
+    __syncwarp();
+    load_scratch_C(x, scratch, lane);
+    __syncwarp();
+    // pass C -- len = 2: coefficient pairs (i, i + 2) inside each group of four
 #pragma unroll
-    for (int r = 0; r < 8; r++) {
-        uint32_t t = mul_shoup(x[r], tw.z2[r]);          // only meaningful on the upper lane
-        uint32_t send = up ? t : x[r];
-        uint32_t got = __shfl_xor_sync(kFullMask, send, 2);
-        uint32_t v = up ? (got - t + 2 * kQ) : (x[r] + got);  // up: a - zeta b ; low: a + zeta b
-        x[r] = canon16(v);
-    }
+    for (int h = 0; h < 2; h++)
+#pragma unroll
+        for (int r = 0; r < 2; r++) ct_bfly(x[4 * h + r], x[4 * h + r + 2], tw.z2[h]);
+#pragma unroll
+    for (int r = 0; r < 8; r++) x[r] = canon16(x[r]);  // < 4096 + 14q < 2^16
 }
 
 // Gentleman-Sande butterfly for the inverse transform (ml_kem.c:359-373): a' = a + b, b' = zeta (b - a).
@@ -303,47 +344,42 @@ __device__ __forceinline__ void gs_bfly(uint32_t &a, uint32_t &b, uint2 z, uint3
 }
 
 // ml_kem.c:336 InverseNTT including the final multiplication by 3303 (:378-381).
-// x in layout B, values < q (or any 12-bit value).  Returns layout A, canonical.  `tw` must come from
-// load_lane_twiddles_inv.
+// x in layout C, values < 4096.  Returns layout A, canonical.  tw from load_lane_twiddles_inv.
 __device__ __forceinline__ void intt_warp(uint32_t x[8], uint16_t *scratch, int lane, const LaneTwiddles &tw) {
-    // len = 2
-    const bool up = lane & 2;
+    // pass C -- len = 2.  inputs < 4096 <= 2q: sums < 8192, products < 2q
 #pragma unroll
-    for (int r = 0; r < 8; r++) {
-        uint32_t got = __shfl_xor_sync(kFullMask, x[r], 2);
-        // low lane: a + b ; upper lane: zeta (b - a) with a = got, b = own.  Inputs < 4096 -> bias 2q.
-        uint32_t d = mul_shoup(x[r] - got + 2 * kQ, tw.z2[r]);
-        x[r] = up ? d : (x[r] + got);  // bounds: low < 8192, up < 2q
+    for (int h = 0; h < 2; h++)
+#pragma unroll
+        for (int r = 0; r < 2; r++) gs_bfly(x[4 * h + r], x[4 * h + r + 2], tw.z2[h], 2 * kQ);
+    store_scratch_C(x, scratch, lane);
+    __syncwarp();
+    load_scratch_B(x, scratch, lane);
+    __syncwarp();
+    // pass B -- len = 4: inputs < 8192, sums < 16384; the bias must be a multiple of q >= 8191: 3q
+#pragma unroll
+    for (int h = 0; h < 4; h++) {
+        gs_bfly(x[2 * h], x[2 * h + 1], tw.z4[h], 3 * kQ);
+        x[2 * h] = barrett16(x[2 * h]);  // <= q, keeps the later sums below 2^16
     }
-    // len = 4, 8, 16 (layout B register bits 0, 1, 2).  All values are < 8192 here.
-    // len 4: a' < 16384; the bias must be a multiple of q that is >= the bound of a: 3q = 9987
-#pragma unroll
-    for (int h = 0; h < 4; h++) gs_bfly(x[2 * h], x[2 * h + 1], tw.z4[h], 3 * kQ);
-    // after len 4: a < 16384, b < 2q.  reduce a to keep the sums below 2^16 later on
-#pragma unroll
-    for (int h = 0; h < 4; h++) x[2 * h] = barrett16(x[2 * h]);  // <= q
-    // len 8: inputs < 2q (6658): a' < 4q ; bias 2q
+    // len = 8: inputs < 2q: sums < 4q, bias 2q
 #pragma unroll
     for (int h = 0; h < 2; h++)
 #pragma unroll
         for (int r = 0; r < 2; r++) gs_bfly(x[4 * h + r], x[4 * h + r + 2], tw.z8[h], 2 * kQ);
-    // len 16: inputs < 4q: a' < 8q ; bias 4q
+    // len = 16: inputs < 4q: sums < 8q, bias 4q
 #pragma unroll
     for (int r = 0; r < 4; r++) gs_bfly(x[r], x[r + 4], tw.z16, 4 * kQ);
-    // values < 8q = 26632 < 2^16: transpose B -> A
-#pragma unroll
-    for (int r = 0; r < 8; r++) scratch[pidx(idxB(lane, r))] = (uint16_t)x[r];
+    store_scratch_B(x, scratch, lane);  // < 8q = 26632
     __syncwarp();
-#pragma unroll
-    for (int r = 0; r < 8; r++) x[r] = scratch[pidx(idxA(lane, r))];
+    load_scratch_A(x, scratch, lane);
     __syncwarp();
-    // len = 32: inputs < 8q: a' < 16q = 53264 < 2^16, bias 8q ; then reduce the sums
+    // pass A -- len = 32: inputs < 8q: sums < 16q = 53264 < 2^16, bias 8q; reduce the sums
 #pragma unroll
     for (int h = 0; h < 4; h++) {
         gs_bfly(x[2 * h], x[2 * h + 1], c_tw.zeta[7 - h], 8 * kQ);
-        x[2 * h] = barrett16(x[2 * h]);  // <= q
+        x[2 * h] = barrett16(x[2 * h]);
     }
-    // len = 64: inputs < 2q: a' < 4q, bias 2q
+    // len = 64: inputs < 2q: sums < 4q, bias 2q
 #pragma unroll
     for (int h = 0; h < 2; h++)
 #pragma unroll
@@ -390,6 +426,27 @@ __device__ __forceinline__ void pack8(const uint32_t v[8], uint8_t *dst) {
 #pragma unroll
     for (int b = 0; b < D; b++) dst[b] = (uint8_t)(b < 8 ? (lo >> (8 * b)) : (hi >> (8 * (b - 8))));
 }
+// Unpack the 8 d-bit values owned by `lane` (bits [8 d lane, 8 d lane + 8 d) of the row) from a packed row
+// in shared memory.  `row` must be 4-byte aligned and readable up to 4 bytes past its end.
+template <int D>
+__device__ __forceinline__ void unpack8(const uint8_t *row, int lane, uint32_t v[8]) {
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(row);
+    const int bit = 8 * D * lane, wi = bit >> 5, s = bit & 31;
+    constexpr int NA = (8 * D + 31) / 32;  // aligned words holding the lane's 8 d bits
+    uint32_t raw[NA + 1], a[NA + 1];
+#pragma unroll
+    for (int k = 0; k <= NA; k++) raw[k] = ((8 * D) % 32 == 0 && k == NA) ? 0u : w[wi + k];  // s == 0 when 8d is a word multiple
+#pragma unroll
+    for (int k = 0; k < NA; k++) a[k] = ((8 * D) % 32 == 0) ? raw[k] : __funnelshift_r(raw[k], raw[k + 1], s);
+    a[NA] = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const int o = D * i, k = o >> 5, sh = o & 31;
+        uint32_t f = (sh + D <= 32) ? (a[k] >> sh) : __funnelshift_r(a[k], a[k + 1], sh);
+        v[i] = f & ((1u << D) - 1u);
+    }
+}
+
 // Extract the d-bit value of coefficient c from a little-endian packed byte string (shared or global).
 template <int D>
 __device__ __forceinline__ uint32_t unpack1(const uint8_t *src, int c) {

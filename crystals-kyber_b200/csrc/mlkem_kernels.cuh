@@ -34,7 +34,7 @@ using P1024 = ParamSet<4, 2, 2, 11, 5>;
 
 constexpr int kHashTPB = 128;   // threads per block of the thread-per-item hash kernels
 constexpr int kNoiseTPB = 128;  // threads (= sponges) per block of k_noise
-constexpr int kSlotWords = 137; // shared-memory words per sampled polynomial slot (odd: conflict-free per-thread writes)
+constexpr int kSlotWords = 129; // shared-memory words per sampled polynomial slot (odd: conflict-free per-thread writes)
 
 // =================================================================================================
 // Hash kernels: one item per thread
@@ -250,41 +250,13 @@ __device__ __forceinline__ void prf_cbd_codes(const Lane seed[4], uint32_t nonce
     }
 }
 
-// Store a polynomial held in layout B as 128 coalesced 32-bit words (coefficient pairs) at `dst`.
-__device__ __forceinline__ void store_layoutB_global(const uint32_t x[8], uint16_t *scratch, int lane, uint32_t *dst) {
-#pragma unroll
-    for (int r = 0; r < 8; r++) scratch[pidx(idxB(lane, r))] = (uint16_t)x[r];
-    __syncwarp();
-    const uint32_t *sw = reinterpret_cast<const uint32_t *>(scratch);
-#pragma unroll
-    for (int r = 0; r < 4; r++) {
-        int t = lane + 32 * r;  // pair index: coefficients 2t, 2t+1
-        dst[t] = sw[pidx(2 * t) >> 1];
-    }
-    __syncwarp();
+// A polynomial in layout C is one 16-byte vector per lane: natural-order global stores / loads are single
+// fully coalesced 128-bit accesses (512 contiguous bytes per warp).
+__device__ __forceinline__ void store_layoutC_global(const uint32_t x[8], int lane, uint16_t *dst) {
+    reinterpret_cast<uint4 *>(dst)[lane] = pack_pairs(x);
 }
-// Same for layout A.
-__device__ __forceinline__ void store_layoutA_global(const uint32_t x[8], uint16_t *scratch, int lane, uint32_t *dst) {
-#pragma unroll
-    for (int r = 0; r < 8; r++) scratch[pidx(idxA(lane, r))] = (uint16_t)x[r];
-    __syncwarp();
-    const uint32_t *sw = reinterpret_cast<const uint32_t *>(scratch);
-#pragma unroll
-    for (int r = 0; r < 4; r++) {
-        int t = lane + 32 * r;
-        dst[t] = sw[pidx(2 * t) >> 1];
-    }
-    __syncwarp();
-}
-// Load 128 coalesced words (coefficient pairs) from `src` into the padded scratch.
-__device__ __forceinline__ void load_global_to_scratch(const uint32_t *src, uint16_t *scratch, int lane) {
-    uint32_t *sw = reinterpret_cast<uint32_t *>(scratch);
-#pragma unroll
-    for (int r = 0; r < 4; r++) {
-        int t = lane + 32 * r;
-        sw[pidx(2 * t) >> 1] = src[t];
-    }
-    __syncwarp();
+__device__ __forceinline__ void load_layoutC_global(uint32_t x[8], int lane, const uint16_t *src) {
+    unpack_pairs(__ldg(reinterpret_cast<const uint4 *>(src) + lane), x);
 }
 
 // Grid: (ceil(n / kNoiseTPB), npoly).  Thread = one (item, nonce) sponge; blockIdx.y selects the nonce,
@@ -322,7 +294,7 @@ __global__ void __launch_bounds__(kNoiseTPB) k_noise(int n, const uint8_t *__res
                 x[r] = noise_code_to_coeff((codes[c >> 3] >> (4 * (c & 7))) & 15u);
             }
             ntt_warp(x, scratch, lane, tw);
-            store_layoutB_global(x, scratch, lane, reinterpret_cast<uint32_t *>(out16 + out16_stride * it + 256 * p));
+            store_layoutC_global(x, lane, out16 + out16_stride * it + 256 * p);
         }
     } else {
         if (item >= n) return;
@@ -344,14 +316,58 @@ __global__ void __launch_bounds__(kNoiseTPB) k_noise(int n, const uint8_t *__res
 // (= groups that may be consumed by a successful run); tests lower it to exercise the restart path.
 //
 // Returns with 256 canonical coefficients in slot[0..255]; b32/b33 are updated like the caller's buffer.
+//
+// Parsing cost matters (112 candidates per block against 4320 instructions per permutation), so the
+// inner loop is arranged for the alu pipe: the 12-bit field is moved to the top of a register (a multiply
+// by a power of two on the fma pipe, or one funnel shift when it straddles two words), compared there
+// against q << 20 without masking, and stored through a running shared-memory address.  Bounds are only
+// checked in blocks that can complete the polynomial (CHECKED); the give-up rule is applied by
+// overwriting the groups beyond the limit with 0xFFF fields, which are always rejected.
+template <bool CHECKED>
+__device__ __forceinline__ void parse_block(const Lane a[25], uint32_t &addr, uint32_t end_addr) {
+#pragma unroll
+    for (int ch = 0; ch < 7; ch++) {  // 3 lanes = 6 words = 16 candidates
+        const uint32_t w[7] = {a[3 * ch].lo, a[3 * ch].hi, a[3 * ch + 1].lo, a[3 * ch + 1].hi, a[3 * ch + 2].lo, a[3 * ch + 2].hi, 0u};
+#pragma unroll
+        for (int m = 0; m < 16; m++) {  // candidate m = bits [12 m, 12 m + 12): d1 / d2 of group m / 2 (ml_kem.c:208-209)
+            const int bit = 12 * m, wi = bit >> 5, sh = bit & 31;
+            uint32_t t;  // the field in bits [20, 32), don't-care bits below
+            if (sh == 20) t = w[wi];
+            else if (sh < 20) t = w[wi] * (1u << (20 - sh));
+            else t = __funnelshift_r(w[wi], w[wi + 1], sh - 20);
+            bool ok = t < (kQ << 20);                         // d < q  (:211, :216)
+            if (CHECKED) ok = ok && (addr < end_addr);         // j < N  (:203, :216)
+            uint32_t d;
+            asm("mul.hi.u32 %0, %1, 4096;" : "=r"(d) : "r"(t));  // t >> 20 on the fma pipe
+            if (ok) {
+                asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"((uint16_t)d) : "memory");
+                addr += 2;
+            }
+        }
+    }
+}
+
+// Replace every three-byte group of the block at index >= usable by 0xFFFFFF (both candidates rejected).
+__device__ __forceinline__ void mask_groups(Lane a[25], int usable) {
+    const int cut = 24 * max(usable, 0);
+#pragma unroll
+    for (int k = 0; k < 42; k++) {
+        const int lo = 32 * k;
+        uint32_t m = cut <= lo ? 0xFFFFFFFFu : (cut >= lo + 32 ? 0u : (0xFFFFFFFFu << (cut - lo)));
+        if (k & 1) a[k >> 1].hi |= m;
+        else a[k >> 1].lo |= m;
+    }
+}
+
 __device__ __forceinline__ void sample_ntt_thread(const Lane rho[4], uint32_t &b32, uint32_t &b33, uint16_t *slot, bool active,
                                                   int group_limit) {
     Lane a[25];
-    int j = active ? 0 : kN;  // inactive lanes (beyond the batch) just follow along
+    const uint32_t base = (uint32_t)__cvta_generic_to_shared(slot), end_addr = base + 2 * kN;
+    uint32_t addr = active ? base : end_addr;  // inactive lanes (beyond the batch) just follow along
     int groups_left = 0;
     bool need_init = true;
     // Loop until every lane of the warp holds a full polynomial.
-    while (__any_sync(kFullMask, j < kN)) {
+    while (__any_sync(kFullMask, addr < end_addr)) {
         if (need_init) {  // XOF.Init + Absorb(rho || b32 || b33), ml_kem.c:200-201
             keccak_zero(a);
 #pragma unroll
@@ -361,27 +377,22 @@ __device__ __forceinline__ void sample_ntt_thread(const Lane rho[4], uint32_t &b
             groups_left = group_limit;
             need_init = false;
         }
-        keccak_f1600(a);
-        // one 168-byte block = 56 three-byte groups = 7 chunks of 3 lanes (16 candidates each)
-#pragma unroll
-        for (int ch = 0; ch < 7; ch++) {
-            uint32_t w[6] = {a[3 * ch].lo, a[3 * ch].hi, a[3 * ch + 1].lo, a[3 * ch + 1].hi, a[3 * ch + 2].lo, a[3 * ch + 2].hi};
-#pragma unroll
-            for (int g = 0; g < 8; g++) {  // group g of the chunk = 24 bits at bit offset 24 g
-                const int bit = 24 * g, wi = bit >> 5, sh = bit & 31;
-                uint32_t v = sh <= 8 ? (w[wi] >> sh) : __funnelshift_r(w[wi], w[wi + (wi < 5 ? 1 : 0)], sh);
-                uint32_t d1 = v & 0xFFFu, d2 = (v >> 12) & 0xFFFu;  // ml_kem.c:208-209
-                bool live = groups_left > 0;
-                if (live && d1 < kQ && j < kN) slot[j++] = (uint16_t)d1;  // :211-214
-                if (live && d2 < kQ && j < kN) slot[j++] = (uint16_t)d2;  // :216-219
-                groups_left -= 1;
-            }
+        keccak_f1600(a);  // one 168-byte block = 56 three-byte groups
+        const bool running = addr < end_addr;
+        // give-up rule (:221-227): only `groups_left` more groups may be consumed.  Rare (block 5 with the
+        // reference's limit), so it is handled by masking; safe in place because such a lane either completes
+        // within this block or restarts from a fresh state.
+        if (__any_sync(kFullMask, running && groups_left < 56)) {
+            if (running && groups_left < 56) mask_groups(a, groups_left);
         }
-        // give-up rule (:221-227,237-242): out of groups without a full polynomial -> bump the seed, restart
-        if (groups_left <= 0 && j < kN) {
+        if (__all_sync(kFullMask, addr + 2 * 112 <= end_addr)) parse_block<false>(a, addr, end_addr);
+        else parse_block<true>(a, addr, end_addr);
+        groups_left -= 56;
+        // (:237-242) out of groups without a full polynomial -> bump the seed in the caller's buffer, restart
+        if (groups_left <= 0 && addr < end_addr) {
             b32 = (b32 + 1) & 0xFFu;
             b33 = (b33 + 1) & 0xFFu;
-            j = 0;
+            addr = base;
             need_init = true;
         }
     }
@@ -411,12 +422,20 @@ struct MatvecArgs {
     uint32_t *flags;         // EncryptCompare: flags[i] |= 1 when a re-encrypted row differs
 };
 
+// Dynamic shared memory of k_sample_matvec: 32 K sampling slots, then per warp a 512-byte transform scratch
+// and a 384-byte staging row for the packed output.
+constexpr int kMatvecWarpBytes = 512 + 384;
+template <class P>
+constexpr size_t matvec_smem_bytes() {
+    return (size_t)32 * P::K * kSlotWords * 4 + 16 + (size_t)P::K * kMatvecWarpBytes;
+}
+
 // Block = 32 K threads = 32 (item,row) groups x K matrix columns.  Phase 1: each thread samples one matrix
 // entry into its slot.  Phase 2: each warp takes groups round-robin and finishes the row.
 template <class P, int MODE>
 __global__ void __launch_bounds__(32 * P::K) k_sample_matvec(MatvecArgs g) {
     constexpr int K = P::K;
-    extern __shared__ __align__(16) uint32_t s_slots[];  // 32 K slots of kSlotWords words
+    extern __shared__ __align__(16) uint32_t s_slots[];  // 32 K slots of kSlotWords words, then the per-warp areas
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     {
         const int grp = tid / K, col = tid - grp * K;
@@ -433,19 +452,22 @@ __global__ void __launch_bounds__(32 * P::K) k_sample_matvec(MatvecArgs g) {
     }
     __syncthreads();
 
+    uint8_t *warp_area = reinterpret_cast<uint8_t *>(s_slots) + (((size_t)32 * K * kSlotWords * 4 + 15) & ~(size_t)15) + warp * kMatvecWarpBytes;
+    uint16_t *scratch = reinterpret_cast<uint16_t *>(warp_area);
+    uint8_t *stage = warp_area + 512;
     uint2 gam[4];
 #pragma unroll
-    for (int r = 0; r < 4; r++) gam[r] = c_tw.gamma[lane + 32 * r];
+    for (int r = 0; r < 4; r++) gam[r] = lane_gamma(lane + 32 * r);
     LaneTwiddles tw;
     if (MODE != kModeKeyGen) load_lane_twiddles_inv(tw, lane);
-    uint32_t diff = 0;
 
     for (int grp = warp; grp < 32; grp += K) {
         const long long gg = (long long)blockIdx.x * 32 + grp;
         const int item = (int)(gg / K), row = (int)(gg - (long long)item * K);
         if (item >= g.n) break;  // groups are ordered by item
-        uint32_t *slot0 = s_slots + kSlotWords * (grp * K);
-        // ---- row . vector in the NTT domain (ml_kem.c:618 VectorMultiply), lazily accumulated
+        const uint32_t *slot0 = s_slots + kSlotWords * (grp * K);
+        // ---- row . vector in the NTT domain (ml_kem.c:618 VectorMultiply), lazily accumulated.
+        // Lane handles coefficient pairs t = lane + 32 r (conflict-free slot reads, coalesced vector reads).
         uint32_t acc[8];
 #pragma unroll
         for (int r = 0; r < 8; r++) acc[r] = 0;
@@ -460,10 +482,6 @@ __global__ void __launch_bounds__(32 * P::K) k_sample_matvec(MatvecArgs g) {
                 basemul_acc(acc[2 * r], acc[2 * r + 1], a & 0xFFFFu, a >> 16, b & 0xFFFFu, b >> 16, gam[r]);
             }
         }
-#pragma unroll
-        for (int r = 0; r < 8; r++) acc[r] = canon32(acc[r]);
-        __syncwarp();  // every lane is done reading the group's slots: they become scratch from here on
-        uint8_t *stage = reinterpret_cast<uint8_t *>(slot0 + kSlotWords);  // slot 1 of the group: packed bytes
         int nwords;
         if (MODE == kModeKeyGen) {
             // t^[row] = A[row] . s^ + e^[row]   (ml_kem.c:723-727), then ByteEncode12 (:736-742)
@@ -472,7 +490,7 @@ __global__ void __launch_bounds__(32 * P::K) k_sample_matvec(MatvecArgs g) {
             for (int r = 0; r < 4; r++) {
                 int t = lane + 32 * r;
                 uint32_t e = __ldg(ev + t);
-                uint32_t c0 = csubq(acc[2 * r] + (e & 0xFFFFu)), c1 = csubq(acc[2 * r + 1] + (e >> 16));
+                uint32_t c0 = csubq(canon32(acc[2 * r]) + (e & 0xFFFFu)), c1 = csubq(canon32(acc[2 * r + 1]) + (e >> 16));
                 uint32_t v = c0 | (c1 << 12);
                 stage[3 * t] = (uint8_t)v;
                 stage[3 * t + 1] = (uint8_t)(v >> 8);
@@ -481,17 +499,15 @@ __global__ void __launch_bounds__(32 * P::K) k_sample_matvec(MatvecArgs g) {
             nwords = 96;
         } else {
             // u[row] = InverseNTT(At[row] . y^) + e1[row]  (ml_kem.c:854-864); Compress_du + ByteEncode_du (:886-896)
-            uint16_t *scratch = reinterpret_cast<uint16_t *>(slot0);
-            uint32_t *sw = slot0;
+            uint32_t *sw = reinterpret_cast<uint32_t *>(scratch);
 #pragma unroll
             for (int r = 0; r < 4; r++) {
                 int t = lane + 32 * r;
-                sw[pidx(2 * t) >> 1] = acc[2 * r] | (acc[2 * r + 1] << 16);
+                sw[sidx(2 * t) >> 1] = canon32(acc[2 * r]) | (canon32(acc[2 * r + 1]) << 16);
             }
             __syncwarp();
             uint32_t x[8];
-#pragma unroll
-            for (int r = 0; r < 8; r++) x[r] = scratch[pidx(idxB(lane, r))];
+            load_scratch_C(x, scratch, lane);
             __syncwarp();
             intt_warp(x, scratch, lane, tw);
             const uint32_t *codes = g.addc + g.addc_stride * item + 32 * row;
@@ -499,13 +515,11 @@ __global__ void __launch_bounds__(32 * P::K) k_sample_matvec(MatvecArgs g) {
             for (int r = 0; r < 8; r++) {
                 uint32_t e = noise_code_to_coeff((__ldg(codes + (lane >> 3) + 4 * r) >> (4 * (lane & 7))) & 15u);
                 x[r] = compress<P::DU>(csubq(x[r] + e));
-                scratch[pidx(idxA(lane, r))] = (uint16_t)x[r];
             }
+            store_scratch_A(x, scratch, lane);
             __syncwarp();
-            uint32_t v8[8];
-#pragma unroll
-            for (int i = 0; i < 8; i++) v8[i] = scratch[pidx(8 * lane + i)];
-            pack8<P::DU>(v8, stage + P::DU * lane);
+            load_scratch_C(x, scratch, lane);
+            pack8<P::DU>(x, stage + P::DU * lane);
             nwords = 8 * P::DU;
         }
         __syncwarp();
@@ -517,7 +531,6 @@ __global__ void __launch_bounds__(32 * P::K) k_sample_matvec(MatvecArgs g) {
             for (int w = lane; w < nwords; w += 32) d |= stw[w] ^ __ldg(cw + w);
             d = __any_sync(kFullMask, d != 0) ? 1u : 0u;
             if (lane == 0) atomicOr(g.flags + item, d);  // unconditional: no data-dependent control flow
-            diff |= d;
         } else {
             uint32_t *ow = reinterpret_cast<uint32_t *>(g.out + g.out_stride * item + row_off);
             for (int w = lane; w < nwords; w += 32) ow[w] = stw[w];
@@ -528,7 +541,6 @@ __global__ void __launch_bounds__(32 * P::K) k_sample_matvec(MatvecArgs g) {
         }
         __syncwarp();
     }
-    (void)diff;
 }
 
 // =================================================================================================
@@ -551,66 +563,63 @@ struct EncVArgs {
     uint32_t *flags;
 };
 
+// Copy `bytes` (multiple of 16) from global to this warp's shared staging area with 128-bit accesses.
+__device__ __forceinline__ void stage_row(uint8_t *dst, const uint8_t *src, int bytes, int lane) {
+    const uint4 *s4 = reinterpret_cast<const uint4 *>(src);
+    uint4 *d4 = reinterpret_cast<uint4 *>(dst);
+    for (int i = lane; i < bytes / 16; i += 32) d4[i] = __ldg(s4 + i);
+}
+
 // v = InverseNTT(t^ . y^) + e2 + Decompress_1(m)  (ml_kem.c:867-880); c2 = ByteEncode_dv(Compress_dv(v)) (:899-904).
-// Also copies rho into nothing: purely the v row.  COMPARE: OR the mismatch into flags instead of storing.
+// One item per warp; every lane owns 8 consecutive coefficients (= 12 bytes of each ByteEncode12 row).
+// COMPARE: OR the mismatch against the received ciphertext into flags instead of storing.
 template <class P, bool COMPARE>
 __global__ void __launch_bounds__(kWarpTPB) k_encrypt_v(EncVArgs g) {
-    constexpr int K = P::K;
-    __shared__ __align__(16) uint16_t s_scratch[(kWarpTPB / 32) * kScratchU16];
-    __shared__ __align__(16) uint8_t s_stage[(kWarpTPB / 32) * 32 * P::DV];
+    constexpr int K = P::K, NW = kWarpTPB / 32;
+    __shared__ __align__(16) uint16_t s_scratch[NW * kScratchU16];
+    __shared__ __align__(16) uint8_t s_rows[NW * (384 * K + 16)];
+    __shared__ __align__(16) uint8_t s_stage[NW * 32 * P::DV];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int item = blockIdx.x * (kWarpTPB / 32) + warp;
-    if (item >= g.n) return;
     uint16_t *scratch = s_scratch + warp * kScratchU16;
+    uint8_t *rows = s_rows + warp * (384 * K + 16);
     uint8_t *stage = s_stage + warp * 32 * P::DV;
     uint2 gam[4];
 #pragma unroll
-    for (int r = 0; r < 4; r++) gam[r] = c_tw.gamma[lane + 32 * r];
+    for (int i = 0; i < 4; i++) gam[i] = lane_gamma(4 * lane + i);
     LaneTwiddles tw;
     load_lane_twiddles_inv(tw, lane);
+  for (int item = blockIdx.x * NW + warp; item < g.n; item += gridDim.x * NW) {  // persistent warps
+    stage_row(rows, g.ek + g.ek_stride * item, 384 * K, lane);
+    __syncwarp();
 
-    const uint8_t *ek = g.ek + g.ek_stride * item;
-    const uint32_t *yv = reinterpret_cast<const uint32_t *>(g.yhat + g.yhat_stride * item);
+    const uint16_t *yv = g.yhat + g.yhat_stride * item;
     uint32_t acc[8];
 #pragma unroll
     for (int r = 0; r < 8; r++) acc[r] = 0;
 #pragma unroll
     for (int j = 0; j < K; j++) {
+        uint32_t t[8], y[8];
+        unpack8<12>(rows + 384 * j, lane, t);  // ByteDecode12 without reduction (ml_kem.c:806-808, D4)
+        load_layoutC_global(y, lane, yv + 256 * j);
 #pragma unroll
-        for (int r = 0; r < 4; r++) {
-            int t = lane + 32 * r;
-            const uint8_t *p = ek + 384 * j + 3 * t;  // ByteDecode12 without reduction (ml_kem.c:806-808, D4)
-            uint32_t v = (uint32_t)__ldg(p) | ((uint32_t)__ldg(p + 1) << 8) | ((uint32_t)__ldg(p + 2) << 16);
-            uint32_t b = __ldg(yv + 128 * j + t);
-            basemul_acc(acc[2 * r], acc[2 * r + 1], v & 0xFFFu, v >> 12, b & 0xFFFFu, b >> 16, gam[r]);
-        }
+        for (int i = 0; i < 4; i++) basemul_acc(acc[2 * i], acc[2 * i + 1], t[2 * i], t[2 * i + 1], y[2 * i], y[2 * i + 1], gam[i]);
     }
-    uint32_t *sw = reinterpret_cast<uint32_t *>(scratch);
-#pragma unroll
-    for (int r = 0; r < 4; r++) {
-        int t = lane + 32 * r;
-        sw[pidx(2 * t) >> 1] = canon32(acc[2 * r]) | (canon32(acc[2 * r + 1]) << 16);
-    }
-    __syncwarp();
     uint32_t x[8];
 #pragma unroll
-    for (int r = 0; r < 8; r++) x[r] = scratch[pidx(idxB(lane, r))];
-    __syncwarp();
-    intt_warp(x, scratch, lane, tw);
+    for (int r = 0; r < 8; r++) x[r] = canon32(acc[r]);
+    intt_warp(x, scratch, lane, tw);  // layout C in, layout A out
     const uint32_t *codes = g.addc + g.addc_stride * item + 32 * K;
     const uint32_t *mw = reinterpret_cast<const uint32_t *>(g.m + 32 * (size_t)item);
 #pragma unroll
     for (int r = 0; r < 8; r++) {
         uint32_t e = noise_code_to_coeff((__ldg(codes + (lane >> 3) + 4 * r) >> (4 * (lane & 7))) & 15u);
         uint32_t mu = ((__ldg(mw + r) >> lane) & 1u) * 1665u;  // Decompress_1(bit) = 1665 bit (ml_kem.c:867-870)
-        uint32_t v = csubq(csubq(x[r] + e) + mu);
-        scratch[pidx(idxA(lane, r))] = (uint16_t)compress<P::DV>(v);
+        x[r] = compress<P::DV>(csubq(csubq(x[r] + e) + mu));
     }
+    store_scratch_A(x, scratch, lane);
     __syncwarp();
-    uint32_t v8[8];
-#pragma unroll
-    for (int i = 0; i < 8; i++) v8[i] = scratch[pidx(8 * lane + i)];
-    pack8<P::DV>(v8, stage + P::DV * lane);
+    load_scratch_C(x, scratch, lane);
+    pack8<P::DV>(x, stage + P::DV * lane);
     __syncwarp();
     const uint32_t *stw = reinterpret_cast<const uint32_t *>(stage);
     const size_t off = (size_t)P::C1ROW * K;
@@ -624,71 +633,66 @@ __global__ void __launch_bounds__(kWarpTPB) k_encrypt_v(EncVArgs g) {
         uint32_t *ow = reinterpret_cast<uint32_t *>(g.c + g.c_stride * item + off);
         for (int w = lane; w < 8 * P::DV; w += 32) ow[w] = stw[w];
     }
+    __syncwarp();
+  }
 }
 
-// ml_kem.c:942 PKE_Decrypt: m' = ByteEncode_1(Compress_1(v - InverseNTT(s^ . NTT(u)))).
+// ml_kem.c:942 PKE_Decrypt: m' = ByteEncode_1(Compress_1(v - InverseNTT(s^ . NTT(u)))).  One item per warp; the
+// ciphertext and the ByteEncode12 rows of s^ are staged in shared memory with 128-bit loads.
 template <class P>
 __global__ void __launch_bounds__(kWarpTPB) k_decrypt(int n, const uint8_t *__restrict__ dk, size_t dk_stride,
                                                       const uint8_t *__restrict__ c, uint8_t *__restrict__ mout) {
-    constexpr int K = P::K;
-    __shared__ __align__(16) uint16_t s_scratch[(kWarpTPB / 32) * kScratchU16];
+    constexpr int K = P::K, NW = kWarpTPB / 32;
+    __shared__ __align__(16) uint16_t s_scratch[NW * kScratchU16];
+    __shared__ __align__(16) uint8_t s_ct[NW * (P::C + 16)];
+    __shared__ __align__(16) uint8_t s_sk[NW * (384 * K + 16)];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int item = blockIdx.x * (kWarpTPB / 32) + warp;
-    if (item >= n) return;
     uint16_t *scratch = s_scratch + warp * kScratchU16;
-    const uint32_t *sw = reinterpret_cast<const uint32_t *>(scratch);
+    uint8_t *ct = s_ct + warp * (P::C + 16), *sk = s_sk + warp * (384 * K + 16);
     uint2 gam[4];
 #pragma unroll
-    for (int r = 0; r < 4; r++) gam[r] = c_tw.gamma[lane + 32 * r];
-    LaneTwiddles tw;
+    for (int i = 0; i < 4; i++) gam[i] = lane_gamma(4 * lane + i);
+    LaneTwiddles tw, twi;
     load_lane_twiddles(tw, lane);
-    const uint8_t *ci = c + (size_t)P::C * item;
-    const uint8_t *sk = dk + dk_stride * item;
+    load_lane_twiddles_inv(twi, lane);
+  for (int item = blockIdx.x * NW + warp; item < n; item += gridDim.x * NW) {  // persistent warps
+    stage_row(ct, c + (size_t)P::C * item, P::C, lane);
+    stage_row(sk, dk + dk_stride * item, 384 * K, lane);
+    __syncwarp();
     uint32_t acc[8];
 #pragma unroll
     for (int r = 0; r < 8; r++) acc[r] = 0;
     for (int i = 0; i < K; i++) {
         // u^[i] = NTT(Decompress_du(ByteDecode_du(c1[i])))   (ml_kem.c:978-987)
-        uint32_t x[8];
+        uint32_t x[8], sh[8];
+        unpack8<P::DU>(ct + P::C1ROW * i, lane, x);
 #pragma unroll
-        for (int r = 0; r < 8; r++) x[r] = decompress<P::DU>(unpack1<P::DU>(ci + P::C1ROW * i, idxA(lane, r)));
-        ntt_warp(x, scratch, lane, tw);
-#pragma unroll
-        for (int r = 0; r < 8; r++) scratch[pidx(idxB(lane, r))] = (uint16_t)x[r];
+        for (int r = 0; r < 8; r++) x[r] = decompress<P::DU>(x[r]);
+        store_scratch_C(x, scratch, lane);
         __syncwarp();
-#pragma unroll
-        for (int r = 0; r < 4; r++) {
-            int t = lane + 32 * r;
-            const uint8_t *p = sk + 384 * i + 3 * t;  // s^[i] = ByteDecode12(dk_pke[i]) (ml_kem.c:996-998)
-            uint32_t s = (uint32_t)__ldg(p) | ((uint32_t)__ldg(p + 1) << 8) | ((uint32_t)__ldg(p + 2) << 16);
-            uint32_t u = sw[pidx(2 * t) >> 1];
-            basemul_acc(acc[2 * r], acc[2 * r + 1], s & 0xFFFu, s >> 12, u & 0xFFFFu, u >> 16, gam[r]);
-        }
+        load_scratch_A(x, scratch, lane);
         __syncwarp();
-    }
-    uint32_t *sww = reinterpret_cast<uint32_t *>(scratch);
+        ntt_warp(x, scratch, lane, tw);  // layout C out: 8 consecutive coefficients = 4 base-case pairs
+        unpack8<12>(sk + 384 * i, lane, sh);  // s^[i] = ByteDecode12(dk_pke[i]) (ml_kem.c:996-998), no reduction
 #pragma unroll
-    for (int r = 0; r < 4; r++) {
-        int t = lane + 32 * r;
-        sww[pidx(2 * t) >> 1] = canon32(acc[2 * r]) | (canon32(acc[2 * r + 1]) << 16);
+        for (int p = 0; p < 4; p++) basemul_acc(acc[2 * p], acc[2 * p + 1], sh[2 * p], sh[2 * p + 1], x[2 * p], x[2 * p + 1], gam[p]);
     }
-    __syncwarp();
     uint32_t x[8];
 #pragma unroll
-    for (int r = 0; r < 8; r++) x[r] = scratch[pidx(idxB(lane, r))];
-    __syncwarp();
-    load_lane_twiddles_inv(tw, lane);
-    intt_warp(x, scratch, lane, tw);
+    for (int r = 0; r < 8; r++) x[r] = canon32(acc[r]);
+    intt_warp(x, scratch, lane, twi);
     // w = v - x (ml_kem.c:1001-1003), m' bit = Compress_1(w) (:1009-1012); coefficient lane+32r is bit lane of word r
     uint32_t myword = 0;
 #pragma unroll
     for (int r = 0; r < 8; r++) {
-        uint32_t v = decompress<P::DV>(unpack1<P::DV>(ci + P::C1ROW * K, idxA(lane, r)));
+        uint32_t v = decompress<P::DV>(unpack1<P::DV>(ct + P::C1ROW * K, idxA(lane, r)));
         uint32_t w = csubq(v + kQ - x[r]);
         uint32_t word = __ballot_sync(kFullMask, compress<1>(w) & 1u);
         if (lane == r) myword = word;
     }
     if (lane < 8) reinterpret_cast<uint32_t *>(mout + 32 * (size_t)item)[lane] = myword;
+    __syncwarp();
+  }
 }
 
 // KeyGen: dk_pke rows = ByteEncode12(s^[i]) (ml_kem.c:750-756), plus the rho / ek-tail copies.
@@ -731,6 +735,8 @@ __global__ void __launch_bounds__(kWarpTPB) k_keygen_encode_s(int n, const uint1
 constexpr int kPrimTPB = 256;  // 8 polynomials per block
 
 // ml_kem.c:287 NTT over n polynomials of 256 uint16 (natural order in, natural order out).
+// Loads: 8 x 16-bit per lane in layout A (each warp instruction reads 64 contiguous bytes); stores: one
+// 128-bit vector per lane (layout C = natural order).
 __global__ void __launch_bounds__(kPrimTPB) k_ntt_batch(int n, const uint16_t *__restrict__ in, uint16_t *__restrict__ out) {
     __shared__ __align__(16) uint16_t s_scratch[(kPrimTPB / 32) * kScratchU16];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -738,16 +744,15 @@ __global__ void __launch_bounds__(kPrimTPB) k_ntt_batch(int n, const uint16_t *_
     LaneTwiddles tw;
     load_lane_twiddles(tw, lane);
     for (long long p = (long long)blockIdx.x * (kPrimTPB / 32) + warp; p < n; p += (long long)gridDim.x * (kPrimTPB / 32)) {
-        load_global_to_scratch(reinterpret_cast<const uint32_t *>(in + 256 * p), scratch, lane);
+        const uint16_t *src = in + 256 * p;
         uint32_t x[8];
 #pragma unroll
-        for (int r = 0; r < 8; r++) x[r] = scratch[pidx(idxA(lane, r))] & 0xFFFu;
-        __syncwarp();
+        for (int r = 0; r < 8; r++) x[r] = __ldg(src + idxA(lane, r)) & 0xFFFu;
         ntt_warp(x, scratch, lane, tw);
-        store_layoutB_global(x, scratch, lane, reinterpret_cast<uint32_t *>(out + 256 * p));
+        store_layoutC_global(x, lane, out + 256 * p);
     }
 }
-// ml_kem.c:336 InverseNTT.
+// ml_kem.c:336 InverseNTT: 128-bit loads (layout C), 16-bit stores in layout A.
 __global__ void __launch_bounds__(kPrimTPB) k_intt_batch(int n, const uint16_t *__restrict__ in, uint16_t *__restrict__ out) {
     __shared__ __align__(16) uint16_t s_scratch[(kPrimTPB / 32) * kScratchU16];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -755,13 +760,14 @@ __global__ void __launch_bounds__(kPrimTPB) k_intt_batch(int n, const uint16_t *
     LaneTwiddles tw;
     load_lane_twiddles_inv(tw, lane);
     for (long long p = (long long)blockIdx.x * (kPrimTPB / 32) + warp; p < n; p += (long long)gridDim.x * (kPrimTPB / 32)) {
-        load_global_to_scratch(reinterpret_cast<const uint32_t *>(in + 256 * p), scratch, lane);
         uint32_t x[8];
+        load_layoutC_global(x, lane, in + 256 * p);
 #pragma unroll
-        for (int r = 0; r < 8; r++) x[r] = scratch[pidx(idxB(lane, r))] & 0xFFFu;
-        __syncwarp();
+        for (int r = 0; r < 8; r++) x[r] &= 0xFFFu;
         intt_warp(x, scratch, lane, tw);
-        store_layoutA_global(x, scratch, lane, reinterpret_cast<uint32_t *>(out + 256 * p));
+        uint16_t *dst = out + 256 * p;
+#pragma unroll
+        for (int r = 0; r < 8; r++) dst[idxA(lane, r)] = (uint16_t)x[r];
     }
 }
 // ml_kem.c:415 MultiplyNTTs (operands may be any 12-bit value, D4).
@@ -770,7 +776,7 @@ __global__ void __launch_bounds__(kPrimTPB) k_mulntt_batch(int n, const uint16_t
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint2 gam[4];
 #pragma unroll
-    for (int r = 0; r < 4; r++) gam[r] = c_tw.gamma[lane + 32 * r];
+    for (int r = 0; r < 4; r++) gam[r] = lane_gamma(lane + 32 * r);
     for (long long p = (long long)blockIdx.x * (kPrimTPB / 32) + warp; p < n; p += (long long)gridDim.x * (kPrimTPB / 32)) {
         const uint32_t *fw = reinterpret_cast<const uint32_t *>(f + 256 * p), *gw = reinterpret_cast<const uint32_t *>(gq + 256 * p);
         uint32_t *hw = reinterpret_cast<uint32_t *>(h + 256 * p);
@@ -909,7 +915,7 @@ __global__ void __launch_bounds__(kPrimTPB) k_encode_batch(int n, const uint16_t
 }
 template <int D, bool DECOMPRESS>
 __global__ void __launch_bounds__(kPrimTPB) k_decode_batch(int n, const uint8_t *__restrict__ in, uint16_t *__restrict__ out) {
-    __shared__ __align__(16) uint8_t s_stage[(kPrimTPB / 32) * 32 * D];
+    __shared__ __align__(16) uint8_t s_stage[(kPrimTPB / 32) * 32 * D + 16];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint8_t *stage = s_stage + warp * 32 * D;
     for (long long p = (long long)blockIdx.x * (kPrimTPB / 32) + warp; p < n; p += (long long)gridDim.x * (kPrimTPB / 32)) {
@@ -918,11 +924,9 @@ __global__ void __launch_bounds__(kPrimTPB) k_decode_batch(int n, const uint8_t 
         for (int i = lane; i < 2 * D; i += 32) sv[i] = __ldg(iv + i);
         __syncwarp();
         uint32_t v[8];
+        unpack8<D>(stage, lane, v);
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
-            uint32_t c = unpack1<D>(stage, 8 * lane + i);
-            v[i] = DECOMPRESS ? decompress<D>(c) : c;
-        }
+        for (int i = 0; i < 8; i++) v[i] = DECOMPRESS ? decompress<D>(v[i]) : v[i];
         reinterpret_cast<uint4 *>(out + 256 * p)[lane] =
             make_uint4(v[0] | (v[1] << 16), v[2] | (v[3] << 16), v[4] | (v[5] << 16), v[6] | (v[7] << 16));
         __syncwarp();
