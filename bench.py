@@ -236,7 +236,6 @@ def main():
     sampler.start()
     time.sleep(0.3)
     launches0 = lib.mlkem_b200_launch_count()
-    kem.profile(True)  # two event records per kernel launch (~300 launches per step): negligible
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     t_wall0 = time.time()
@@ -246,12 +245,26 @@ def main():
     e1.record(stream)
     barrier()
     t_wall1 = time.time()
-    kem.profile(False)
     launches = lib.mlkem_b200_launch_count() - launches0
     ms = max_over_ranks(e0.elapsed_time(e1))
     clocks = sampler.summary(t_wall0, t_wall1)
-    prof = kem.profile_report()
     value = world * n * steps / (ms * 1e-3)
+
+    # ---- per-kernel durations: the same steps again with the chunks serialised on one stream (in the timed region
+    # above, kernels of different chunks overlap on two streams, so a kernel's own duration cannot be read there)
+    kem.set_streams(1)
+    kem.profile(True)
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    p0.record(stream)
+    for _ in range(steps):
+        step_device()
+    p1.record(stream)
+    barrier()
+    kem.profile(False)
+    kem.set_streams(2)
+    serial_ms = p0.elapsed_time(p1)
+    prof = kem.profile_report()
 
     # ---- correctness of what was just timed (outside the timed region)
     ok = torch.ones(n, dtype=torch.bool, device=dev)
@@ -329,6 +342,7 @@ def main():
                 "ms_per_step": 1e3 * e2e_s / steps, "path": "mlkem_b200_encaps_batch + mlkem_b200_decaps_batch with MLKEM_B200_MEM_HOST (pinned buffers)"},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
         "kernel_ms_per_step": {k: v["ms"] / steps for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])},
+        "serialized_ms_per_step": serial_ms / steps,
     }
 
     # ---- extras: the other numbers BASELINE's metric names (NTT polys/s, codec GB/s, KeyGen/s), rank 0 only

@@ -245,6 +245,9 @@ class MLKEM:
     def profile(self, enable: bool):
         self.lib.mlkem_b200_profile(1 if enable else 0)
 
+    def set_streams(self, n: int):
+        self.lib.mlkem_b200_set_streams(n)
+
     def profile_report(self):
         import json
 

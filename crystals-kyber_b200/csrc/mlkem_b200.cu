@@ -23,6 +23,7 @@ using namespace mlkem;
 
 thread_local char tl_error[512] = "";
 std::atomic<unsigned long long> g_launches{0};
+std::atomic<int> g_streams{2};  // streams that device-memory calls interleave their chunks on (1 = serial)
 
 #define CU(call)                                                                                              \
     do {                                                                                                      \
@@ -98,6 +99,7 @@ void build_tables(TwiddleTables &t, uint2 rc[24]) {
     for (unsigned i = 0; i < 128; i++) {
         t.zeta[i] = shoup_pair(pow17(bitrev7(i)));           // ml_kem.c:300-307
         t.gamma[i] = shoup_pair(pow17(2 * bitrev7(i) + 1));  // ml_kem.c:424-433
+        t.gamma32[i] = make_uint2(t.gamma[i].x, (unsigned)(((unsigned long long)t.gamma[i].x << 32) / kQ));
     }
     t.zeta_inv_last[0] = shoup_pair((t.zeta[1].x * 3303u) % kQ);  // ml_kem.c:378-381 folded into the last layer
     t.zeta_inv_last[1] = shoup_pair(3303u);
@@ -128,6 +130,7 @@ struct DeviceCtx {
     size_t ws_bytes[kSlots] = {0, 0};
     void *io[kSlots] = {nullptr, nullptr};  // device staging of host-resident inputs / outputs
     size_t io_bytes[kSlots] = {0, 0};
+    cudaEvent_t ev_fork = nullptr, ev_join[kSlots] = {nullptr, nullptr};
 };
 DeviceCtx g_ctx[kMaxDevices];
 std::mutex g_mutex;
@@ -177,6 +180,8 @@ int acquire(const mlkem_b200_opts *o, int *dev, DeviceCtx **ctx) {
         CU(cudaMemcpyToSymbol(g_tw, &t, sizeof t));
         CU(cudaMemcpyToSymbol(c_keccak_rc, rc, sizeof rc));
         for (int s = 0; s < kSlots; s++) CU(cudaStreamCreateWithFlags(&c.stream[s], cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&c.ev_fork, cudaEventDisableTiming));
+        for (int s = 0; s < kSlots; s++) CU(cudaEventCreateWithFlags(&c.ev_join[s], cudaEventDisableTiming));
         if (int r = allow_smem_matvec<P512>()) return r;
         if (int r = allow_smem_matvec<P768>()) return r;
         if (int r = allow_smem_matvec<P1024>()) return r;
@@ -364,18 +369,39 @@ int drive(const mlkem_b200_opts *o, size_t n, size_t ws_per_item, std::vector<Bu
         // NULL is the CUDA default stream (what torch hands over for its default stream), not a library stream:
         // the caller orders its own work against ours through the stream it names.
         cudaStream_t st = static_cast<cudaStream_t>(o->stream);
+        // Large batches are cut into chunks that alternate between the library's two streams (forked from and
+        // joined back into the caller's stream): the kernels of a chunk are a dependent chain that alternates
+        // between alu-bound hashing and fma-heavy polynomial arithmetic, so two chains in flight fill both pipes
+        // and each other's tails.
+        if (!(o && o->chunk_items > 0) && n >= ((size_t)1 << 16) && nchunks < 2 && g_streams.load() > 1) {
+            chunk = ((n + 1) / 2 + 1023) & ~(size_t)1023;
+        }
+        const size_t nch = (n + chunk - 1) / chunk;
+        const int nstreams = (nch >= 2 && g_streams.load() > 1) ? kSlots : 1;
         {
             std::lock_guard<std::mutex> lock(g_mutex);
-            if (int rc = ensure_buffer(&ctx->ws[0], &ctx->ws_bytes[0], chunk * ws_per_item + kWsSlack)) return rc;
+            for (int k = 0; k < nstreams; k++)
+                if (int rc = ensure_buffer(&ctx->ws[k], &ctx->ws_bytes[k], chunk * ws_per_item + kWsSlack)) return rc;
         }
-        for (size_t ci = 0; ci < nchunks; ci++) {
+        if (nstreams > 1) {
+            CU(cudaEventRecord(ctx->ev_fork, st));
+            for (int k = 0; k < kSlots; k++) CU(cudaStreamWaitEvent(ctx->stream[k], ctx->ev_fork, 0));
+        }
+        for (size_t ci = 0; ci < nch; ci++) {
             size_t i0 = ci * chunk, cn = (i0 + chunk <= n) ? chunk : n - i0;
             for (size_t b = 0; b < bufs.size(); b++) {
                 const uint8_t *base = static_cast<const uint8_t *>(bufs[b].in ? bufs[b].in : bufs[b].out);
                 ptrs[b] = const_cast<uint8_t *>(base) + i0 * bufs[b].item_bytes;
             }
-            Arena arena(ctx->ws[0]);
-            if (int rc = run(st, arena, (int)cn, ptrs.data())) return rc;
+            const int k = nstreams > 1 ? (int)(ci % kSlots) : 0;
+            Arena arena(ctx->ws[k]);
+            if (int rc = run(nstreams > 1 ? ctx->stream[k] : st, arena, (int)cn, ptrs.data())) return rc;
+        }
+        if (nstreams > 1) {
+            for (int k = 0; k < kSlots; k++) {
+                CU(cudaEventRecord(ctx->ev_join[k], ctx->stream[k]));
+                CU(cudaStreamWaitEvent(st, ctx->ev_join[k], 0));
+            }
         }
         return MLKEM_B200_OK;
     }

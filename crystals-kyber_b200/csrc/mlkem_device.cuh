@@ -33,7 +33,8 @@ constexpr uint32_t kFullMask = 0xFFFFFFFFu;
 struct TwiddleTables {
     uint2 zeta[128];
     uint2 zeta_inv_last[2];  // {zeta[1] * 3303 mod q, 3303}
-    uint2 gamma[128];
+    uint2 gamma[128];        // {w, floor(w 2^16 / q)}
+    uint2 gamma32[128];      // {w, floor(w 2^32 / q)} for mul_shoup_fma
 };
 // The library is a single translation unit (mlkem_b200.cu), so the tables are defined right here.
 // c_tw (constant bank) serves the warp-uniform lookups; g_tw (global memory, read through L1 with __ldg) serves
@@ -43,7 +44,7 @@ __constant__ TwiddleTables c_tw;
 __device__ TwiddleTables g_tw;
 __constant__ uint2 c_keccak_rc[24];
 __device__ __forceinline__ uint2 lane_zeta(int i) { return __ldg(&g_tw.zeta[i]); }
-__device__ __forceinline__ uint2 lane_gamma(int i) { return __ldg(&g_tw.gamma[i]); }
+__device__ __forceinline__ uint2 lane_gamma(int i) { return __ldg(&g_tw.gamma32[i]); }
 
 // ------------------------------------------------------------------------------------------------
 // 1. Field arithmetic
@@ -53,6 +54,12 @@ __device__ __forceinline__ uint2 lane_gamma(int i) { return __ldg(&g_tw.gamma[i]
 __device__ __forceinline__ uint32_t mul_shoup(uint32_t a, uint2 w) {
     uint32_t qh = (a * w.y) >> 16;
     return a * w.x - qh * kQ;
+}
+// Same product with the quotient estimate taken by a high multiply (a < 2^32, w32 = floor(w 2^32 / q)): three
+// fma-pipe instructions and none on the alu pipe.  Used where the alu pipe is the bottleneck (next to Keccak).
+__device__ __forceinline__ uint32_t mul_shoup_fma(uint32_t a, uint32_t w, uint32_t w32) {
+    uint32_t qh = __umulhi(a, w32);
+    return a * w - qh * kQ;
 }
 // x mod q for x < 2^16, result in [0, q].
 __device__ __forceinline__ uint32_t barrett16(uint32_t x) {
@@ -398,7 +405,7 @@ __device__ __forceinline__ void intt_warp(uint32_t x[8], uint16_t *scratch, int 
 // (D4: ByteDecode12 does not reduce), each term is < 3 * 4096^2 so four terms fit 32 bits.
 __device__ __forceinline__ void basemul_acc(uint32_t &acc0, uint32_t &acc1, uint32_t a0, uint32_t a1, uint32_t b0,
                                             uint32_t b1, uint2 gamma) {
-    uint32_t a1g = mul_shoup(a1, gamma);  // < 2q
+    uint32_t a1g = mul_shoup_fma(a1, gamma.x, gamma.y);  // gamma = {w, floor(w 2^32 / q)} from the gamma32 table; < 2q
     acc0 += a0 * b0 + a1g * b1;
     acc1 += a0 * b1 + a1 * b0;
 }
@@ -461,8 +468,11 @@ __device__ __forceinline__ uint32_t unpack1(const uint8_t *src, int c) {
 
 // Noise polynomials travel between kernels as 4-bit codes (coefficient + 3), 8 per 32-bit word.
 __device__ __forceinline__ uint32_t noise_code_to_coeff(uint32_t code) {  // code in 0..6 -> canonical
-    int32_t c = (int32_t)code - 3;
-    return (uint32_t)(c + ((c >> 31) & (int32_t)kQ));
+    return csubq(code + (kQ - 3));
+}
+// (x + e) mod q for canonical x and the noise coefficient e given by its code: one 3-input add, two min-subtracts.
+__device__ __forceinline__ uint32_t add_noise_code(uint32_t x, uint32_t code) {
+    return csubq(csubq(x + code + (kQ - 3)));  // x + code + q - 3 < 2q + 3
 }
 
 }  // namespace mlkem

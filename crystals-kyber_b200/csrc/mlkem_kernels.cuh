@@ -471,15 +471,16 @@ __global__ void __launch_bounds__(32 * P::K) k_sample_matvec(MatvecArgs g) {
         uint32_t acc[8];
 #pragma unroll
         for (int r = 0; r < 8; r++) acc[r] = 0;
-        const uint32_t *vec = reinterpret_cast<const uint32_t *>(g.vec + g.vec_stride * item);
+        // (16-bit loads instead of 32-bit loads + mask/shift: the load/store pipe has slack, the alu pipe does not)
+        const uint16_t *vec = g.vec + g.vec_stride * item;
 #pragma unroll
         for (int j = 0; j < K; j++) {
-            const uint32_t *aw = slot0 + kSlotWords * j;
+            const uint16_t *aw = reinterpret_cast<const uint16_t *>(slot0 + kSlotWords * j);
 #pragma unroll
             for (int r = 0; r < 4; r++) {
                 int t = lane + 32 * r;
-                uint32_t a = aw[t], b = __ldg(vec + 128 * j + t);
-                basemul_acc(acc[2 * r], acc[2 * r + 1], a & 0xFFFFu, a >> 16, b & 0xFFFFu, b >> 16, gam[r]);
+                uint32_t a0 = aw[2 * t], a1 = aw[2 * t + 1], b0 = __ldg(vec + 256 * j + 2 * t), b1 = __ldg(vec + 256 * j + 2 * t + 1);
+                basemul_acc(acc[2 * r], acc[2 * r + 1], a0, a1, b0, b1, gam[r]);
             }
         }
         int nwords;
@@ -513,8 +514,8 @@ __global__ void __launch_bounds__(32 * P::K) k_sample_matvec(MatvecArgs g) {
             const uint32_t *codes = g.addc + g.addc_stride * item + 32 * row;
 #pragma unroll
             for (int r = 0; r < 8; r++) {
-                uint32_t e = noise_code_to_coeff((__ldg(codes + (lane >> 3) + 4 * r) >> (4 * (lane & 7))) & 15u);
-                x[r] = compress<P::DU>(csubq(x[r] + e));
+                uint32_t code = (__ldg(codes + (lane >> 3) + 4 * r) >> (4 * (lane & 7))) & 15u;
+                x[r] = compress<P::DU>(add_noise_code(x[r], code));
             }
             store_scratch_A(x, scratch, lane);
             __syncwarp();
@@ -612,9 +613,9 @@ __global__ void __launch_bounds__(kWarpTPB) k_encrypt_v(EncVArgs g) {
     const uint32_t *mw = reinterpret_cast<const uint32_t *>(g.m + 32 * (size_t)item);
 #pragma unroll
     for (int r = 0; r < 8; r++) {
-        uint32_t e = noise_code_to_coeff((__ldg(codes + (lane >> 3) + 4 * r) >> (4 * (lane & 7))) & 15u);
+        uint32_t code = (__ldg(codes + (lane >> 3) + 4 * r) >> (4 * (lane & 7))) & 15u;
         uint32_t mu = ((__ldg(mw + r) >> lane) & 1u) * 1665u;  // Decompress_1(bit) = 1665 bit (ml_kem.c:867-870)
-        x[r] = compress<P::DV>(csubq(csubq(x[r] + e) + mu));
+        x[r] = compress<P::DV>(csubq(add_noise_code(x[r], code) + mu));
     }
     store_scratch_A(x, scratch, lane);
     __syncwarp();

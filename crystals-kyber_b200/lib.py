@@ -56,6 +56,7 @@ SIGNATURES = {
     "mlkem_b200_hash_batch": (C.c_int, [C.c_int, C.c_size_t, C.c_size_t, _P8, _P8, _PO]),
     "mlkem_b200_tables": (C.c_int, [C.c_void_p, C.c_void_p]),
     "mlkem_b200_profile": (None, [C.c_int]),
+    "mlkem_b200_set_streams": (None, [C.c_int]),
     "mlkem_b200_profile_report": (C.c_int, [C.c_char_p, C.c_int]),
     "mlkem_b200_int32_peak": (C.c_int, [C.POINTER(C.c_double)]),
 }

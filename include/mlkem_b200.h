@@ -157,6 +157,9 @@ int mlkem_b200_hash_batch(int which, size_t n, size_t len, const uint8_t *in, ui
  * ({"kernel name": {"launches": L, "ms": total}, ...}) into buf, clears the records and returns the number of
  * bytes written (0 when nothing was recorded). */
 void mlkem_b200_profile(int enable);
+/* Device-memory calls interleave their chunks on 2 internal streams by default (kernels of different chunks
+ * overlap).  n = 1 serialises them on the caller's stream, which is what per-kernel timing needs. */
+void mlkem_b200_set_streams(int n);
 int mlkem_b200_profile_report(char *buf, int cap);
 
 /* INT32 roofline denominators of the current device, measured now: sustained thread-operations per second
