@@ -575,7 +575,7 @@ __device__ __forceinline__ void stage_row(uint8_t *dst, const uint8_t *src, int 
 // One item per warp; every lane owns 8 consecutive coefficients (= 12 bytes of each ByteEncode12 row).
 // COMPARE: OR the mismatch against the received ciphertext into flags instead of storing.
 template <class P, bool COMPARE>
-__global__ void __launch_bounds__(kWarpTPB) k_encrypt_v(EncVArgs g) {
+__global__ void __launch_bounds__(kWarpTPB, 8) k_encrypt_v(EncVArgs g) {
     constexpr int K = P::K, NW = kWarpTPB / 32;
     __shared__ __align__(16) uint16_t s_scratch[NW * kScratchU16];
     __shared__ __align__(16) uint8_t s_rows[NW * (384 * K + 16)];
