@@ -220,7 +220,7 @@ def main():
     K = torch.empty((n, 32), dtype=torch.uint8, device=dev)
     Kd = torch.empty((n, 32), dtype=torch.uint8, device=dev)
     stream = torch.cuda.current_stream(dev)
-    o_dev = Opts(local, MEM_DEVICE, stream.cuda_stream, 0, 0)
+    o_dev = Opts(local, MEM_DEVICE, stream.cuda_stream, 0, 0, 0)
     P = lambda t: C.c_void_p(t.data_ptr())
 
     def step_device():
@@ -284,7 +284,7 @@ def main():
     hc = torch.empty((ne, sz["c"]), dtype=torch.uint8, pin_memory=True)
     hK = torch.empty((ne, 32), dtype=torch.uint8, pin_memory=True)
     hKd = torch.empty((ne, 32), dtype=torch.uint8, pin_memory=True)
-    o_host = Opts(local, MEM_HOST, None, 0, 0)
+    o_host = Opts(local, MEM_HOST, None, 0, 0, 0)
 
     def step_host():
         rc = lib.mlkem_b200_encaps_batch(PS, ne, P(hek), P(hm), P(hc), P(hK), C.byref(o_host))

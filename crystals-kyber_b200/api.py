@@ -33,14 +33,17 @@ def _is_torch(x):
 
 
 class MLKEM:
-    def __init__(self, chunk_items: int = 0, sample_group_limit: int = 0):
+    def __init__(self, chunk_items: int = 0, sample_group_limit: int = 0, fips203: bool = False):
+        """fips203=True selects the conformant variant (SHAKE256 PRF/J, real modulus check) instead of the
+        reference's behaviour -- see MLKEM_B200_FLAG_FIPS203 in include/mlkem_b200.h."""
         self.lib = load()
         self.chunk_items = chunk_items
         self.sample_group_limit = sample_group_limit
+        self.flags = 1 if fips203 else 0
 
     # ------------------------------------------------------------------ plumbing
     def _opts(self, device_mem: bool, device: int = -1, stream=None):
-        return Opts(device, MEM_DEVICE if device_mem else MEM_HOST, stream, self.chunk_items, self.sample_group_limit)
+        return Opts(device, MEM_DEVICE if device_mem else MEM_HOST, stream, self.chunk_items, self.sample_group_limit, self.flags)
 
     def _check(self, rc, what):
         if rc != 0:
@@ -102,6 +105,36 @@ class MLKEM:
     def check_dk(self, ps, dk):
         n = self._count(dk, sizes(ps)["dk"])
         return self._call("mlkem_b200_check_dk_batch", (ps, n), [(dk, np.uint8)], [((n,), np.int32)])
+
+    # ------------------------------------------------------------------ public wrappers (entropy + checks), host memory
+    def kem_keygen(self, ps, n):
+        sz = sizes(ps)
+        ek, dk = np.empty((n, sz["ek"]), np.uint8), np.empty((n, sz["dk"]), np.uint8)
+        o = self._opts(False)
+        self._check(self.lib.mlkem_b200_kem_keygen_batch(ps, n, C.c_void_p(ek.ctypes.data), C.c_void_p(dk.ctypes.data), C.byref(o)),
+                    "mlkem_b200_kem_keygen_batch")
+        return ek, dk
+
+    def kem_encaps(self, ps, ek, ek_len=None):
+        sz = sizes(ps if ps in PARAMS else 768)  # an unknown set is the library's error to report (-1)
+        ek = np.ascontiguousarray(ek, np.uint8)
+        n = ek.size // sz["ek"] if ek_len is None else ek.shape[0]
+        c, K = np.empty((n, sz["c"]), np.uint8), np.empty((n, 32), np.uint8)
+        o = self._opts(False)
+        rc = self.lib.mlkem_b200_kem_encaps_batch(ps, n, C.c_void_p(ek.ctypes.data), sz["ek"] if ek_len is None else ek_len,
+                                                  C.c_void_p(c.ctypes.data), C.c_void_p(K.ctypes.data), C.byref(o))
+        return rc, c, K
+
+    def kem_decaps(self, ps, dk, c, dk_len=None, c_len=None):
+        sz = sizes(ps)
+        dk, c = np.ascontiguousarray(dk, np.uint8), np.ascontiguousarray(c, np.uint8)
+        n = c.size // sz["c"]
+        K, status = np.empty((n, 32), np.uint8), np.empty(n, np.int32)
+        o = self._opts(False)
+        rc = self.lib.mlkem_b200_kem_decaps_batch(ps, n, C.c_void_p(dk.ctypes.data), sz["dk"] if dk_len is None else dk_len,
+                                                  C.c_void_p(c.ctypes.data), sz["c"] if c_len is None else c_len,
+                                                  C.c_void_p(K.ctypes.data), C.c_void_p(status.ctypes.data), C.byref(o))
+        return rc, K, status
 
     # ------------------------------------------------------------------ K-PKE
     def pke_keygen(self, ps, d):

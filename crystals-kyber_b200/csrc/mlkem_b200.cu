@@ -226,16 +226,24 @@ constexpr size_t kWsSlack = 16 * 256;
 // Stores c, or (cmp != nullptr) ORs the mismatch of the re-encryption against cmp into flags.
 template <class P>
 int enqueue_encrypt(cudaStream_t st, Arena &ws, int n, const uint8_t *ek, size_t ek_stride, const uint8_t *m,
-                    const uint8_t *seed, size_t seed_stride, uint8_t *c, const uint8_t *cmp, uint32_t *flags, int group_limit) {
+                    const uint8_t *seed, size_t seed_stride, uint8_t *c, const uint8_t *cmp, uint32_t *flags, int group_limit, bool fips) {
     constexpr int K = P::K;
     uint16_t *yhat = ws.take<uint16_t>((size_t)n * K * 256);
     uint32_t *codes = ws.take<uint32_t>((size_t)n * (K + 1) * 32);
     // y^ = NTT(CBD_eta1(PRF(r, 0..K-1)))            ml_kem.c:826-836
-    LAUNCH((k_noise<P::ETA1, true>), dim3(cdiv(n, kNoiseTPB), K), kNoiseTPB, 0, st, n, seed, seed_stride, 0, yhat, (size_t)K * 256,
-           (uint32_t *)nullptr, (size_t)0);
-    // e1, e2 = CBD_eta2(PRF(r, K..2K))               ml_kem.c:839-851
-    LAUNCH((k_noise<P::ETA2, false>), dim3(cdiv(n, kNoiseTPB), K + 1), kNoiseTPB, 0, st, n, seed, seed_stride, K, (uint16_t *)nullptr,
-           (size_t)0, codes, (size_t)(K + 1) * 32);
+    // (PRF = SHAKE128 as in the reference, or SHAKE256 in FIPS mode)
+    if (!fips) {
+        LAUNCH((k_noise<P::ETA1, true>), dim3(cdiv(n, kNoiseTPB), K), kNoiseTPB, 0, st, n, seed, seed_stride, 0, yhat, (size_t)K * 256,
+               (uint32_t *)nullptr, (size_t)0);
+        // e1, e2 = CBD_eta2(PRF(r, K..2K))               ml_kem.c:839-851
+        LAUNCH((k_noise<P::ETA2, false>), dim3(cdiv(n, kNoiseTPB), K + 1), kNoiseTPB, 0, st, n, seed, seed_stride, K, (uint16_t *)nullptr,
+               (size_t)0, codes, (size_t)(K + 1) * 32);
+    } else {
+        LAUNCH((k_noise<P::ETA1, true, kRateSha3_256>), dim3(cdiv(n, kNoiseTPB), K), kNoiseTPB, 0, st, n, seed, seed_stride, 0, yhat,
+               (size_t)K * 256, (uint32_t *)nullptr, (size_t)0);
+        LAUNCH((k_noise<P::ETA2, false, kRateSha3_256>), dim3(cdiv(n, kNoiseTPB), K + 1), kNoiseTPB, 0, st, n, seed, seed_stride, K,
+               (uint16_t *)nullptr, (size_t)0, codes, (size_t)(K + 1) * 32);
+    }
     MatvecArgs a{};
     a.n = n;
     a.group_limit = group_limit;
@@ -276,7 +284,7 @@ int enqueue_encrypt(cudaStream_t st, Arena &ws, int n, const uint8_t *ek, size_t
 
 // KeyGen_internal (ml_kem.c:1034) when z != nullptr, PKE_KeyGen (ml_kem.c:651) otherwise.
 template <class P>
-int enqueue_keygen(cudaStream_t st, Arena &ws, int n, const uint8_t *d, const uint8_t *z, uint8_t *ek, uint8_t *dk, int group_limit) {
+int enqueue_keygen(cudaStream_t st, Arena &ws, int n, const uint8_t *d, const uint8_t *z, uint8_t *ek, uint8_t *dk, int group_limit, bool fips) {
     constexpr int K = P::K;
     const bool full = z != nullptr;
     const size_t dk_stride = full ? P::DK : P::DKPKE;
@@ -284,8 +292,12 @@ int enqueue_keygen(cudaStream_t st, Arena &ws, int n, const uint8_t *d, const ui
     uint16_t *se = ws.take<uint16_t>((size_t)n * 2 * K * 256);
     LAUNCH(k_keygen_G, cdiv(n, kHashTPB), kHashTPB, 0, st, n, d, (uint32_t)K, rs);
     // s^ (nonces 0..K-1) and e^ (nonces K..2K-1), ml_kem.c:696-720; sigma = rs + 32
-    LAUNCH((k_noise<P::ETA1, true>), dim3(cdiv(n, kNoiseTPB), 2 * K), kNoiseTPB, 0, st, n, rs + 32, (size_t)64, 0, se, (size_t)2 * K * 256,
-           (uint32_t *)nullptr, (size_t)0);
+    if (!fips)
+        LAUNCH((k_noise<P::ETA1, true>), dim3(cdiv(n, kNoiseTPB), 2 * K), kNoiseTPB, 0, st, n, rs + 32, (size_t)64, 0, se, (size_t)2 * K * 256,
+               (uint32_t *)nullptr, (size_t)0);
+    else
+        LAUNCH((k_noise<P::ETA1, true, kRateSha3_256>), dim3(cdiv(n, kNoiseTPB), 2 * K), kNoiseTPB, 0, st, n, rs + 32, (size_t)64, 0, se,
+               (size_t)2 * K * 256, (uint32_t *)nullptr, (size_t)0);
     MatvecArgs a{};
     a.n = n;
     a.group_limit = group_limit;
@@ -306,14 +318,14 @@ int enqueue_keygen(cudaStream_t st, Arena &ws, int n, const uint8_t *d, const ui
 }
 
 template <class P>
-int enqueue_encaps(cudaStream_t st, Arena &ws, int n, const uint8_t *ek, const uint8_t *m, uint8_t *c, uint8_t *Kout, int group_limit) {
+int enqueue_encaps(cudaStream_t st, Arena &ws, int n, const uint8_t *ek, const uint8_t *m, uint8_t *c, uint8_t *Kout, int group_limit, bool fips) {
     uint8_t *r = ws.take<uint8_t>((size_t)n * 32);
     LAUNCH((k_encaps_HG<P>), cdiv(n, kHashTPB), kHashTPB, 0, st, n, ek, m, Kout, r);
-    return enqueue_encrypt<P>(st, ws, n, ek, P::EK, m, r, 32, c, nullptr, nullptr, group_limit);
+    return enqueue_encrypt<P>(st, ws, n, ek, P::EK, m, r, 32, c, nullptr, nullptr, group_limit, fips);
 }
 
 template <class P>
-int enqueue_decaps(cudaStream_t st, Arena &ws, int n, const uint8_t *dk, const uint8_t *c, uint8_t *Kout, int group_limit) {
+int enqueue_decaps(cudaStream_t st, Arena &ws, int n, const uint8_t *dk, const uint8_t *c, uint8_t *Kout, int group_limit, bool fips) {
     constexpr int K = P::K;
     uint8_t *mp = ws.take<uint8_t>((size_t)n * 32);
     uint8_t *Kr = ws.take<uint8_t>((size_t)n * 64);
@@ -322,8 +334,9 @@ int enqueue_decaps(cudaStream_t st, Arena &ws, int n, const uint8_t *dk, const u
     LAUNCH((k_decrypt<P>), warp_grid(n, kWarpTPB / 32), kWarpTPB, 0, st, n, dk, (size_t)P::DK, c, mp);
     LAUNCH((k_decaps_G<P>), cdiv(n, kHashTPB), kHashTPB, 0, st, n, mp, dk, Kr);
     // c' = K-PKE.Encrypt(ek_pke, m', r') compared on the fly (ml_kem.c:1206-1215)
-    if (int rc = enqueue_encrypt<P>(st, ws, n, dk + 384 * K, P::DK, mp, Kr + 32, 64, nullptr, c, flags, group_limit)) return rc;
-    LAUNCH((k_decaps_J_select<P>), cdiv(n, kHashTPB), kHashTPB, 0, st, n, dk, c, Kr, flags, Kout);
+    if (int rc = enqueue_encrypt<P>(st, ws, n, dk + 384 * K, P::DK, mp, Kr + 32, 64, nullptr, c, flags, group_limit, fips)) return rc;
+    if (!fips) LAUNCH((k_decaps_J_select<P>), cdiv(n, kHashTPB), kHashTPB, 0, st, n, dk, c, Kr, flags, Kout);
+    else LAUNCH((k_decaps_J_select<P, kRateSha3_256>), cdiv(n, kHashTPB), kHashTPB, 0, st, n, dk, c, Kr, flags, Kout);
     return 0;
 }
 
@@ -441,6 +454,7 @@ int drive(const mlkem_b200_opts *o, size_t n, size_t ws_per_item, std::vector<Bu
 }
 
 int group_limit_of(const mlkem_b200_opts *o) { return (o && o->sample_group_limit > 0) ? o->sample_group_limit : 278; }
+bool fips_of(const mlkem_b200_opts *o) { return o && (o->flags & MLKEM_B200_FLAG_FIPS203); }
 
 #define DISPATCH_SET(param_set, CALL)                   \
     switch (param_set) {                                \
@@ -514,36 +528,40 @@ unsigned mlkem_b200_ct_bytes(int set) {
 
 int mlkem_b200_keygen_batch(int set, size_t n, const uint8_t *d, const uint8_t *z, uint8_t *ek, uint8_t *dk, const mlkem_b200_opts *o) {
     const int gl = group_limit_of(o);
+    const bool fips = fips_of(o);
     DISPATCH_SET(set, return drive(o, n, ws_bytes_per_item<P>(), {{d, nullptr, 32}, {z, nullptr, 32}, {nullptr, ek, P::EK}, {nullptr, dk, P::DK}},
                                    [=](cudaStream_t st, Arena &ws, int cn, void **p) {
-                                       return enqueue_keygen<P>(st, ws, cn, (const uint8_t *)p[0], (const uint8_t *)p[1], (uint8_t *)p[2], (uint8_t *)p[3], gl);
+                                       return enqueue_keygen<P>(st, ws, cn, (const uint8_t *)p[0], (const uint8_t *)p[1], (uint8_t *)p[2], (uint8_t *)p[3], gl, fips);
                                    }));
     return MLKEM_B200_ERR_PARAM;
 }
 
 int mlkem_b200_pke_keygen_batch(int set, size_t n, const uint8_t *d, uint8_t *ek, uint8_t *dkpke, const mlkem_b200_opts *o) {
     const int gl = group_limit_of(o);
+    const bool fips = fips_of(o);
     DISPATCH_SET(set, return drive(o, n, ws_bytes_per_item<P>(), {{d, nullptr, 32}, {nullptr, ek, P::EK}, {nullptr, dkpke, P::DKPKE}},
                                    [=](cudaStream_t st, Arena &ws, int cn, void **p) {
-                                       return enqueue_keygen<P>(st, ws, cn, (const uint8_t *)p[0], nullptr, (uint8_t *)p[1], (uint8_t *)p[2], gl);
+                                       return enqueue_keygen<P>(st, ws, cn, (const uint8_t *)p[0], nullptr, (uint8_t *)p[1], (uint8_t *)p[2], gl, fips);
                                    }));
     return MLKEM_B200_ERR_PARAM;
 }
 
 int mlkem_b200_encaps_batch(int set, size_t n, const uint8_t *ek, const uint8_t *m, uint8_t *c, uint8_t *K, const mlkem_b200_opts *o) {
     const int gl = group_limit_of(o);
+    const bool fips = fips_of(o);
     DISPATCH_SET(set, return drive(o, n, ws_bytes_per_item<P>(), {{ek, nullptr, P::EK}, {m, nullptr, 32}, {nullptr, c, P::C}, {nullptr, K, 32}},
                                    [=](cudaStream_t st, Arena &ws, int cn, void **p) {
-                                       return enqueue_encaps<P>(st, ws, cn, (const uint8_t *)p[0], (const uint8_t *)p[1], (uint8_t *)p[2], (uint8_t *)p[3], gl);
+                                       return enqueue_encaps<P>(st, ws, cn, (const uint8_t *)p[0], (const uint8_t *)p[1], (uint8_t *)p[2], (uint8_t *)p[3], gl, fips);
                                    }));
     return MLKEM_B200_ERR_PARAM;
 }
 
 int mlkem_b200_decaps_batch(int set, size_t n, const uint8_t *dk, const uint8_t *c, uint8_t *K, const mlkem_b200_opts *o) {
     const int gl = group_limit_of(o);
+    const bool fips = fips_of(o);
     DISPATCH_SET(set, return drive(o, n, ws_bytes_per_item<P>(), {{dk, nullptr, P::DK}, {c, nullptr, P::C}, {nullptr, K, 32}},
                                    [=](cudaStream_t st, Arena &ws, int cn, void **p) {
-                                       return enqueue_decaps<P>(st, ws, cn, (const uint8_t *)p[0], (const uint8_t *)p[1], (uint8_t *)p[2], gl);
+                                       return enqueue_decaps<P>(st, ws, cn, (const uint8_t *)p[0], (const uint8_t *)p[1], (uint8_t *)p[2], gl, fips);
                                    }));
     return MLKEM_B200_ERR_PARAM;
 }
@@ -556,12 +574,112 @@ int mlkem_b200_check_dk_batch(int set, size_t n, const uint8_t *dk, int32_t *sta
     return MLKEM_B200_ERR_PARAM;
 }
 
+}  // extern "C" (helpers with C++ linkage follow)
+
+// ---- batched forms of the public wrappers (ml_kem.c:1233-1359): entropy, length checks, dk hash check ----------
+
+// ml_kem.c:458 getRandomBytes reads 32 unsigned ints from /dev/urandom and keeps each modulo 256, i.e. 32 uniform
+// bytes; here the bytes are read directly.
+static int host_entropy(uint8_t *out, size_t bytes) {
+    FILE *f = fopen("/dev/urandom", "rb");
+    if (!f) return -2;
+    size_t got = fread(out, 1, bytes, f);
+    fclose(f);
+    return got == bytes ? 0 : -2;  // ml_errno -2: random bit generation failed (ml_kem.c:1243,1297)
+}
+
+// Runs `call(seed_ptr)` with `bytes` of fresh entropy placed where opts says the buffers live.
+template <class F>
+static int with_entropy(const mlkem_b200_opts *o, size_t bytes, F call) {
+    std::vector<uint8_t> host(bytes);
+    if (int rc = host_entropy(host.data(), bytes)) return rc;
+    if (!(o && o->mem == MLKEM_B200_MEM_DEVICE)) return call(host.data());
+    int dev;
+    DeviceCtx *ctx;
+    if (int rc = acquire(o, &dev, &ctx)) return rc;
+    uint8_t *d = nullptr;
+    CU(cudaMalloc(&d, bytes));
+    cudaError_t e = cudaMemcpy(d, host.data(), bytes, cudaMemcpyHostToDevice);
+    int rc = e == cudaSuccess ? call(d) : MLKEM_B200_ERR_CUDA;
+    cudaStreamSynchronize(static_cast<cudaStream_t>(o->stream));  // the seeds must outlive the kernels reading them
+    cudaFree(d);
+    return rc;
+}
+
+extern "C" {
+
+int mlkem_b200_kem_keygen_batch(int set, size_t n, uint8_t *ek, uint8_t *dk, const mlkem_b200_opts *o) {
+    if (!mlkem_b200_ek_bytes(set)) return MLKEM_B200_ERR_PARAM;
+    if (n == 0) return MLKEM_B200_OK;
+    return with_entropy(o, 64 * n, [&](uint8_t *seeds) { return mlkem_b200_keygen_batch(set, n, seeds, seeds + 32 * n, ek, dk, o); });
+}
+
+int mlkem_b200_kem_encaps_batch(int set, size_t n, const uint8_t *ek, size_t ek_len, uint8_t *c, uint8_t *K, const mlkem_b200_opts *o) {
+    unsigned want = mlkem_b200_ek_bytes(set);
+    if (!want) return MLKEM_B200_ERR_PARAM;
+    if (ek_len != want) return MLKEM_B200_ERR_LENGTH;  // type check, ml_kem.c:1267
+    // modulus check (ml_kem.c:1274-1291): an identity in the reference (its ByteDecode12 never reduces), see SURVEY D4.
+    // In FIPS mode it is a real check: any coefficient >= q in any key rejects the call with -4.
+    if (n == 0) return MLKEM_B200_OK;
+    if (fips_of(o)) {
+        std::vector<int32_t> st_host;
+        int32_t *status = nullptr;
+        const bool on_dev = o->mem == MLKEM_B200_MEM_DEVICE;
+        if (on_dev) CU(cudaMalloc(&status, 4 * n));
+        else {
+            st_host.resize(n);
+            status = st_host.data();
+        }
+        int rc = MLKEM_B200_ERR_PARAM;
+        switch (set) {
+#define MODCHK(PS, PT)                                                                                                              \
+    case PS:                                                                                                                        \
+        rc = drive(o, n, 0, {{ek, nullptr, PT::EK}, {nullptr, status, 4}}, [=](cudaStream_t st, Arena &, int cn, void **p) {          \
+            LAUNCH((k_check_ek_modulus<PT>), cdiv(cn, kHashTPB), kHashTPB, 0, st, cn, (const uint8_t *)p[0], (int *)p[1]);            \
+            return 0;                                                                                                               \
+        });                                                                                                                         \
+        break;
+            MODCHK(512, P512) MODCHK(768, P768) MODCHK(1024, P1024)
+#undef MODCHK
+        }
+        if (!rc && on_dev) {
+            st_host.resize(n);
+            cudaStreamSynchronize(static_cast<cudaStream_t>(o->stream));
+            if (cudaMemcpy(st_host.data(), status, 4 * n, cudaMemcpyDeviceToHost) != cudaSuccess) rc = MLKEM_B200_ERR_CUDA;
+        }
+        if (on_dev) cudaFree(status);
+        if (rc) return rc;
+        for (size_t i = 0; i < n; i++)
+            if (st_host[i] != 0) return MLKEM_B200_ERR_MODULUS;
+    }
+    return with_entropy(o, 32 * n, [&](uint8_t *m) { return mlkem_b200_encaps_batch(set, n, ek, m, c, K, o); });
+}
+
+int mlkem_b200_kem_decaps_batch(int set, size_t n, const uint8_t *dk, size_t dk_len, const uint8_t *c, size_t c_len, uint8_t *K,
+                                int32_t *status, const mlkem_b200_opts *o) {
+    if (!mlkem_b200_ek_bytes(set)) return MLKEM_B200_ERR_PARAM;
+    if (c_len != mlkem_b200_ct_bytes(set)) return MLKEM_B200_ERR_LENGTH;   // ml_kem.c:1321
+    if (dk_len != mlkem_b200_dk_bytes(set)) return MLKEM_B200_ERR_LENGTH;  // ml_kem.c:1329
+    if (!status) return MLKEM_B200_ERR_ARG;
+    if (int rc = mlkem_b200_check_dk_batch(set, n, dk, status, o)) return rc;  // hash check, ml_kem.c:1336-1350
+    if (int rc = mlkem_b200_decaps_batch(set, n, dk, c, K, o)) return rc;
+    if (o && o->mem == MLKEM_B200_MEM_DEVICE) {
+        cudaStream_t st = static_cast<cudaStream_t>(o->stream);
+        LAUNCH(k_mask_keys, cdiv(n, kHashTPB), kHashTPB, 0, st, (int)n, (const int *)status, K);
+    } else {
+        for (size_t i = 0; i < n; i++)
+            if (status[i] != 0) memset(K + 32 * i, 0, 32);
+    }
+    return MLKEM_B200_OK;
+}
+
 int mlkem_b200_pke_encrypt_batch(int set, size_t n, const uint8_t *ek, const uint8_t *m, const uint8_t *r, uint8_t *c, const mlkem_b200_opts *o) {
     const int gl = group_limit_of(o);
+    const bool fips = fips_of(o);
     DISPATCH_SET(set, return drive(o, n, ws_bytes_per_item<P>(), {{ek, nullptr, P::EK}, {m, nullptr, 32}, {r, nullptr, 32}, {nullptr, c, P::C}},
                                    [=](cudaStream_t st, Arena &ws, int cn, void **p) {
                                        return enqueue_encrypt<P>(st, ws, cn, (const uint8_t *)p[0], P::EK, (const uint8_t *)p[1], (const uint8_t *)p[2], 32,
-                                                                 (uint8_t *)p[3], nullptr, nullptr, gl);
+                                                                 (uint8_t *)p[3], nullptr, nullptr, gl, fips);
                                    }));
     return MLKEM_B200_ERR_PARAM;
 }
@@ -606,7 +724,7 @@ int mlkem_b200_sample_ntt_batch(size_t n, const uint8_t *seeds, uint16_t *a, uin
     if (seeds_after) bufs.push_back({nullptr, seeds_after, 34});
     const bool has_after = seeds_after != nullptr;
     // 34-byte items are not 16-byte multiples: the chunk size must keep chunk starts aligned
-    mlkem_b200_opts oo = o ? *o : mlkem_b200_opts{-1, MLKEM_B200_MEM_HOST, nullptr, 0, 0};
+    mlkem_b200_opts oo = o ? *o : mlkem_b200_opts{-1, MLKEM_B200_MEM_HOST, nullptr, 0, 0, 0};
     if (oo.chunk_items <= 0) oo.chunk_items = 1 << 16;
     oo.chunk_items = (oo.chunk_items + 7) & ~7;
     return drive(&oo, n, 0, bufs, [=](cudaStream_t st, Arena &, int cn, void **p) {
@@ -626,10 +744,16 @@ int mlkem_b200_cbd_batch(int eta, size_t n, const uint8_t *bytes, uint16_t *f, c
 }
 int mlkem_b200_prf_cbd_batch(int eta, size_t n, const uint8_t *seeds, const uint8_t *nonces, uint16_t *f, const mlkem_b200_opts *o) {
     if (eta != 2 && eta != 3) return MLKEM_B200_ERR_ARG;
-    mlkem_b200_opts oo = o ? *o : mlkem_b200_opts{-1, MLKEM_B200_MEM_HOST, nullptr, 0, 0};
+    const bool fips = fips_of(o);
+    mlkem_b200_opts oo = o ? *o : mlkem_b200_opts{-1, MLKEM_B200_MEM_HOST, nullptr, 0, 0, 0};
     if (oo.chunk_items <= 0) oo.chunk_items = 1 << 16;
     oo.chunk_items = (oo.chunk_items + 15) & ~15;  // 1-byte nonces: keep chunk starts 16-byte aligned
     return drive(&oo, n, 0, {{seeds, nullptr, 32}, {nonces, nullptr, 1}, {nullptr, f, 512}}, [=](cudaStream_t st, Arena &, int cn, void **p) {
+        if (fips) {
+            if (eta == 2) LAUNCH((k_prf_cbd_batch<2, kRateSha3_256>), cdiv(cn, kNoiseTPB), kNoiseTPB, 0, st, cn, (const uint8_t *)p[0], (const uint8_t *)p[1], (uint16_t *)p[2]);
+            else LAUNCH((k_prf_cbd_batch<3, kRateSha3_256>), cdiv(cn, kNoiseTPB), kNoiseTPB, 0, st, cn, (const uint8_t *)p[0], (const uint8_t *)p[1], (uint16_t *)p[2]);
+            return 0;
+        }
         if (eta == 2) LAUNCH((k_prf_cbd_batch<2>), cdiv(cn, kNoiseTPB), kNoiseTPB, 0, st, cn, (const uint8_t *)p[0], (const uint8_t *)p[1], (uint16_t *)p[2]);
         else LAUNCH((k_prf_cbd_batch<3>), cdiv(cn, kNoiseTPB), kNoiseTPB, 0, st, cn, (const uint8_t *)p[0], (const uint8_t *)p[1], (uint16_t *)p[2]);
         return 0;
@@ -692,18 +816,19 @@ int mlkem_b200_compress_batch(int d, size_t ncoef, const uint16_t *x, uint16_t *
 int mlkem_b200_decompress_batch(int d, size_t ncoef, const uint16_t *y, uint16_t *x, const mlkem_b200_opts *o) { return compress_impl(d, ncoef, y, x, o, true); }
 
 int mlkem_b200_hash_batch(int which, size_t n, size_t len, const uint8_t *in, uint8_t *out, const mlkem_b200_opts *o) {
-    if (len % 8 != 0 || which < 0 || which > 2) return MLKEM_B200_ERR_ARG;
+    if (len % 8 != 0 || which < 0 || which > 3) return MLKEM_B200_ERR_ARG;
     if (len % 16 != 0 && !(o && o->mem == MLKEM_B200_MEM_DEVICE)) {
         // chunk starts stay 16-byte aligned when the chunk size is even
     }
-    mlkem_b200_opts oo = o ? *o : mlkem_b200_opts{-1, MLKEM_B200_MEM_HOST, nullptr, 0, 0};
+    mlkem_b200_opts oo = o ? *o : mlkem_b200_opts{-1, MLKEM_B200_MEM_HOST, nullptr, 0, 0, 0};
     if (oo.chunk_items <= 0) oo.chunk_items = 1 << 16;
     oo.chunk_items = (oo.chunk_items + 1) & ~1;
     const int nw = (int)(len / 8);
     return drive(&oo, n, 0, {{in, nullptr, len ? len : 1}, {nullptr, out, which == 1 ? (size_t)64 : (size_t)32}}, [=](cudaStream_t st, Arena &, int cn, void **p) {
         if (which == 0) LAUNCH((k_hash_words<kRateSha3_256, 4>), cdiv(cn, kHashTPB), kHashTPB, 0, st, cn, (const uint8_t *)p[0], nw, kSfxHash, (uint8_t *)p[1]);
         else if (which == 1) LAUNCH((k_hash_words<kRateSha3_512, 8>), cdiv(cn, kHashTPB), kHashTPB, 0, st, cn, (const uint8_t *)p[0], nw, kSfxHash, (uint8_t *)p[1]);
-        else LAUNCH((k_hash_words<kRateShake128, 4>), cdiv(cn, kHashTPB), kHashTPB, 0, st, cn, (const uint8_t *)p[0], nw, kSfxXof, (uint8_t *)p[1]);
+        else if (which == 2) LAUNCH((k_hash_words<kRateShake128, 4>), cdiv(cn, kHashTPB), kHashTPB, 0, st, cn, (const uint8_t *)p[0], nw, kSfxXof, (uint8_t *)p[1]);
+        else LAUNCH((k_hash_words<kRateSha3_256, 4>), cdiv(cn, kHashTPB), kHashTPB, 0, st, cn, (const uint8_t *)p[0], nw, kSfxXof, (uint8_t *)p[1]);
         return 0;
     });
 }

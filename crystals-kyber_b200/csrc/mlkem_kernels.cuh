@@ -129,6 +129,36 @@ __global__ void __launch_bounds__(kHashTPB) k_check_dk_hash(int n, const uint8_t
     status[i] = diff ? -5 : 0;
 }
 
+// The modulus check of ML-KEM.Encaps (FIPS 203 section 7.2; ml_kem.c:1273-1291 where it cannot fail, D4):
+// status[i] = -4 when any 12-bit coefficient of ek is >= q.  FIPS mode only.
+template <class P>
+__global__ void __launch_bounds__(kHashTPB) k_check_ek_modulus(int n, const uint8_t *__restrict__ ek, int *__restrict__ status) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(ek + (size_t)P::EK * i);
+    uint32_t bad = 0;
+    for (int t = 0; t < 96 * P::K; t += 3) {  // 3 words = 8 coefficients
+        uint32_t w0 = __ldg(w + t), w1 = __ldg(w + t + 1), w2 = __ldg(w + t + 2);
+        uint32_t c[8] = {w0 & 0xFFF, (w0 >> 12) & 0xFFF, (w0 >> 24) | ((w1 & 0xF) << 8), (w1 >> 4) & 0xFFF,
+                         (w1 >> 16) & 0xFFF, (w1 >> 28) | ((w2 & 0xFF) << 4), (w2 >> 8) & 0xFFF, w2 >> 20};
+#pragma unroll
+        for (int k = 0; k < 8; k++) bad |= (c[k] >= kQ);
+    }
+    status[i] = bad ? -4 : 0;
+}
+
+// KEM_Decaps returns NULL for an item that fails its input checks (ml_kem.c:1344-1350): the batched form
+// zeroes that item's key instead (status[i] != 0 tells the caller).
+__global__ void __launch_bounds__(kHashTPB) k_mask_keys(int n, const int *__restrict__ status, uint8_t *__restrict__ K) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (status[i] != 0) {
+        uint4 zero = make_uint4(0, 0, 0, 0);
+        reinterpret_cast<uint4 *>(K + 32 * (size_t)i)[0] = zero;
+        reinterpret_cast<uint4 *>(K + 32 * (size_t)i)[1] = zero;
+    }
+}
+
 // Decaps (ml_kem.c:1181-1193): (K', r') = G(m' || h), h = dk[768k+32 .. +32).
 template <class P>
 __global__ void __launch_bounds__(kHashTPB) k_decaps_G(int n, const uint8_t *__restrict__ mprime, const uint8_t *__restrict__ dk,
@@ -150,7 +180,7 @@ __global__ void __launch_bounds__(kHashTPB) k_decaps_G(int n, const uint8_t *__r
 // Decaps tail (ml_kem.c:1196-1215): Kbar = J(z || c) -- SHAKE128 in the reference (D2) -- then a
 // branch-free select between K' and Kbar on the re-encryption mismatch flag.  The reference's compare is
 // an early-exit loop; the selected key is the same.
-template <class P>
+template <class P, int RATE = kRateShake128>
 __global__ void __launch_bounds__(kHashTPB) k_decaps_J_select(int n, const uint8_t *__restrict__ dk, const uint8_t *__restrict__ c,
                                                               const uint8_t *__restrict__ Kr, const uint32_t *__restrict__ flags,
                                                               uint8_t *__restrict__ Kout) {
@@ -159,8 +189,9 @@ __global__ void __launch_bounds__(kHashTPB) k_decaps_J_select(int n, const uint8
     const uint8_t *z = dk + (size_t)P::DK * i + 768 * P::K + 64;
     const uint8_t *ci = c + (size_t)P::C * i;
     Lane a[25];
-    sponge_absorb_words<kRateShake128>(a, 4 + P::C / 8, kSfxXof,
-                                       [&](int w) { return w < 4 ? load_lane(z + 8 * w) : load_lane(ci + 8 * (w - 4)); });
+    // RATE 21 = SHAKE128 (the reference's J, D2); RATE 17 = SHAKE256 (FIPS 203)
+    sponge_absorb_words<RATE>(a, 4 + P::C / 8, kSfxXof,
+                              [&](int w) { return w < 4 ? load_lane(z + 8 * w) : load_lane(ci + 8 * (w - 4)); });
     uint32_t mask = flags[i] ? 0xFFFFFFFFu : 0u;
 #pragma unroll
     for (int w = 0; w < 4; w++) {
@@ -213,40 +244,56 @@ __device__ __forceinline__ void cbd3_words(uint32_t w0, uint32_t w1, uint32_t w2
 }
 
 // PRF + CBD for one (seed, nonce): 32 words of 4-bit codes written through `put(word_index, value)`.
-template <int ETA, typename PUT>
+// RATE = 21 lanes: SHAKE128, what the reference's PRF is (D1, ml_kem.c:508).  RATE = 17 lanes: SHAKE256, the PRF of
+// FIPS 203 (library flag MLKEM_B200_FLAG_FIPS203).
+template <int ETA, int RATE, typename PUT>
 __device__ __forceinline__ void prf_cbd_codes(const Lane seed[4], uint32_t nonce, PUT put) {
     Lane a[25];
     keccak_zero(a);
 #pragma unroll
     for (int w = 0; w < 4; w++) a[w] = seed[w];
     a[4].lo = nonce | (kSfxXof << 8);  // 33-byte message, then suffix 1111 + first pad bit
-    a[kRateShake128 - 1].hi ^= 0x80000000u;
+    a[RATE - 1].hi ^= 0x80000000u;
     keccak_f1600(a);
-    if (ETA == 2) {  // 128 bytes = lanes 0..15
+    if (ETA == 2) {  // 128 bytes = lanes 0..15 (fits one block at either rate)
 #pragma unroll
         for (int l = 0; l < 16; l++) {
             put(2 * l, cbd2_word(a[l].lo));
             put(2 * l + 1, cbd2_word(a[l].hi));
         }
-    } else {  // 192 bytes = 21 lanes of this block + 3 lanes of the next (sha3.c:298-311)
-#pragma unroll
-        for (int g = 0; g < 7; g++) {  // 3 lanes = 6 words = two 96-bit groups
-            uint32_t o0, o1;
-            cbd3_words(a[3 * g].lo, a[3 * g].hi, a[3 * g + 1].lo, o0, o1);
-            put(4 * g, o0);
-            put(4 * g + 1, o1);
-            cbd3_words(a[3 * g + 1].hi, a[3 * g + 2].lo, a[3 * g + 2].hi, o0, o1);
-            put(4 * g + 2, o0);
-            put(4 * g + 3, o1);
-        }
-        keccak_f1600(a);
+    } else {  // 192 bytes = 48 words = 16 groups of 96 bits; the second block is squeezed as in sha3.c:298-311
+        constexpr int W1 = 2 * RATE;      // words in the first block: 42 or 34
+        constexpr int G1 = W1 / 3;        // whole groups in the first block: 14 or 11
         uint32_t o0, o1;
-        cbd3_words(a[0].lo, a[0].hi, a[1].lo, o0, o1);
-        put(28, o0);
-        put(29, o1);
-        cbd3_words(a[1].hi, a[2].lo, a[2].hi, o0, o1);
-        put(30, o0);
-        put(31, o1);
+#pragma unroll
+        for (int g = 0; g < G1; g++) {
+            const int w = 3 * g;
+            uint32_t w0 = (w & 1) ? a[w >> 1].hi : a[w >> 1].lo, w1 = ((w + 1) & 1) ? a[(w + 1) >> 1].hi : a[(w + 1) >> 1].lo,
+                     w2 = ((w + 2) & 1) ? a[(w + 2) >> 1].hi : a[(w + 2) >> 1].lo;
+            cbd3_words(w0, w1, w2, o0, o1);
+            put(2 * g, o0);
+            put(2 * g + 1, o1);
+        }
+        constexpr int LEFT = W1 - 3 * G1;  // words of a group that straddles the blocks: 0 (rate 168) or 1 (rate 136)
+        uint32_t carry = 0;
+        if (LEFT) carry = ((W1 - 1) & 1) ? a[(W1 - 1) >> 1].hi : a[(W1 - 1) >> 1].lo;
+        keccak_f1600(a);
+        int next = 0;  // next unread word of the second block
+        if (LEFT) {
+            cbd3_words(carry, a[0].lo, a[0].hi, o0, o1);
+            put(2 * G1, o0);
+            put(2 * G1 + 1, o1);
+            next = 2;
+        }
+#pragma unroll
+        for (int g = G1 + (LEFT ? 1 : 0); g < 16; g++) {
+            const int w = next + 3 * (g - G1 - (LEFT ? 1 : 0));
+            uint32_t w0 = (w & 1) ? a[w >> 1].hi : a[w >> 1].lo, w1 = ((w + 1) & 1) ? a[(w + 1) >> 1].hi : a[(w + 1) >> 1].lo,
+                     w2 = ((w + 2) & 1) ? a[(w + 2) >> 1].hi : a[(w + 2) >> 1].lo;
+            cbd3_words(w0, w1, w2, o0, o1);
+            put(2 * g, o0);
+            put(2 * g + 1, o1);
+        }
     }
 }
 
@@ -264,7 +311,7 @@ __device__ __forceinline__ void load_layoutC_global(uint32_t x[8], int lane, con
 //   seeds       : 32-byte PRF key of item i at seeds + i*seed_stride
 //   NTT_OUT     : out16 + i*out16_stride + p*256   <- NTT(CBD(...)) as uint16, natural order  (s^, e^, y^)
 //   otherwise   : outc  + i*outc_stride  + p*32    <- 4-bit codes of CBD(...)                 (e1, e2)
-template <int ETA, bool NTT_OUT>
+template <int ETA, bool NTT_OUT, int RATE = kRateShake128>
 __global__ void __launch_bounds__(kNoiseTPB) k_noise(int n, const uint8_t *__restrict__ seeds, size_t seed_stride, int nonce0,
                                                      uint16_t *__restrict__ out16, size_t out16_stride,
                                                      uint32_t *__restrict__ outc, size_t outc_stride) {
@@ -277,7 +324,7 @@ __global__ void __launch_bounds__(kNoiseTPB) k_noise(int n, const uint8_t *__res
     for (int w = 0; w < 4; w++) seed[w] = item < n ? load_lane(seeds + seed_stride * item + 8 * w) : Lane{0u, 0u};
     if (NTT_OUT) {
         uint32_t *mine = s_codes + 33 * threadIdx.x;
-        prf_cbd_codes<ETA>(seed, (uint32_t)(nonce0 + p), [&](int w, uint32_t v) { mine[w] = v; });
+        prf_cbd_codes<ETA, RATE>(seed, (uint32_t)(nonce0 + p), [&](int w, uint32_t v) { mine[w] = v; });
         __syncwarp();  // a warp only ever reads the 32 slots its own lanes wrote
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
         uint16_t *scratch = s_scratch + warp * kScratchU16;
@@ -299,7 +346,7 @@ __global__ void __launch_bounds__(kNoiseTPB) k_noise(int n, const uint8_t *__res
     } else {
         if (item >= n) return;
         uint32_t buf[32];
-        prf_cbd_codes<ETA>(seed, (uint32_t)(nonce0 + p), [&](int w, uint32_t v) { buf[w] = v; });
+        prf_cbd_codes<ETA, RATE>(seed, (uint32_t)(nonce0 + p), [&](int w, uint32_t v) { buf[w] = v; });
         uint4 *dst = reinterpret_cast<uint4 *>(outc + outc_stride * item + 32 * p);
 #pragma unroll
         for (int v = 0; v < 8; v++) dst[v] = make_uint4(buf[4 * v], buf[4 * v + 1], buf[4 * v + 2], buf[4 * v + 3]);
@@ -863,7 +910,7 @@ __global__ void __launch_bounds__(kPrimTPB) k_cbd_batch(int n, const uint8_t *__
 }
 
 // PRF + CBD (+ optional NTT) exposed as a primitive: n (seed, nonce) pairs -> uint16 polynomials.
-template <int ETA>
+template <int ETA, int RATE = kRateShake128>
 __global__ void __launch_bounds__(kNoiseTPB) k_prf_cbd_batch(int n, const uint8_t *__restrict__ seeds, const uint8_t *__restrict__ nonces,
                                                              uint16_t *__restrict__ out) {
     __shared__ uint32_t s_codes[kNoiseTPB * 33];
@@ -874,7 +921,7 @@ __global__ void __launch_bounds__(kNoiseTPB) k_prf_cbd_batch(int n, const uint8_
     for (int w = 0; w < 4; w++) seed[w] = item < n ? load_lane(seeds + 32 * (size_t)item + 8 * w) : Lane{0u, 0u};
     uint32_t nonce = item < n ? nonces[item] : 0u;
     uint32_t *mine = s_codes + 33 * threadIdx.x;
-    prf_cbd_codes<ETA>(seed, nonce, [&](int w, uint32_t v) { mine[w] = v; });
+    prf_cbd_codes<ETA, RATE>(seed, nonce, [&](int w, uint32_t v) { mine[w] = v; });
     __syncwarp();
     for (int t = 0; t < 32; t++) {
         int it = blockIdx.x * kNoiseTPB + warp * 32 + t;

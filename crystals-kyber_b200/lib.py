@@ -6,6 +6,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libmlkem_b200.so")
 
 MEM_HOST, MEM_DEVICE = 0, 1
+FLAG_FIPS203 = 1
 
 
 class MlKemB200Error(RuntimeError):
@@ -14,7 +15,7 @@ class MlKemB200Error(RuntimeError):
 
 class Opts(C.Structure):
     _fields_ = [("device", C.c_int), ("mem", C.c_int), ("stream", C.c_void_p), ("chunk_items", C.c_int),
-                ("sample_group_limit", C.c_int)]
+                ("sample_group_limit", C.c_int), ("flags", C.c_int)]
 
 
 _lib = None
@@ -38,6 +39,9 @@ SIGNATURES = {
     "mlkem_b200_encaps_batch": (C.c_int, [C.c_int, C.c_size_t, _P8, _P8, _P8, _P8, _PO]),
     "mlkem_b200_decaps_batch": (C.c_int, [C.c_int, C.c_size_t, _P8, _P8, _P8, _PO]),
     "mlkem_b200_check_dk_batch": (C.c_int, [C.c_int, C.c_size_t, _P8, C.c_void_p, _PO]),
+    "mlkem_b200_kem_keygen_batch": (C.c_int, [C.c_int, C.c_size_t, _P8, _P8, _PO]),
+    "mlkem_b200_kem_encaps_batch": (C.c_int, [C.c_int, C.c_size_t, _P8, C.c_size_t, _P8, _P8, _PO]),
+    "mlkem_b200_kem_decaps_batch": (C.c_int, [C.c_int, C.c_size_t, _P8, C.c_size_t, _P8, C.c_size_t, _P8, C.c_void_p, _PO]),
     "mlkem_b200_pke_keygen_batch": (C.c_int, [C.c_int, C.c_size_t, _P8, _P8, _P8, _PO]),
     "mlkem_b200_pke_encrypt_batch": (C.c_int, [C.c_int, C.c_size_t, _P8, _P8, _P8, _P8, _PO]),
     "mlkem_b200_pke_decrypt_batch": (C.c_int, [C.c_int, C.c_size_t, _P8, C.c_size_t, _P8, _P8, _PO]),

@@ -59,8 +59,16 @@ typedef struct mlkem_b200_opts {
     void *stream;           /* cudaStream_t for MEM_DEVICE calls; NULL = the CUDA default stream */
     int chunk_items;        /* items per internal chunk, 0 = default */
     int sample_group_limit; /* test hook for the SampleNTT give-up rule (ml_kem.c:221-227); 0 = 278 (the reference) */
+    int flags;              /* 0 = bit-exact to the reference; MLKEM_B200_FLAG_FIPS203 see below */
 } mlkem_b200_opts;
-/* A NULL opts pointer means {device -1, MEM_HOST, NULL, 0, 0}. */
+/* A NULL opts pointer means {device -1, MEM_HOST, NULL, 0, 0, 0}. */
+
+/* FIPS 203 mode.  The reference deviates from FIPS 203: its PRF and J are SHAKE128
+ * and its ByteDecode12 never reduces, so the modulus check of KEM_Encaps cannot fail (D4).  With this flag PRF and J are
+ * SHAKE256 and mlkem_b200_kem_encaps_batch performs a real modulus check (-4): the outputs are those of a conformant
+ * ML-KEM (pinned in tests against an independent FIPS 203 implementation), NOT those of the reference. */
+#define MLKEM_B200_FLAG_FIPS203 1
+#define MLKEM_B200_ERR_MODULUS (-4)   /* FIPS mode only: an encapsulation key has a coefficient >= q (ml_errno -4) */
 
 const char *mlkem_b200_version(void);
 const char *mlkem_b200_last_error(void);          /* text of the last CUDA error seen by this thread */
@@ -91,6 +99,20 @@ int mlkem_b200_decaps_batch(int param_set, size_t n, const uint8_t *dk, const ui
                             const mlkem_b200_opts *opts);
 /* The dk hash check of KEM_Decaps, ml_kem.c:1336-1350: status[i] = 0 or -5.  status: n x int32. */
 int mlkem_b200_check_dk_batch(int param_set, size_t n, const uint8_t *dk, int32_t *status, const mlkem_b200_opts *opts);
+
+/* ---- batched forms of the public wrappers: entropy + input checks around the internal algorithms --------- */
+
+/* KEM_KeyGen, ml_kem.c:1233: (d, z) come from the host entropy source (/dev/urandom, as getRandomBytes ml_kem.c:458).
+ * Returns -2 when the entropy source fails (ml_errno -2). */
+int mlkem_b200_kem_keygen_batch(int param_set, size_t n, uint8_t *ek, uint8_t *dk, const mlkem_b200_opts *opts);
+/* KEM_Encaps, ml_kem.c:1257: type check on ek_len (-3), the reference's modulus check is an identity,
+ * m from the entropy source. */
+int mlkem_b200_kem_encaps_batch(int param_set, size_t n, const uint8_t *ek, size_t ek_len, uint8_t *c, uint8_t *K,
+                                const mlkem_b200_opts *opts);
+/* KEM_Decaps, ml_kem.c:1310: type checks on dk_len and c_len (-3, whole call), then per item the hash check
+ * (status[i] = -5, K[i] zeroed -- the reference returns NULL for such an item) and Decaps_internal. */
+int mlkem_b200_kem_decaps_batch(int param_set, size_t n, const uint8_t *dk, size_t dk_len, const uint8_t *c, size_t c_len,
+                                uint8_t *K, int32_t *status, const mlkem_b200_opts *opts);
 
 /* ---- K-PKE (FIPS 203 Alg. 13-15) -------------------------------------------------------------------- */
 
@@ -145,7 +167,7 @@ int mlkem_b200_decode_decompress_batch(int d, size_t n, const uint8_t *B, uint16
 /* ---- hashes ---------------------------------------------------------------------------------------- */
 
 /* which = 0: H = SHA3-256 (ml_kem.c:521), 32 B out.  1: G = SHA3-512 (:559), 64 B out.
- * 2: J = SHAKE128 with 32 B out (:540 -- the reference uses capacity 256).
+ * 2: J = SHAKE128 with 32 B out (:540 -- the reference uses capacity 256).  3: SHAKE256 with 32 B out (J of FIPS 203).
  * in: n messages of `len` bytes each, len a multiple of 8 (true of every H/G/J input of ML-KEM except
  * G(d||k), which only occurs inside KeyGen). */
 int mlkem_b200_hash_batch(int which, size_t n, size_t len, const uint8_t *in, uint8_t *out, const mlkem_b200_opts *opts);

@@ -131,18 +131,27 @@ ORC_API void orc_sponge(unsigned rate, uint8_t dsfx, const uint8_t *in, size_t i
     }
 }
 
+/*
+ * FIPS 203 mode -- NOT the reference's behaviour.  When switched on, PRF and J are SHAKE256
+ * (rate 136) as FIPS 203 section 4.1 specifies, and ByteDecode_12 reduces mod q so that the modulus check of
+ * ML-KEM.Encaps can fail.  The reference cannot pin this mode (it implements D1/D2/D4 instead); tests pin it
+ * against hashlib and an independent FIPS 203 implementation (the `cryptography` package).
+ */
+static int orc_fips = 0;
+ORC_API void orc_set_fips(int on) { orc_fips = on ? 1 : 0; }
+
 /* ml_kem.c:521  H(s) = SHA3-256(s)  (c = 512 -> rate 136, sfx 01) */
 ORC_API void orc_H(const uint8_t *in, size_t len, uint8_t out[32]) { orc_sponge(136, 0x06, in, len, out, 32); }
 /* ml_kem.c:559  G(c) = SHA3-512(c)  (c = 1024 -> rate 72, sfx 01) */
 ORC_API void orc_G(const uint8_t *in, size_t len, uint8_t out[64]) { orc_sponge(72, 0x06, in, len, out, 64); }
 /* ml_kem.c:540  J: sha3_b(..., c = N = 256, sfx 1111) => rate 168 => SHAKE128 (D2) */
-ORC_API void orc_J(const uint8_t *in, size_t len, uint8_t out[32]) { orc_sponge(168, 0x1F, in, len, out, 32); }
+ORC_API void orc_J(const uint8_t *in, size_t len, uint8_t out[32]) { orc_sponge(orc_fips ? 136 : 168, 0x1F, in, len, out, 32); }
 /* ml_kem.c:496  PRF_eta(s,b): sha3_b(s||b, 8*64*eta, c = N = 256, sfx 1111) => SHAKE128 (D1) */
 ORC_API void orc_PRF(const uint8_t s[32], uint8_t b, unsigned eta, uint8_t *out) {
     uint8_t seed[33];
     memcpy(seed, s, 32);
     seed[32] = b;
-    orc_sponge(168, 0x1F, seed, 33, out, 64 * eta);
+    orc_sponge(orc_fips ? 136 : 168, 0x1F, seed, 33, out, 64 * eta);
 }
 /* Standard SHAKE256, used only by the optional FIPS-mode cross checks in tests. */
 ORC_API void orc_shake256(const uint8_t *in, size_t len, uint8_t *out, size_t outlen) {
@@ -207,6 +216,7 @@ ORC_API void orc_byte_decode(const uint8_t *B, unsigned d, uint16_t F[ORC_N]) {
             unsigned pos = i * d + j;
             v |= (uint16_t)(((B[pos >> 3] >> (pos & 7)) & 1) << j);
         }
+        if (orc_fips && d == 12) v = (uint16_t)(v % ORC_Q); /* FIPS 203 Alg. 6 with m = q */
         F[i] = v;
     }
 }

@@ -109,11 +109,17 @@ class Oracle(_Lib):
     def G(self, data: bytes):
         return self.sponge(72, 0x06, data, 64)
 
-    def J(self, data: bytes):
-        return self.sponge(168, 0x1F, data, 32)
+    def J(self, data: bytes):  # orc_J: SHAKE128 like the reference, SHAKE256 after set_fips(True)
+        buf, p = _u8(np.frombuffer(data, np.uint8) if len(data) else np.zeros(0, np.uint8))
+        out = np.empty(32, np.uint8)
+        self.fn("J")(p, C.c_size_t(len(data)), out.ctypes.data_as(C.POINTER(C.c_uint8)))
+        return out.tobytes()
 
-    def PRF(self, s: bytes, b: int, eta: int):
-        return self.sponge(168, 0x1F, s + bytes([b]), 64 * eta)
+    def PRF(self, s: bytes, b: int, eta: int):  # orc_PRF, same remark
+        buf, p = _u8(np.frombuffer(s, np.uint8))
+        out = np.empty(64 * eta, np.uint8)
+        self.fn("PRF")(p, C.c_uint8(b), C.c_uint(eta), out.ctypes.data_as(C.POINTER(C.c_uint8)))
+        return out.tobytes()
 
     # ---- batch functions ----------------------------------------------------------------
     def _polys(self, name, *ins):
@@ -146,6 +152,10 @@ class Oracle(_Lib):
         r = self.fn("sample_ntt", C.c_int)(s.ctypes.data_as(C.POINTER(C.c_uint8)),
                                            out.ctypes.data_as(C.POINTER(C.c_uint16)))
         return out, s.tobytes(), int(r)
+
+    def set_fips(self, on: bool):
+        """FIPS 203 mode (SHAKE256 PRF/J, reducing ByteDecode12) -- not the reference's behaviour, see mlkem_oracle.c."""
+        self.fn("set_fips")(C.c_int(1 if on else 0))
 
     def set_sample_group_limit(self, usable):
         """TEST HOOK, see orc_set_sample_group_limit (0 restores the reference's 278)."""

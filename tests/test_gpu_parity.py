@@ -250,6 +250,75 @@ def test_check_dk_detects_corruption(mlkem):
     assert st[5] == -5 and st[9] == -5 and (np.delete(st, [5, 9]) == 0).all()
 
 
+def test_public_wrapper_batches(mlkem, oracle):
+    """Batched KEM_KeyGen / KEM_Encaps / KEM_Decaps (ml_kem.c:1233-1359): entropy from the host source, the
+    reference's length checks (-3) and per-item hash check (-5)."""
+    n = 300
+    ek, dk = mlkem.kem_keygen(768, n)
+    assert len({bytes(r) for r in ek[:, -32:]}) == n  # fresh rho per item
+    oek_check = [oracle.check_decaps_input(768, dk[i].tobytes(), 1088) for i in (0, 7, n - 1)]
+    assert oek_check == [0, 0, 0]
+    rc, c, K = mlkem.kem_encaps(768, ek)
+    assert rc == 0
+    bad_dk = dk.copy()
+    bad_dk[17, 1152 + 5] ^= 1  # corrupt the embedded ek of item 17 -> hash check fails for that item only
+    rc, Kd, status = mlkem.kem_decaps(768, bad_dk, c)
+    assert rc == 0 and status[17] == -5 and (np.delete(status, 17) == 0).all()
+    assert (Kd[17] == 0).all() and (np.delete(Kd, 17, 0) == np.delete(K, 17, 0)).all()
+    assert (oracle.decaps(768, dk, c) == K).all()
+    assert mlkem.kem_encaps(768, ek, ek_len=1)[0] == -3            # EncapsDecaps_test.c passes ek_len = 1
+    assert mlkem.kem_decaps(768, dk, c, c_len=5)[0] == -3
+    assert mlkem.kem_decaps(768, dk, c, dk_len=2399)[0] == -3
+    assert mlkem.kem_encaps(999, ek)[0] == -1
+
+
+@pytest.mark.parametrize("ps", SETS)
+def test_fips_mode(oracle, ps):
+    """MLKEM_B200_FLAG_FIPS203: SHAKE256 PRF / J and a real modulus check.  Checked against the oracle's FIPS switch
+    (itself pinned to hashlib and to the `cryptography` package in tests/test_oracle.py) and, for 768 / 1024, directly
+    against `cryptography`."""
+    import crystals_kyber_b200 as ck
+
+    gpu = ck.MLKEM(fips203=True)
+    rng = np.random.default_rng(ps + 1)
+    n = 700
+    d, z, m = (rng.integers(0, 256, (n, 32), dtype=np.uint8) for _ in range(3))
+    ek, dk = gpu.keygen(ps, d, z)
+    c, K = gpu.encaps(ps, ek, m)
+    bad, sel = tamper(c)
+    Kd = gpu.decaps(ps, dk, bad)
+    oracle.set_fips(True)
+    try:
+        oek, odk = oracle.keygen(ps, d, z)
+        oc, oK = oracle.encaps(ps, oek, m)
+        oKd = oracle.decaps(ps, odk, bad)
+        s32 = rng.integers(0, 256, (n, 32), dtype=np.uint8)
+        nonces = rng.integers(0, 256, n, dtype=np.uint8)
+        for eta in (2, 3):
+            assert (gpu.prf_cbd(s32, nonces, eta) == oracle.prf_cbd(s32, nonces, eta)).all()
+    finally:
+        oracle.set_fips(False)
+    assert (ek == oek).all() and (dk == odk).all() and (c == oc).all() and (K == oK).all() and (Kd == oKd).all()
+    ref_ek, _ = oracle.keygen(ps, d[:4], z[:4])
+    assert (ref_ek != ek[:4]).any()  # and it really is a different function from the reference's
+    data = rng.integers(0, 256, (50, 1120), dtype=np.uint8)
+    assert [bytes(r) for r in gpu.hash_batch(3, data, 1120)] == [hashlib.shake_256(bytes(r)).digest(32) for r in data]
+    # modulus check of KEM_Encaps: cannot fail in the reference (D4), fails with -4 here
+    ek_bad = ek[:3].copy()
+    ek_bad[1, 0:2] = 0xFF  # coefficient 0 of item 1 = 0xFFF >= q
+    assert gpu.kem_encaps(ps, ek_bad)[0] == -4
+    assert gpu.kem_encaps(ps, ek[:3])[0] == 0
+    assert ck.MLKEM().kem_encaps(ps, ek_bad)[0] == 0
+    if ps in (768, 1024):
+        mlkem_mod = pytest.importorskip("cryptography.hazmat.primitives.asymmetric.mlkem")
+        Priv = mlkem_mod.MLKEM768PrivateKey if ps == 768 else mlkem_mod.MLKEM1024PrivateKey
+        for i in range(8):
+            key = Priv.from_seed_bytes(d[i].tobytes() + z[i].tobytes())
+            assert key.public_key().public_bytes_raw() == ek[i].tobytes()
+            assert key.decapsulate(c[i].tobytes()) == K[i].tobytes()
+            assert key.decapsulate(bad[i].tobytes()) == Kd[i].tobytes()
+
+
 def test_device_memory_path(mlkem, oracle):
     """torch CUDA tensors in, torch CUDA tensors out, kernels on the current torch stream."""
     import torch
