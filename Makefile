@@ -12,7 +12,7 @@ all: lib tools oracle
 
 lib: $(LIB)
 
-$(LIB): $(CSRC)/mlkem_b200.cu $(CSRC)/mlkem_kernels.cuh $(CSRC)/mlkem_device.cuh $(CSRC)/ml_kem_compat.inl $(CSRC)/mlkem_profile.inl include/mlkem_b200.h include/ml_kem.h
+$(LIB): $(CSRC)/mlkem_b200.cu $(CSRC)/mlkem_kernels.cuh $(CSRC)/mlkem_device.cuh $(CSRC)/ml_kem_compat.inl $(CSRC)/mlkem_profile.inl $(CSRC)/sha3_compat.inl include/mlkem_b200.h include/ml_kem.h include/sha3.h
 	$(NVCC) $(NVFLAGS) -shared -o $@ $(CSRC)/mlkem_b200.cu
 
 tools: build/microbench build/keccak_bench

@@ -251,6 +251,20 @@ class MLKEM:
         n = self._count(data, length)
         return self._call("mlkem_b200_hash_batch", (which, n, length), [(data, np.uint8)], [((n, 64 if which == 1 else 32), np.uint8)])
 
+    def sha3_bits(self, msgs_bits, sfx, c, d):
+        """sha3_b (sha3.c:408) for a batch of equal-length bit strings: msgs_bits [n, nbits] of 0/1 -> [n, d] bits."""
+        bits = np.atleast_2d(np.asarray(msgs_bits, dtype=np.uint8))
+        n, nbits = bits.shape
+        packed = np.packbits(bits, axis=1, bitorder="little") if nbits else np.zeros((n, 1), np.uint8)
+        packed = np.ascontiguousarray(packed)
+        out = np.zeros((n, (d + 7) // 8), np.uint8)
+        sf = np.asarray(sfx, dtype=np.uint8)
+        o = self._opts(False)
+        rc = self.lib.mlkem_b200_sha3_bits_batch(n, C.c_void_p(packed.ctypes.data), nbits, C.c_void_p(sf.ctypes.data), c, d,
+                                                 C.c_void_p(out.ctypes.data), C.byref(o))
+        self._check(rc, "mlkem_b200_sha3_bits_batch")
+        return np.unpackbits(out, axis=1, bitorder="little")[:, :d]
+
     def tables(self):
         z, g = np.empty(128, np.uint16), np.empty(128, np.uint16)
         self._check(self.lib.mlkem_b200_tables(C.c_void_p(z.ctypes.data), C.c_void_p(g.ctypes.data)), "mlkem_b200_tables")

@@ -833,6 +833,43 @@ int mlkem_b200_hash_batch(int which, size_t n, size_t len, const uint8_t *in, ui
     });
 }
 
+// sha3_b of sha3.c:408 for n equal-length messages of `nbits` bits each (bits packed LSB-first into
+// ceil(nbits/8) bytes per message, item-major).  Host memory only: this is the reference's general SHA-3
+// front-end, not part of the KEM hot path.
+int mlkem_b200_sha3_bits_batch(size_t n, const uint8_t *msgs, size_t nbits, const uint8_t sfx[4], unsigned c, size_t d, uint8_t *out,
+                               const mlkem_b200_opts *o) {
+    if (c == 0 || c >= 1600 || (1600 - c) % 64 != 0 || d == 0 || !sfx || !out || (nbits && !msgs)) return MLKEM_B200_ERR_ARG;
+    if (o && o->mem == MLKEM_B200_MEM_DEVICE) return MLKEM_B200_ERR_ARG;
+    if (n == 0) return MLKEM_B200_OK;
+    const size_t r = 1600 - c, slen = sfx[2] ? 4 : 2, m = nbits + slen;  // sha3.c:414-431
+    const size_t x = m % r, padlen = (x == r - 1) ? r + 1 : r - x;       // sha3.c:264-268
+    const size_t total = m + padlen, blk_bytes = r / 8, nblocks = total / r, msg_bytes = (nbits + 7) / 8;
+    const size_t out_bytes = (d + 7) / 8, out_stride = (out_bytes + 7) & ~size_t(7);
+    std::vector<uint8_t> padded(n * nblocks * blk_bytes, 0), res(n * out_stride);
+    for (size_t i = 0; i < n; i++) {  // layout only: N || sfx || pad, bit by bit where not byte aligned
+        uint8_t *P = padded.data() + i * nblocks * blk_bytes;
+        const uint8_t *M = msgs + i * msg_bytes;
+        memcpy(P, M, nbits / 8);
+        for (size_t b = nbits & ~size_t(7); b < nbits; b++) P[b >> 3] |= (uint8_t)(((M[b >> 3] >> (b & 7)) & 1) << (b & 7));
+        for (size_t k = 0; k < slen; k++) P[(nbits + k) >> 3] |= (uint8_t)((sfx[k] & 1) << ((nbits + k) & 7));
+        P[m >> 3] |= (uint8_t)(1u << (m & 7));
+        // the reference's pad() yields 1 0^r 1 when (m+2) % r == 0 and Sponge copies only its first two bits (sha3.c:228,272-277)
+        if ((m + 2) % r != 0) P[(total - 1) >> 3] |= (uint8_t)(1u << ((total - 1) & 7));
+    }
+    const int rl = (int)(r / 64), nb = (int)nblocks, ob = (int)out_bytes;
+    int rc = drive(o, n, 0, {{padded.data(), nullptr, nblocks * blk_bytes}, {nullptr, res.data(), out_stride}},
+                   [=](cudaStream_t st, Arena &, int cn, void **p) {
+                       LAUNCH(k_sponge_padded, cdiv(cn, kHashTPB), kHashTPB, 0, st, cn, (const uint8_t *)p[0], nb, rl, (uint8_t *)p[1], ob);
+                       return 0;
+                   });
+    if (rc) return rc;
+    for (size_t i = 0; i < n; i++) {
+        memcpy(out + i * out_bytes, res.data() + i * out_stride, out_bytes);
+        if (d % 8) out[i * out_bytes + out_bytes - 1] &= (uint8_t)((1u << (d % 8)) - 1);
+    }
+    return MLKEM_B200_OK;
+}
+
 int mlkem_b200_tables(uint16_t zeta[128], uint16_t gamma[128]) {
     int dev;
     DeviceCtx *ctx;
@@ -850,3 +887,4 @@ int mlkem_b200_tables(uint16_t zeta[128], uint16_t gamma[128]) {
 
 #include "mlkem_profile.inl"
 #include "ml_kem_compat.inl"
+#include "sha3_compat.inl"

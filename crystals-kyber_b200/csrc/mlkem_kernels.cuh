@@ -215,6 +215,40 @@ __global__ void __launch_bounds__(kHashTPB) k_hash_words(int n, const uint8_t *_
     for (int w = 0; w < OUTW; w++) store_lane(out + (size_t)OUTW * 8 * i + 8 * w, a[w]);
 }
 
+// General sponge over pre-padded messages (the SHA-3 front-end sha3_b / sha3_h / sha3_s, sha3.c:408-494).
+// The host lays out N || suffix || pad (sha3.c:226,257-277, a pure bit-layout step) as `nblocks` blocks of
+// `rl` 64-bit lanes per message; the device absorbs them and squeezes `out_bytes` bytes following
+// sha3.c:298-311 (a permutation only when more output is still needed).  One message per thread.
+__global__ void __launch_bounds__(kHashTPB) k_sponge_padded(int n, const uint8_t *__restrict__ padded, int nblocks, int rl,
+                                                            uint8_t *__restrict__ out, int out_bytes) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint8_t *p = padded + (size_t)i * nblocks * rl * 8;
+    Lane a[25];
+    keccak_zero(a);
+    for (int b = 0; b < nblocks; b++) {
+#pragma unroll
+        for (int l = 0; l < 25; l++)
+            if (l < rl) {
+                Lane w = load_lane(p + ((size_t)b * rl + l) * 8);
+                a[l].lo ^= w.lo;
+                a[l].hi ^= w.hi;
+            }
+        keccak_f1600(a);
+    }
+    const int out_stride = (out_bytes + 7) & ~7;
+    uint8_t *o = out + (size_t)i * out_stride;
+    int done = 0;
+    while (done < out_bytes) {
+        int take = min(rl * 8, out_bytes - done);
+#pragma unroll
+        for (int l = 0; l < 25; l++)
+            if (l * 8 < take) store_lane(o + done + l * 8, a[l]);
+        done += take;
+        if (done < out_bytes) keccak_f1600(a);
+    }
+}
+
 // =================================================================================================
 // Noise: PRF_eta(seed, nonce) = SHAKE128(seed || nonce) (D1) -> SamplePolyCBD_eta -> [NTT]
 // =================================================================================================

@@ -58,6 +58,7 @@ SIGNATURES = {
     "mlkem_b200_compress_encode_batch": (C.c_int, [C.c_int, C.c_size_t, _P16, _P8, _PO]),
     "mlkem_b200_decode_decompress_batch": (C.c_int, [C.c_int, C.c_size_t, _P8, _P16, _PO]),
     "mlkem_b200_hash_batch": (C.c_int, [C.c_int, C.c_size_t, C.c_size_t, _P8, _P8, _PO]),
+    "mlkem_b200_sha3_bits_batch": (C.c_int, [C.c_size_t, _P8, C.c_size_t, C.c_void_p, C.c_uint, C.c_size_t, _P8, _PO]),
     "mlkem_b200_tables": (C.c_int, [C.c_void_p, C.c_void_p]),
     "mlkem_b200_profile": (None, [C.c_int]),
     "mlkem_b200_set_streams": (None, [C.c_int]),
@@ -68,7 +69,7 @@ SIGNATURES = {
 COMPAT_SYMBOLS = ["ml_errno", "init", "KEM_KeyGen", "KEM_Encaps", "KEM_Decaps", "SampleNTT", "SamplePolyCBD", "NTT",
                   "InverseNTT", "BitRev7", "BitsToBytes", "BytesToBits", "Compress", "Decompress", "ByteEncode",
                   "ByteDecode", "BaseCaseMultiply", "MultiplyNTTs", "PKE_KeyGen", "PKE_Encrypt", "PKE_Decrypt",
-                  "KeyGen_internal", "Encaps_internal", "Decaps_internal"]
+                  "KeyGen_internal", "Encaps_internal", "Decaps_internal", "h2b", "b2h", "sha3_b", "sha3_h", "sha3_s"]
 
 
 def load(path: str = LIB_PATH):

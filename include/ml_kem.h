@@ -24,6 +24,7 @@
 #ifndef ML_KEM_H
 #define ML_KEM_H
 
+#include "sha3.h" /* union bit and the SHA-3 front-end, as the reference's ml_kem.h:10 does */
 #include <stdio.h>
 #include <stdlib.h>
 
@@ -39,9 +40,6 @@ extern "C" {
 
 extern int ml_errno; /* reference ml_kem.h:26, ml_kem.c:16 */
 
-union bit { /* reference sha3.h:15-17 */
-    unsigned int b : 1;
-};
 union byte { /* reference ml_kem.h:35-38 */
     unsigned int s : 7; /* 7-bit index (BitRev7) */
     unsigned int e : 8; /* the byte value */

@@ -172,6 +172,14 @@ int mlkem_b200_decode_decompress_batch(int d, size_t n, const uint8_t *B, uint16
  * G(d||k), which only occurs inside KeyGen). */
 int mlkem_b200_hash_batch(int which, size_t n, size_t len, const uint8_t *in, uint8_t *out, const mlkem_b200_opts *opts);
 
+/* sha3_b, sha3.c:408: the reference's general SHA-3 front-end for messages of any BIT length.
+ * msgs: n messages of nbits bits, packed LSB-first into ceil(nbits/8) bytes each; sfx = the reference's 4 suffix
+ * bits (sfx[2] == 1 selects the 4-bit XOF suffix, else the first 2 bits); c = capacity in bits (1600 - c must be a
+ * multiple of 64: every SHA-3 / SHAKE instance); d = output bits; out: n x ceil(d/8) bytes, unused top bits zero.
+ * Host memory only.  Reproduces the reference's padding deviation for (nbits + |sfx| + 2) % r == 0. */
+int mlkem_b200_sha3_bits_batch(size_t n, const uint8_t *msgs, size_t nbits, const uint8_t sfx[4], unsigned c, size_t d,
+                               uint8_t *out, const mlkem_b200_opts *opts);
+
 /* ---- measurement hooks (bench.py) -------------------------------------------------------------------- */
 
 /* Per-kernel timing: while enabled, every kernel launch of the library is bracketed by CUDA events on its

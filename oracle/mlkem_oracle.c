@@ -161,6 +161,44 @@ ORC_API void orc_shake128(const uint8_t *in, size_t len, uint8_t *out, size_t ou
     orc_sponge(168, 0x1F, in, len, out, outlen);
 }
 
+/*
+ * sha3_b for messages of any BIT length (sha3.c:408 sha3_b, :257 Sponge, :226 pad).  Bits are packed
+ * LSB-first into bytes (bit i of the message = bit i%8 of byte i/8), as h2b / b2h do (sha3.c:329,367).
+ *   nbits message bits, suffix = sfx[0..slen) with slen = 4 when sfx[2] == 1 else 2 (sha3.c:414-431),
+ *   capacity c bits (rate r = 1600 - c, must be a multiple of 8 here), d output bits (zero-padded to a byte).
+ * One deviation of the reference from FIPS 202 is reproduced: pad() computes j = r - ((m+2) % r) (sha3.c:228),
+ * which is r instead of 0 when (m+2) % r == 0, while Sponge copies only r - (m % r) = 2 pad bits (sha3.c:264-277):
+ * the padding is then "10" instead of "11".  It cannot happen for byte-aligned messages (all of ML-KEM).
+ */
+ORC_API int orc_sha3_bits(const uint8_t *msg, size_t nbits, const uint8_t sfx[4], unsigned c, size_t d, uint8_t *out) {
+    if (c == 0 || c >= 1600 || (1600 - c) % 8) return -1;
+    const size_t r = 1600 - c, slen = sfx[2] ? 4 : 2, m = nbits + slen;
+    size_t x = m % r, padlen = (x == r - 1) ? r + 1 : r - x;
+    size_t total = m + padlen, nbytes = total / 8;
+    uint8_t *P = (uint8_t *)__builtin_alloca(nbytes < 4096 ? nbytes : 1);
+    if (nbytes >= 4096) return -2; /* test helper: short messages only */
+    memset(P, 0, nbytes);
+    for (size_t i = 0; i < nbits; i++) P[i >> 3] |= (uint8_t)(((msg[i >> 3] >> (i & 7)) & 1) << (i & 7));
+    for (size_t i = 0; i < slen; i++) P[(nbits + i) >> 3] |= (uint8_t)((sfx[i] & 1) << ((nbits + i) & 7));
+    P[m >> 3] |= (uint8_t)(1u << (m & 7));                    /* first pad bit */
+    if ((m + 2) % r != 0) P[(total - 1) >> 3] |= (uint8_t)(1u << ((total - 1) & 7)); /* last pad bit -- absent in the quirk case */
+    uint64_t s[25];
+    memset(s, 0, sizeof s);
+    for (size_t b = 0; b < total / r; b++) {
+        for (size_t i = 0; i < r / 8; i++) ((uint8_t *)s)[i] ^= P[b * (r / 8) + i];
+        orc_keccak_f1600(s);
+    }
+    size_t outbytes = (d + 7) / 8, done = 0;
+    while (done < outbytes) {
+        size_t take = outbytes - done < r / 8 ? outbytes - done : r / 8;
+        memcpy(out + done, s, take);
+        done += take;
+        if (done < outbytes) orc_keccak_f1600(s);
+    }
+    if (d % 8) out[outbytes - 1] &= (uint8_t)((1u << (d % 8)) - 1);
+    return 0;
+}
+
 /* ------------------------------------------------------------------ */
 /* L1 codec primitives (ml_kem.c:26-177)                                */
 /* ------------------------------------------------------------------ */

@@ -103,6 +103,18 @@ class Oracle(_Lib):
                           out.ctypes.data_as(C.POINTER(C.c_uint8)), C.c_size_t(outlen))
         return out.tobytes()
 
+    def sha3_bits(self, msg_bits, sfx, c, d):
+        """sha3_b on a list/array of bits; returns the d output bits as a numpy array."""
+        bits = np.asarray(msg_bits, dtype=np.uint8)
+        packed = np.packbits(bits, bitorder="little") if bits.size else np.zeros(1, np.uint8)
+        out = np.zeros((d + 7) // 8, np.uint8)
+        sf = np.asarray(sfx, dtype=np.uint8)
+        rc = self.fn("sha3_bits", C.c_int)(packed.ctypes.data_as(C.POINTER(C.c_uint8)), C.c_size_t(bits.size),
+                                           sf.ctypes.data_as(C.POINTER(C.c_uint8)), C.c_uint(c), C.c_size_t(d),
+                                           out.ctypes.data_as(C.POINTER(C.c_uint8)))
+        assert rc == 0
+        return np.unpackbits(out, bitorder="little")[:d]
+
     def H(self, data: bytes):
         return self.sponge(136, 0x06, data, 32)
 
@@ -361,6 +373,23 @@ class Reference(_Lib):
         self.fn("basecase_multiply")(C.c_uint16(a0), C.c_uint16(a1), C.c_uint16(b0), C.c_uint16(b1),
                                      C.c_uint16(gamma), out)
         return int(out[0]), int(out[1])
+
+    def sha3_bits(self, msg_bits, sfx, c, d):
+        bits = np.asarray(msg_bits, dtype=np.uint8)
+        packed = np.packbits(bits, bitorder="little") if bits.size else np.zeros(1, np.uint8)
+        out = np.zeros((d + 7) // 8, np.uint8)
+        sf = np.asarray(sfx, dtype=np.uint8)
+        self.fn("sha3_bits")(packed.ctypes.data_as(C.POINTER(C.c_uint8)), C.c_uint(bits.size),
+                             sf.ctypes.data_as(C.POINTER(C.c_uint8)), C.c_uint(c), C.c_uint(d),
+                             out.ctypes.data_as(C.POINTER(C.c_uint8)))
+        return np.unpackbits(out, bitorder="little")[:d]
+
+    def sha3_s(self, text: bytes, sfx, c, d):
+        out = np.zeros(d // 8, np.uint8)
+        sf = np.asarray(sfx, dtype=np.uint8)
+        self.fn("sha3_s")(C.c_char_p(text), C.c_uint(len(text)), sf.ctypes.data_as(C.POINTER(C.c_uint8)), C.c_uint(c), C.c_uint(d),
+                          out.ctypes.data_as(C.POINTER(C.c_uint8)))
+        return out.tobytes()
 
     def _hash(self, name, data: bytes, outlen):
         b, pb = _u8(np.frombuffer(data, np.uint8) if len(data) else np.zeros(1, np.uint8))

@@ -180,6 +180,27 @@ REF_API void ref_G(const uint8_t *in, unsigned len, uint8_t out[64]) {
     free(o); free(I);
 }
 
+/* sha3_b (sha3.c:408) on bit strings packed LSB-first into bytes; out receives ceil(d/8) bytes. */
+REF_API void ref_sha3_bits(const uint8_t *msg, unsigned nbits, const uint8_t sfx[4], unsigned c, unsigned d, uint8_t *out) {
+    union bit *b = malloc(sizeof(union bit) * (nbits ? nbits : 1));
+    union bit sf[4];
+    for (unsigned i = 0; i < nbits; i++) b[i].b = (msg[i >> 3] >> (i & 7)) & 1;
+    for (int i = 0; i < 4; i++) sf[i].b = sfx[i] & 1;
+    union bit *o = sha3_b(b, nbits, d, c, sf);
+    memset(out, 0, (d + 7) / 8);
+    for (unsigned i = 0; i < d; i++) out[i >> 3] |= (uint8_t)((o[i].b & 1) << (i & 7));
+    free(o);
+    free(b);
+}
+/* sha3_s (sha3.c:465) on a character string. */
+REF_API void ref_sha3_s(const char *str, unsigned len, const uint8_t sfx[4], unsigned c, unsigned d, uint8_t *out) {
+    union bit sf[4];
+    for (int i = 0; i < 4; i++) sf[i].b = sfx[i] & 1;
+    unsigned char *o = sha3_s(str, len, d, c, sf);
+    memcpy(out, o, d / 8);
+    free(o);
+}
+
 static int params_of(int set, struct PARAMS *p) {
     if (set != 512 && set != 768 && set != 1024) return -1;
     *p = init((enum ML_KEM)set);

@@ -43,3 +43,8 @@ def ref_vectors():
 @pytest.fixture(scope="session")
 def archive_stdout():
     return json.load(open(os.path.join(GOLDEN, "archive_stdout.json")))
+
+
+@pytest.fixture(scope="session")
+def sha_examples():
+    return json.load(open(os.path.join(GOLDEN, "sha_examples.json")))

@@ -168,6 +168,47 @@ def ref_vectors(r: Reference):
     return v
 
 
+def sha_examples(r: Reference):
+    """The 16 NIST example files of Test_Examples/SHA, parsed like Test_Archive/SHA/sha_ex_psr.pl does (message bits
+    after "Msg as bit string", expected value after "Hash val is" / "Output val is"), each checked here against the
+    compiled reference the way sha_testing.sh does (XOFs squeeze 4096 bits), plus reference outputs for message
+    lengths around the block boundary, including the lengths where the reference's padding deviates from FIPS 202."""
+    import glob
+    import re
+
+    out = {"examples": [], "boundary": []}
+    for path in sorted(glob.glob(f"{REF}/Test_Examples/SHA/*.txt")):
+        name = os.path.basename(path)[:-4]
+        txt = open(path).read()
+        m = re.search(r"Msg as bit string\n(.*?)\n\s*\n", txt, re.S)
+        bits = re.sub(r"\s", "", m.group(1)) if m else ""
+        bits = bits if re.fullmatch(r"[01]+", bits or "x") else ""
+        m = re.search(r"(?:Hash val is|Output val is)\n(.*)$", txt, re.S)
+        expect = re.sub(r"\s", "", m.group(1)).lower()
+        kind, dlen = name.split("_")[0].split("-")
+        dlen = int(dlen)
+        if kind == "XOF":
+            sfx, c, d = [1, 1, 1, 1], 2 * dlen, 4096
+        else:
+            sfx, c, d = [0, 1, 0, 0], 2 * dlen, dlen
+        got = r.sha3_bits([int(b) for b in bits], sfx, c, d)
+        hexs = np.packbits(got, bitorder="little").tobytes().hex()
+        assert hexs == expect, name
+        out["examples"].append({"name": name, "bits": bits, "sfx": sfx, "c": c, "d": d, "hex": expect})
+    rng = np.random.default_rng(202)
+    for sfx, c, d in (([0, 1, 0, 0], 448, 224), ([0, 1, 0, 0], 512, 256), ([0, 1, 0, 0], 768, 384), ([0, 1, 0, 0], 1024, 512),
+                      ([1, 1, 1, 1], 256, 1400), ([1, 1, 1, 1], 512, 1100)):
+        rr, slen = 1600 - c, (4 if sfx[2] else 2)
+        for n in (rr - slen - 3, rr - slen - 2, rr - slen - 1, rr - slen, rr - slen + 1, 2 * rr - slen - 2, 2 * rr - slen - 1, 13, 777):
+            bits = rng.integers(0, 2, n, dtype=np.uint8)
+            got = r.sha3_bits(bits, sfx, c, d)
+            out["boundary"].append({"bits": "".join(map(str, bits)), "sfx": sfx, "c": c, "d": d,
+                                    "out_bits_sha256": hashlib.sha256(got.tobytes()).hexdigest(),
+                                    "quirk": (n + slen + 2) % rr == 0})
+    out["sha3_s"] = [{"text": t, "hex": r.sha3_s(t.encode(), [0, 1, 0, 0], 512, 256).hex()} for t in ("", "abc", "CRYSTALS-Kyber on B200")]
+    return out
+
+
 def main():
     build()
     r = Reference()
@@ -175,6 +216,7 @@ def main():
     json.dump(arch, open(os.path.join(OUT, "archive_stdout.json"), "w"), indent=1, sort_keys=True)
     vec = ref_vectors(r)
     json.dump(vec, open(os.path.join(OUT, "ref_vectors.json"), "w"), indent=0, sort_keys=True)
+    json.dump(sha_examples(r), open(os.path.join(OUT, "sha_examples.json"), "w"), indent=0, sort_keys=True)
     for k, val in arch.items():
         print(f"{k:28s} {val['sha256'][:16]} {val['bytes']} B")
     print("wrote", OUT)

@@ -319,6 +319,34 @@ def test_fips_mode(oracle, ps):
             assert key.decapsulate(bad[i].tobytes()) == Kd[i].tobytes()
 
 
+def test_sha3_front_end(mlkem, oracle, sha_examples):
+    """sha3_b / sha3_s (sha3.c:408,465) on the GPU: the 16 NIST example files the reference's sha_testing.sh checks,
+    reference outputs for lengths around the block boundary (incl. its padding deviation), random batches vs the oracle,
+    and the reference-signature sha3_s through ctypes."""
+    import ctypes as C
+
+    for ex in sha_examples["examples"]:
+        got = mlkem.sha3_bits([int(b) for b in ex["bits"]] if ex["bits"] else np.zeros((1, 0), np.uint8), ex["sfx"], ex["c"], ex["d"])[0]
+        assert np.packbits(got, bitorder="little").tobytes().hex() == ex["hex"], ex["name"]
+    for b in sha_examples["boundary"]:
+        got = mlkem.sha3_bits([int(x) for x in b["bits"]], b["sfx"], b["c"], b["d"])[0]
+        assert hashlib.sha256(got.tobytes()).hexdigest() == b["out_bits_sha256"]
+    rng = np.random.default_rng(8)
+    for sfx, c, d, nbits in (([0, 1, 0, 0], 512, 256, 1085), ([1, 1, 1, 1], 256, 3000, 2689), ([0, 1, 0, 0], 1024, 512, 7)):
+        msgs = rng.integers(0, 2, (300, nbits), dtype=np.uint8)
+        got = mlkem.sha3_bits(msgs, sfx, c, d)
+        for i in (0, 1, 150, 299):
+            assert (got[i] == oracle.sha3_bits(msgs[i], sfx, c, d)).all()
+    lib = mlkem.lib
+    lib.sha3_s.restype, lib.sha3_s.argtypes = C.POINTER(C.c_ubyte), [C.c_char_p, C.c_uint, C.c_uint, C.c_uint, C.POINTER(C.c_uint)]
+    for rec in sha_examples["sha3_s"]:
+        sfx = (C.c_uint * 4)(0, 1, 0, 0)
+        t = rec["text"].encode()
+        out = lib.sha3_s(t, len(t), 256, 512, sfx)
+        assert bytes(out[i] for i in range(32)).hex() == rec["hex"] == hashlib.sha3_256(t).hexdigest()
+        C.CDLL(None).free(out)
+
+
 def test_device_memory_path(mlkem, oracle):
     """torch CUDA tensors in, torch CUDA tensors out, kernels on the current torch stream."""
     import torch
