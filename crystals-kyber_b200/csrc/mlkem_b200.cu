@@ -24,6 +24,10 @@ using namespace mlkem;
 thread_local char tl_error[512] = "";
 std::atomic<unsigned long long> g_launches{0};
 std::atomic<int> g_streams{2};  // streams that device-memory calls interleave their chunks on (1 = serial)
+int env_int(const char *name, int dflt) {
+    const char *v = getenv(name);
+    return v && *v ? atoi(v) : dflt;
+}
 
 #define CU(call)                                                                                              \
     do {                                                                                                      \
@@ -120,17 +124,19 @@ void build_tables(TwiddleTables &t, uint2 rc[24]) {
 // ------------------------------------------------------------------------------------------------
 // Per-device context
 // ------------------------------------------------------------------------------------------------
-constexpr int kSlots = 2;
+constexpr int kSlots = 4;   // streams / workspaces per device (host-memory calls use the first two)
+constexpr int kHostSlots = 2;
 constexpr int kMaxDevices = 64;
 
 struct DeviceCtx {
     bool ready = false;
-    cudaStream_t stream[kSlots] = {nullptr, nullptr};
-    void *ws[kSlots] = {nullptr, nullptr};  // kernel workspace (intermediates between kernels)
-    size_t ws_bytes[kSlots] = {0, 0};
-    void *io[kSlots] = {nullptr, nullptr};  // device staging of host-resident inputs / outputs
-    size_t io_bytes[kSlots] = {0, 0};
-    cudaEvent_t ev_fork = nullptr, ev_join[kSlots] = {nullptr, nullptr};
+    cudaStream_t stream[kSlots] = {};
+    void *ws[kSlots] = {};  // kernel workspace (intermediates between kernels)
+    size_t ws_bytes[kSlots] = {};
+    void *io[kSlots] = {};  // device staging of host-resident inputs / outputs
+    size_t io_bytes[kSlots] = {};
+    cudaEvent_t ev_fork = nullptr, ev_join[kSlots] = {};
+    std::mutex call_mutex;  // one call at a time enqueues on this device's streams / workspaces
 };
 DeviceCtx g_ctx[kMaxDevices];
 std::mutex g_mutex;
@@ -367,8 +373,14 @@ int drive(const mlkem_b200_opts *o, size_t n, size_t ws_per_item, std::vector<Bu
     int dev;
     DeviceCtx *ctx;
     if (int rc = acquire(o, &dev, &ctx)) return rc;
+    // Calls from several host threads are serialised per device while they enqueue: the workspaces and the
+    // library streams are shared, and stream order then keeps consecutive calls from touching them concurrently.
+    std::lock_guard<std::mutex> call_lock(ctx->call_mutex);
     const bool on_device = o && o->mem == MLKEM_B200_MEM_DEVICE;
-    size_t chunk = (o && o->chunk_items > 0) ? (size_t)o->chunk_items : (on_device ? (size_t)1 << 18 : (size_t)1 << 16);
+    static const int env_chunk = env_int("MLKEM_B200_CHUNK", 0), env_streams = env_int("MLKEM_B200_STREAMS", 0);  // tuning knobs
+    if (env_streams > 0) g_streams.store(env_streams > kSlots ? kSlots : env_streams);
+    size_t chunk = (o && o->chunk_items > 0) ? (size_t)o->chunk_items
+                   : (on_device ? (env_chunk > 0 ? (size_t)env_chunk : (size_t)1 << 18) : (size_t)1 << 16);
     if (chunk > n) chunk = n;
     const size_t nchunks = (n + chunk - 1) / chunk;
     std::vector<void *> ptrs(bufs.size());
@@ -390,7 +402,10 @@ int drive(const mlkem_b200_opts *o, size_t n, size_t ws_per_item, std::vector<Bu
             chunk = ((n + 1) / 2 + 1023) & ~(size_t)1023;
         }
         const size_t nch = (n + chunk - 1) / chunk;
-        const int nstreams = (nch >= 2 && g_streams.load() > 1) ? kSlots : 1;
+        int nstreams = g_streams.load();
+        if (nstreams > kSlots) nstreams = kSlots;
+        if ((size_t)nstreams > nch) nstreams = (int)nch;
+        if (nstreams < 1) nstreams = 1;
         {
             std::lock_guard<std::mutex> lock(g_mutex);
             for (int k = 0; k < nstreams; k++)
@@ -398,7 +413,7 @@ int drive(const mlkem_b200_opts *o, size_t n, size_t ws_per_item, std::vector<Bu
         }
         if (nstreams > 1) {
             CU(cudaEventRecord(ctx->ev_fork, st));
-            for (int k = 0; k < kSlots; k++) CU(cudaStreamWaitEvent(ctx->stream[k], ctx->ev_fork, 0));
+            for (int k = 0; k < nstreams; k++) CU(cudaStreamWaitEvent(ctx->stream[k], ctx->ev_fork, 0));
         }
         for (size_t ci = 0; ci < nch; ci++) {
             size_t i0 = ci * chunk, cn = (i0 + chunk <= n) ? chunk : n - i0;
@@ -406,12 +421,12 @@ int drive(const mlkem_b200_opts *o, size_t n, size_t ws_per_item, std::vector<Bu
                 const uint8_t *base = static_cast<const uint8_t *>(bufs[b].in ? bufs[b].in : bufs[b].out);
                 ptrs[b] = const_cast<uint8_t *>(base) + i0 * bufs[b].item_bytes;
             }
-            const int k = nstreams > 1 ? (int)(ci % kSlots) : 0;
+            const int k = nstreams > 1 ? (int)(ci % nstreams) : 0;
             Arena arena(ctx->ws[k]);
             if (int rc = run(nstreams > 1 ? ctx->stream[k] : st, arena, (int)cn, ptrs.data())) return rc;
         }
         if (nstreams > 1) {
-            for (int k = 0; k < kSlots; k++) {
+            for (int k = 0; k < nstreams; k++) {
                 CU(cudaEventRecord(ctx->ev_join[k], ctx->stream[k]));
                 CU(cudaStreamWaitEvent(st, ctx->ev_join[k], 0));
             }
@@ -425,14 +440,14 @@ int drive(const mlkem_b200_opts *o, size_t n, size_t ws_per_item, std::vector<Bu
     for (auto &b : bufs) io_per_item += (b.item_bytes + 15) & ~size_t(15);
     {
         std::lock_guard<std::mutex> lock(g_mutex);
-        const int nslots = nchunks > 1 ? kSlots : 1;
+        const int nslots = nchunks > 1 ? kHostSlots : 1;
         for (int s = 0; s < nslots; s++) {
             if (int rc = ensure_buffer(&ctx->ws[s], &ctx->ws_bytes[s], chunk * ws_per_item + kWsSlack)) return rc;
             if (int rc = ensure_buffer(&ctx->io[s], &ctx->io_bytes[s], chunk * io_per_item + 256 * bufs.size())) return rc;
         }
     }
     for (size_t ci = 0; ci < nchunks; ci++) {
-        const int s = (int)(ci % kSlots);
+        const int s = (int)(ci % kHostSlots);
         cudaStream_t st = ctx->stream[s];
         size_t i0 = ci * chunk, cn = (i0 + chunk <= n) ? chunk : n - i0;
         Arena io(ctx->io[s]);
@@ -449,7 +464,7 @@ int drive(const mlkem_b200_opts *o, size_t n, size_t ws_per_item, std::vector<Bu
                 CU(cudaMemcpyAsync(static_cast<uint8_t *>(bufs[b].out) + i0 * bufs[b].item_bytes, ptrs[b], cn * bufs[b].item_bytes,
                                    cudaMemcpyDeviceToHost, st));
     }
-    for (int s = 0; s < kSlots; s++) CU(cudaStreamSynchronize(ctx->stream[s]));
+    for (int s = 0; s < kHostSlots; s++) CU(cudaStreamSynchronize(ctx->stream[s]));
     return MLKEM_B200_OK;
 }
 
