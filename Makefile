@@ -25,8 +25,9 @@ build/keccak_bench: $(CSRC)/keccak_bench.cu
 	mkdir -p build
 	$(NVCC) $(ARCH) -O3 -lineinfo -o $@ $<
 
-oracle:
+oracle: lib
 	$(MAKE) -C oracle
+	$(MAKE) -C oracle drivers
 
 clean:
 	rm -f $(LIB) build/microbench build/keccak_bench

@@ -465,6 +465,38 @@ def test_reference_signature_api(mlkem, oracle):
         libc.free(ptr)
 
 
+def test_unmodified_reference_drivers_linked_against_the_library(mlkem, archive_stdout):
+    """The reference's own Test_Archive drivers, compiled UNMODIFIED from /root/reference against include/ml_kem.h and
+    linked with libmlkem_b200.so instead of ml_kem.o (oracle/Makefile `drivers`; the binaries travel in oracle/_ref).
+    Their stdout must be byte-identical to what they print when linked with the reference itself."""
+    import os
+    import subprocess
+
+    ddir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "drivers")
+    if not os.path.isdir(ddir):
+        pytest.skip("oracle/_ref/drivers not built (needs /root/reference at build time)")
+    ran = 0
+    for name, rec in archive_stdout.items():
+        exe = os.path.join(ddir, name)
+        if not os.path.exists(exe):
+            continue
+        out = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=600)
+        assert hashlib.sha256(out.stdout).hexdigest() == rec["sha256"], (name, out.stdout[:200], out.stderr[:200])
+        ran += 1
+    assert ran >= 9
+    # EncapsDecaps_test.c (makefile target test12) passes ek_len = 1: the reference prints the type-check error and exits 1
+    out = subprocess.run([os.path.join(ddir, "EncapsDecaps_test")], stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=120)
+    assert out.returncode == 1 and b"KEM_Encaps() :: Type check failed" in out.stderr and out.stdout == b""
+    # KeyGen_test.c (target test11): random keys; structure only
+    out = subprocess.run([os.path.join(ddir, "KeyGen_test")], stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=120)
+    assert out.returncode == 0
+    ek_line, dk_line = [l for l in out.stdout.decode().split("\n") if l.startswith(("Encapsulation key:", "Decapsulation key:"))]
+    ek = [int(x) for x in ek_line.split(":")[1].split()]
+    dk = [int(x) for x in dk_line.split(":")[1].split()]
+    assert len(ek) == 800 and len(dk) == 1632 and dk[768:768 + 800] == ek
+    assert bytes(dk[768 + 800:768 + 832]) == hashlib.sha3_256(bytes(ek)).digest()
+
+
 def test_live_reference_if_present(mlkem, reference):
     """When oracle/_ref travelled to the box: the CUDA library against the compiled reference itself."""
     rng = np.random.default_rng(99)
