@@ -465,6 +465,33 @@ def test_reference_signature_api(mlkem, oracle):
         libc.free(ptr)
 
 
+def test_argument_errors_and_empty_batches(mlkem):
+    import ctypes as C
+
+    import torch
+
+    from crystals_kyber_b200.lib import MEM_DEVICE, Opts
+
+    lib = mlkem.lib
+    buf = np.zeros(4096, np.uint8)
+    p = C.c_void_p(buf.ctypes.data)
+    assert lib.mlkem_b200_keygen_batch(768, 0, p, p, p, p, None) == 0           # empty batch: nothing to do
+    assert lib.mlkem_b200_keygen_batch(999, 1, p, p, p, p, None) == -1          # ml_errno -1: unknown parameter set
+    assert lib.mlkem_b200_keygen_batch(768, 1, None, p, p, p, None) == -11      # NULL buffer
+    assert lib.mlkem_b200_byte_encode_batch(7, 1, p, p, None) == -11            # d not in {1,4,5,10,11,12}
+    assert lib.mlkem_b200_cbd_batch(4, 1, p, p, None) == -11                    # eta not in {2,3}
+    assert lib.mlkem_b200_compress_batch(10, 12, p, p, None) == -11             # element count must be a multiple of 8
+    assert lib.mlkem_b200_hash_batch(0, 1, 13, p, p, None) == -11               # length must be a multiple of 8
+    t = torch.zeros(8192, dtype=torch.uint8, device="cuda")
+    o = Opts(0, MEM_DEVICE, None, 0, 0, 0)
+    mis = C.c_void_p(t.data_ptr() + 4)
+    ok = C.c_void_p(t.data_ptr())
+    assert lib.mlkem_b200_ntt_batch(1, mis, ok, C.byref(o)) == -11              # device pointers must be 16-byte aligned
+    assert b"aligned" in lib.mlkem_b200_last_error()
+    assert mlkem.ntt(np.zeros((0, 256), np.uint16)).shape == (0, 256)
+    assert mlkem.keygen(768, np.zeros((0, 32), np.uint8), np.zeros((0, 32), np.uint8))[0].shape == (0, 1184)
+
+
 def test_unmodified_reference_drivers_linked_against_the_library(mlkem, archive_stdout):
     """The reference's own Test_Archive drivers, compiled UNMODIFIED from /root/reference against include/ml_kem.h and
     linked with libmlkem_b200.so instead of ml_kem.o (oracle/Makefile `drivers`; the binaries travel in oracle/_ref).
