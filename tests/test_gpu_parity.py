@@ -465,6 +465,44 @@ def test_reference_signature_api(mlkem, oracle):
         libc.free(ptr)
 
 
+def test_second_device_from_one_process(mlkem, oracle):
+    """opts.device selects the GPU: one process driving two devices (shard by index, no collective)."""
+    import threading
+
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import crystals_kyber_b200 as ck
+    from crystals_kyber_b200 import workload as wl
+
+    n = 4000
+    results = {}
+
+    def run(dev):
+        b, e = ck.shard_range(n, dev, 2)
+        device = torch.device("cuda", dev)
+        d, z, m = wl.derive_inputs(lambda msg, ln: mlkem.hash_batch(1, msg, ln), b, e, device)
+        ek, dk = mlkem.keygen(768, d, z)
+        c, K = mlkem.encaps(768, ek, m)
+        Kd = mlkem.decaps(768, dk, c)
+        torch.cuda.synchronize(device)
+        results[dev] = tuple(t.cpu().numpy() for t in (ek, c, K, Kd))
+
+    threads = [threading.Thread(target=run, args=(dev,)) for dev in (0, 1)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    d, z, m = wl.derive_inputs(lambda msg, ln: oracle.hash_batch(1, msg, ln), 0, n)
+    oek, odk = oracle.keygen(768, d, z)
+    oc, oK = oracle.encaps(768, oek, m)
+    for dev in (0, 1):
+        b, e = ck.shard_range(n, dev, 2)
+        ek, c, K, Kd = results[dev]
+        assert (ek == oek[b:e]).all() and (c == oc[b:e]).all() and (K == oK[b:e]).all() and (Kd == oK[b:e]).all()
+
+
 def test_argument_errors_and_empty_batches(mlkem):
     import ctypes as C
 
