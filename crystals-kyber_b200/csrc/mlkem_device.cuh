@@ -89,6 +89,16 @@ __device__ __forceinline__ uint32_t compress(uint32_t x) {
     qh += (r >= kQ);
     return qh & ((1u << D) - 1u);
 }
+// The same for CANONICAL x (< q) and the d of the parameter sets: a single multiply-high.  The constants were found
+// by exhaustive search over all x < q (tools/find_compress_constants.py): floor(((x << d) + c) M / 2^32) mod 2^d equals
+// Compress_d(x) with (c, M) = (1665, 1290167) for d in {1, 4, 5} and (1664, 1290168) for d in {10, 11}.
+template <int D>
+__device__ __forceinline__ uint32_t compress_canon(uint32_t x) {
+    static_assert(D == 1 || D == 4 || D == 5 || D == 10 || D == 11, "no verified constants for this d");
+    constexpr uint32_t c = (D >= 10) ? 1664u : 1665u, M = (D >= 10) ? 1290168u : 1290167u;
+    return __umulhi(x * (1u << D) + c, M) & ((1u << D) - 1u);
+}
+
 // ml_kem.c:104 Decompress_d: (q y + 2^(d-1)) >> d.
 template <int D>
 __device__ __forceinline__ uint32_t decompress(uint32_t y) {
@@ -415,23 +425,34 @@ __device__ __forceinline__ void basemul_acc(uint32_t &acc0, uint32_t &acc1, uint
 // coefficient i occupies bits [d i, d i + d).  A lane that owns 8 consecutive coefficients therefore
 // owns exactly d consecutive bytes.
 // ------------------------------------------------------------------------------------------------
-// Pack 8 d-bit values into d bytes at `dst` (shared memory, byte granular).
+// Pack 8 d-bit values into d bytes at `dst` (shared memory; dst = row + d * lane, so it is 2-byte aligned for even d
+// and 4-byte aligned for d = 4, 12).  The packed words are built with multiply-adds (the fields are disjoint, so
+// + is |) to keep the work on the fma pipe.
 template <int D>
 __device__ __forceinline__ void pack8(const uint32_t v[8], uint8_t *dst) {
-    uint64_t lo = 0;  // bits 0..63
-    uint32_t hi = 0;  // bits 64..95
+    constexpr int NW = (8 * D + 31) / 32;
+    uint32_t w[NW];
 #pragma unroll
-    for (int i = 0; i < 8; i++) {
-        const int off = D * i;
-        if (off < 64) {
-            lo |= (uint64_t)v[i] << off;
-            if (off + D > 64) hi |= v[i] >> (64 - off);
-        } else {
-            hi |= v[i] << (off - 64);
+    for (int k = 0; k < NW; k++) {
+        uint32_t acc = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const int off = D * i - 32 * k;  // bit offset of field i relative to word k
+            if (off >= 0 && off < 32) acc += v[i] * (1u << off);
+            else if (off < 0 && off + D > 0) acc += v[i] >> (-off);
         }
+        w[k] = acc;
     }
+    if (D % 4 == 0) {  // d = 4, 12: whole words
 #pragma unroll
-    for (int b = 0; b < D; b++) dst[b] = (uint8_t)(b < 8 ? (lo >> (8 * b)) : (hi >> (8 * (b - 8))));
+        for (int k = 0; k < NW; k++) reinterpret_cast<uint32_t *>(dst)[k] = w[k];
+    } else if (D % 2 == 0) {  // d = 10: five half-words
+#pragma unroll
+        for (int h = 0; h < D / 2; h++) reinterpret_cast<uint16_t *>(dst)[h] = (uint16_t)(w[h >> 1] >> (16 * (h & 1)));
+    } else {
+#pragma unroll
+        for (int b8 = 0; b8 < D; b8++) dst[b8] = (uint8_t)(w[b8 >> 2] >> (8 * (b8 & 3)));
+    }
 }
 // Unpack the 8 d-bit values owned by `lane` (bits [8 d lane, 8 d lane + 8 d) of the row) from a packed row
 // in shared memory.  `row` must be 4-byte aligned and readable up to 4 bytes past its end.

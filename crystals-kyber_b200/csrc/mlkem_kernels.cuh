@@ -596,7 +596,7 @@ __global__ void __launch_bounds__(32 * P::K) k_sample_matvec(MatvecArgs g) {
 #pragma unroll
             for (int r = 0; r < 8; r++) {
                 uint32_t code = (__ldg(codes + (lane >> 3) + 4 * r) >> (4 * (lane & 7))) & 15u;
-                x[r] = compress<P::DU>(add_noise_code(x[r], code));
+                x[r] = compress_canon<P::DU>(add_noise_code(x[r], code));
             }
             store_scratch_A(x, scratch, lane);
             __syncwarp();
@@ -696,7 +696,7 @@ __global__ void __launch_bounds__(kWarpTPB, 8) k_encrypt_v(EncVArgs g) {
     for (int r = 0; r < 8; r++) {
         uint32_t code = (__ldg(codes + (lane >> 3) + 4 * r) >> (4 * (lane & 7))) & 15u;
         uint32_t mu = ((__ldg(mw + r) >> lane) & 1u) * 1665u;  // Decompress_1(bit) = 1665 bit (ml_kem.c:867-870)
-        x[r] = compress<P::DV>(csubq(add_noise_code(x[r], code) + mu));
+        x[r] = compress_canon<P::DV>(csubq(add_noise_code(x[r], code) + mu));
     }
     store_scratch_A(x, scratch, lane);
     __syncwarp();
@@ -769,7 +769,7 @@ __global__ void __launch_bounds__(kWarpTPB) k_decrypt(int n, const uint8_t *__re
     for (int r = 0; r < 8; r++) {
         uint32_t v = decompress<P::DV>(unpack1<P::DV>(ct + P::C1ROW * K, idxA(lane, r)));
         uint32_t w = csubq(v + kQ - x[r]);
-        uint32_t word = __ballot_sync(kFullMask, compress<1>(w) & 1u);
+        uint32_t word = __ballot_sync(kFullMask, compress_canon<1>(w) & 1u);
         if (lane == r) myword = word;
     }
     if (lane < 8) reinterpret_cast<uint32_t *>(mout + 32 * (size_t)item)[lane] = myword;
