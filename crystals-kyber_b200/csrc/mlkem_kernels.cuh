@@ -542,26 +542,57 @@ __global__ void __launch_bounds__(32 * P::K) k_sample_matvec(MatvecArgs g) {
     LaneTwiddles tw;
     if (MODE != kModeKeyGen) load_lane_twiddles_inv(tw, lane);
 
+    // The vector operand of a group is fetched one group ahead (software pipelining in registers): its global-load
+    // latency was the largest exposed stall of phase 2 in the ncu source view.
+    // (16-bit loads instead of 32-bit loads + mask/shift: the load/store pipe has slack, the alu pipe does not.)
+    uint32_t vnext[8 * K];
+    auto fetch_vec = [&](int grp, uint32_t *dst) {
+        const long long gg = (long long)blockIdx.x * 32 + grp;
+        const int item = (int)(gg / K);
+        if (grp < 32 && item < g.n) {
+            const uint16_t *vec = g.vec + g.vec_stride * item;
+#pragma unroll
+            for (int j = 0; j < K; j++)
+#pragma unroll
+                for (int r = 0; r < 4; r++) {
+                    int t = lane + 32 * r;
+                    dst[8 * j + 2 * r] = __ldg(vec + 256 * j + 2 * t);
+                    dst[8 * j + 2 * r + 1] = __ldg(vec + 256 * j + 2 * t + 1);
+                }
+        }
+    };
+    fetch_vec(warp, vnext);
+
     for (int grp = warp; grp < 32; grp += K) {
         const long long gg = (long long)blockIdx.x * 32 + grp;
         const int item = (int)(gg / K), row = (int)(gg - (long long)item * K);
         if (item >= g.n) break;  // groups are ordered by item
         const uint32_t *slot0 = s_slots + kSlotWords * (grp * K);
+        uint32_t vcur[8 * K];
+#pragma unroll
+        for (int i = 0; i < 8 * K; i++) vcur[i] = vnext[i];
+        fetch_vec(grp + K, vnext);
+        // compare mode: the received ciphertext row is needed only at the very end of the iteration -- load it now
+        constexpr int kCmpWords = (8 * P::DU + 31) / 32;
+        uint32_t cmpw[kCmpWords];
+        if (MODE == kModeEncryptCompare) {
+            const uint32_t *cw = reinterpret_cast<const uint32_t *>(g.cmp + g.out_stride * item + (size_t)P::C1ROW * row);
+#pragma unroll
+            for (int i = 0; i < kCmpWords; i++) cmpw[i] = (lane + 32 * i < 8 * P::DU) ? __ldg(cw + lane + 32 * i) : 0u;
+        }
         // ---- row . vector in the NTT domain (ml_kem.c:618 VectorMultiply), lazily accumulated.
         // Lane handles coefficient pairs t = lane + 32 r (conflict-free slot reads, coalesced vector reads).
         uint32_t acc[8];
 #pragma unroll
         for (int r = 0; r < 8; r++) acc[r] = 0;
-        // (16-bit loads instead of 32-bit loads + mask/shift: the load/store pipe has slack, the alu pipe does not)
-        const uint16_t *vec = g.vec + g.vec_stride * item;
 #pragma unroll
         for (int j = 0; j < K; j++) {
             const uint16_t *aw = reinterpret_cast<const uint16_t *>(slot0 + kSlotWords * j);
 #pragma unroll
             for (int r = 0; r < 4; r++) {
                 int t = lane + 32 * r;
-                uint32_t a0 = aw[2 * t], a1 = aw[2 * t + 1], b0 = __ldg(vec + 256 * j + 2 * t), b1 = __ldg(vec + 256 * j + 2 * t + 1);
-                basemul_acc(acc[2 * r], acc[2 * r + 1], a0, a1, b0, b1, gam[r]);
+                uint32_t a0 = aw[2 * t], a1 = aw[2 * t + 1];
+                basemul_acc(acc[2 * r], acc[2 * r + 1], a0, a1, vcur[8 * j + 2 * r], vcur[8 * j + 2 * r + 1], gam[r]);
             }
         }
         int nwords;
@@ -608,9 +639,10 @@ __global__ void __launch_bounds__(32 * P::K) k_sample_matvec(MatvecArgs g) {
         const uint32_t *stw = reinterpret_cast<const uint32_t *>(stage);
         const size_t row_off = (MODE == kModeKeyGen ? 384 : P::C1ROW) * (size_t)row;
         if (MODE == kModeEncryptCompare) {
-            const uint32_t *cw = reinterpret_cast<const uint32_t *>(g.cmp + g.out_stride * item + row_off);
             uint32_t d = 0;
-            for (int w = lane; w < nwords; w += 32) d |= stw[w] ^ __ldg(cw + w);
+#pragma unroll
+            for (int i = 0; i < kCmpWords; i++)
+                if (lane + 32 * i < nwords) d |= stw[lane + 32 * i] ^ cmpw[i];
             d = __any_sync(kFullMask, d != 0) ? 1u : 0u;
             if (lane == 0) atomicOr(g.flags + item, d);  // unconditional: no data-dependent control flow
         } else {
