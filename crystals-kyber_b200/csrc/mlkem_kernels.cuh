@@ -684,71 +684,106 @@ __device__ __forceinline__ void stage_row(uint8_t *dst, const uint8_t *src, int 
     for (int i = lane; i < bytes / 16; i += 32) d4[i] = __ldg(s4 + i);
 }
 
+// Asynchronous global -> shared copies (cp.async, LDGSTS): the persistent warps of k_encrypt_v / k_decrypt fetch the
+// inputs of their NEXT item while they work on the current one (two buffers per warp), so the global-load latency is
+// off the critical path without spending registers on the prefetch.
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
+    uint32_t s = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void stage_row_async(uint8_t *dst, const uint8_t *src, int bytes, int lane) {
+    for (int i = lane; i < bytes / 16; i += 32) cp_async16(dst + 16 * i, src + 16 * i);
+}
+
 // v = InverseNTT(t^ . y^) + e2 + Decompress_1(m)  (ml_kem.c:867-880); c2 = ByteEncode_dv(Compress_dv(v)) (:899-904).
 // One item per warp; every lane owns 8 consecutive coefficients (= 12 bytes of each ByteEncode12 row).
 // COMPARE: OR the mismatch against the received ciphertext into flags instead of storing.
 template <class P, bool COMPARE>
 __global__ void __launch_bounds__(kWarpTPB, 8) k_encrypt_v(EncVArgs g) {
     constexpr int K = P::K, NW = kWarpTPB / 32;
+    constexpr int kRowsBytes = 384 * K, kVecBytes = 512 * K, kBufBytes = kRowsBytes + kVecBytes + 16;  // t^ rows | y^ | slack
     __shared__ __align__(16) uint16_t s_scratch[NW * kScratchU16];
-    __shared__ __align__(16) uint8_t s_rows[NW * (384 * K + 16)];
+    __shared__ __align__(16) uint8_t s_in[NW * 2 * kBufBytes];
     __shared__ __align__(16) uint8_t s_stage[NW * 32 * P::DV];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint16_t *scratch = s_scratch + warp * kScratchU16;
-    uint8_t *rows = s_rows + warp * (384 * K + 16);
+    uint8_t *inbuf = s_in + warp * 2 * kBufBytes;
     uint8_t *stage = s_stage + warp * 32 * P::DV;
     uint2 gam[4];
 #pragma unroll
     for (int i = 0; i < 4; i++) gam[i] = lane_gamma(4 * lane + i);
     LaneTwiddles tw;
     load_lane_twiddles_inv(tw, lane);
-  for (int item = blockIdx.x * NW + warp; item < g.n; item += gridDim.x * NW) {  // persistent warps
-    stage_row(rows, g.ek + g.ek_stride * item, 384 * K, lane);
-    __syncwarp();
-
-    const uint16_t *yv = g.yhat + g.yhat_stride * item;
-    uint32_t acc[8];
+    auto fetch = [&](int item, uint8_t *buf) {
+        stage_row_async(buf, g.ek + g.ek_stride * item, kRowsBytes, lane);
+        stage_row_async(buf + kRowsBytes, reinterpret_cast<const uint8_t *>(g.yhat + g.yhat_stride * item), kVecBytes, lane);
+    };
+    const int stride = gridDim.x * NW;
+    int item = blockIdx.x * NW + warp, cur = 0;
+    if (item < g.n) fetch(item, inbuf);
+    cp_async_commit();
+    for (; item < g.n; item += stride, cur ^= 1) {  // persistent warps
+        if (item + stride < g.n) fetch(item + stride, inbuf + (cur ^ 1) * kBufBytes);
+        cp_async_commit();
+        cp_async_wait<1>();  // all but the newest group have landed: this item's buffer is complete
+        __syncwarp();
+        const uint8_t *rows = inbuf + cur * kBufBytes;
+        const uint16_t *yv = reinterpret_cast<const uint16_t *>(rows + kRowsBytes);
+        // e2 codes and the message bits are needed after the inverse transform: issue their loads now
+        const uint32_t *codes = g.addc + g.addc_stride * item + 32 * K;
+        const uint32_t *mw = reinterpret_cast<const uint32_t *>(g.m + 32 * (size_t)item);
+        uint32_t cw8[8], mw8[8];
 #pragma unroll
-    for (int r = 0; r < 8; r++) acc[r] = 0;
+        for (int r = 0; r < 8; r++) {
+            cw8[r] = __ldg(codes + (lane >> 3) + 4 * r);
+            mw8[r] = __ldg(mw + r);
+        }
+        uint32_t acc[8];
 #pragma unroll
-    for (int j = 0; j < K; j++) {
-        uint32_t t[8], y[8];
-        unpack8<12>(rows + 384 * j, lane, t);  // ByteDecode12 without reduction (ml_kem.c:806-808, D4)
-        load_layoutC_global(y, lane, yv + 256 * j);
+        for (int r = 0; r < 8; r++) acc[r] = 0;
 #pragma unroll
-        for (int i = 0; i < 4; i++) basemul_acc(acc[2 * i], acc[2 * i + 1], t[2 * i], t[2 * i + 1], y[2 * i], y[2 * i + 1], gam[i]);
+        for (int j = 0; j < K; j++) {
+            uint32_t t[8], y[8];
+            unpack8<12>(rows + 384 * j, lane, t);  // ByteDecode12 without reduction (ml_kem.c:806-808, D4)
+            unpack_pairs(*reinterpret_cast<const uint4 *>(yv + 256 * j + 8 * lane), y);
+#pragma unroll
+            for (int i = 0; i < 4; i++) basemul_acc(acc[2 * i], acc[2 * i + 1], t[2 * i], t[2 * i + 1], y[2 * i], y[2 * i + 1], gam[i]);
+        }
+        uint32_t x[8];
+#pragma unroll
+        for (int r = 0; r < 8; r++) x[r] = canon32(acc[r]);
+        intt_warp(x, scratch, lane, tw);  // layout C in, layout A out
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+            uint32_t code = (cw8[r] >> (4 * (lane & 7))) & 15u;
+            uint32_t mu = ((mw8[r] >> lane) & 1u) * 1665u;  // Decompress_1(bit) = 1665 bit (ml_kem.c:867-870)
+            x[r] = compress_canon<P::DV>(csubq(add_noise_code(x[r], code) + mu));
+        }
+        store_scratch_A(x, scratch, lane);
+        __syncwarp();
+        load_scratch_C(x, scratch, lane);
+        pack8<P::DV>(x, stage + P::DV * lane);
+        __syncwarp();
+        const uint32_t *stw = reinterpret_cast<const uint32_t *>(stage);
+        const size_t off = (size_t)P::C1ROW * K;
+        if (COMPARE) {
+            const uint32_t *cw = reinterpret_cast<const uint32_t *>(g.cmp + g.c_stride * item + off);
+            uint32_t d = 0;
+            for (int w = lane; w < 8 * P::DV; w += 32) d |= stw[w] ^ __ldg(cw + w);
+            d = __any_sync(kFullMask, d != 0) ? 1u : 0u;
+            if (lane == 0) atomicOr(g.flags + item, d);
+        } else {
+            uint32_t *ow = reinterpret_cast<uint32_t *>(g.c + g.c_stride * item + off);
+            for (int w = lane; w < 8 * P::DV; w += 32) ow[w] = stw[w];
+        }
+        __syncwarp();
     }
-    uint32_t x[8];
-#pragma unroll
-    for (int r = 0; r < 8; r++) x[r] = canon32(acc[r]);
-    intt_warp(x, scratch, lane, tw);  // layout C in, layout A out
-    const uint32_t *codes = g.addc + g.addc_stride * item + 32 * K;
-    const uint32_t *mw = reinterpret_cast<const uint32_t *>(g.m + 32 * (size_t)item);
-#pragma unroll
-    for (int r = 0; r < 8; r++) {
-        uint32_t code = (__ldg(codes + (lane >> 3) + 4 * r) >> (4 * (lane & 7))) & 15u;
-        uint32_t mu = ((__ldg(mw + r) >> lane) & 1u) * 1665u;  // Decompress_1(bit) = 1665 bit (ml_kem.c:867-870)
-        x[r] = compress_canon<P::DV>(csubq(add_noise_code(x[r], code) + mu));
-    }
-    store_scratch_A(x, scratch, lane);
-    __syncwarp();
-    load_scratch_C(x, scratch, lane);
-    pack8<P::DV>(x, stage + P::DV * lane);
-    __syncwarp();
-    const uint32_t *stw = reinterpret_cast<const uint32_t *>(stage);
-    const size_t off = (size_t)P::C1ROW * K;
-    if (COMPARE) {
-        const uint32_t *cw = reinterpret_cast<const uint32_t *>(g.cmp + g.c_stride * item + off);
-        uint32_t d = 0;
-        for (int w = lane; w < 8 * P::DV; w += 32) d |= stw[w] ^ __ldg(cw + w);
-        d = __any_sync(kFullMask, d != 0) ? 1u : 0u;
-        if (lane == 0) atomicOr(g.flags + item, d);
-    } else {
-        uint32_t *ow = reinterpret_cast<uint32_t *>(g.c + g.c_stride * item + off);
-        for (int w = lane; w < 8 * P::DV; w += 32) ow[w] = stw[w];
-    }
-    __syncwarp();
-  }
+    cp_async_wait<0>();
 }
 
 // ml_kem.c:942 PKE_Decrypt: m' = ByteEncode_1(Compress_1(v - InverseNTT(s^ . NTT(u)))).  One item per warp; the
@@ -757,56 +792,67 @@ template <class P>
 __global__ void __launch_bounds__(kWarpTPB) k_decrypt(int n, const uint8_t *__restrict__ dk, size_t dk_stride,
                                                       const uint8_t *__restrict__ c, uint8_t *__restrict__ mout) {
     constexpr int K = P::K, NW = kWarpTPB / 32;
+    constexpr int kSkBytes = 384 * K, kBufBytes = P::C + kSkBytes + 32;  // ciphertext | s^ rows | slack
     __shared__ __align__(16) uint16_t s_scratch[NW * kScratchU16];
-    __shared__ __align__(16) uint8_t s_ct[NW * (P::C + 16)];
-    __shared__ __align__(16) uint8_t s_sk[NW * (384 * K + 16)];
+    __shared__ __align__(16) uint8_t s_in[NW * 2 * kBufBytes];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint16_t *scratch = s_scratch + warp * kScratchU16;
-    uint8_t *ct = s_ct + warp * (P::C + 16), *sk = s_sk + warp * (384 * K + 16);
+    uint8_t *inbuf = s_in + warp * 2 * kBufBytes;
     uint2 gam[4];
 #pragma unroll
     for (int i = 0; i < 4; i++) gam[i] = lane_gamma(4 * lane + i);
     LaneTwiddles tw, twi;
     load_lane_twiddles(tw, lane);
     load_lane_twiddles_inv(twi, lane);
-  for (int item = blockIdx.x * NW + warp; item < n; item += gridDim.x * NW) {  // persistent warps
-    stage_row(ct, c + (size_t)P::C * item, P::C, lane);
-    stage_row(sk, dk + dk_stride * item, 384 * K, lane);
-    __syncwarp();
-    uint32_t acc[8];
-#pragma unroll
-    for (int r = 0; r < 8; r++) acc[r] = 0;
-    for (int i = 0; i < K; i++) {
-        // u^[i] = NTT(Decompress_du(ByteDecode_du(c1[i])))   (ml_kem.c:978-987)
-        uint32_t x[8], sh[8];
-        unpack8<P::DU>(ct + P::C1ROW * i, lane, x);
-#pragma unroll
-        for (int r = 0; r < 8; r++) x[r] = decompress<P::DU>(x[r]);
-        store_scratch_C(x, scratch, lane);
+    auto fetch = [&](int item, uint8_t *buf) {
+        stage_row_async(buf, c + (size_t)P::C * item, P::C, lane);
+        stage_row_async(buf + P::C, dk + dk_stride * item, kSkBytes, lane);
+    };
+    const int stride = gridDim.x * NW;
+    int item = blockIdx.x * NW + warp, cur = 0;
+    if (item < n) fetch(item, inbuf);
+    cp_async_commit();
+    for (; item < n; item += stride, cur ^= 1) {  // persistent warps
+        if (item + stride < n) fetch(item + stride, inbuf + (cur ^ 1) * kBufBytes);
+        cp_async_commit();
+        cp_async_wait<1>();
         __syncwarp();
-        load_scratch_A(x, scratch, lane);
+        const uint8_t *ct = inbuf + cur * kBufBytes, *sk = ct + P::C;
+        uint32_t acc[8];
+#pragma unroll
+        for (int r = 0; r < 8; r++) acc[r] = 0;
+        for (int i = 0; i < K; i++) {
+            // u^[i] = NTT(Decompress_du(ByteDecode_du(c1[i])))   (ml_kem.c:978-987)
+            uint32_t x[8], sh[8];
+            unpack8<P::DU>(ct + P::C1ROW * i, lane, x);
+#pragma unroll
+            for (int r = 0; r < 8; r++) x[r] = decompress<P::DU>(x[r]);
+            store_scratch_C(x, scratch, lane);
+            __syncwarp();
+            load_scratch_A(x, scratch, lane);
+            __syncwarp();
+            ntt_warp(x, scratch, lane, tw);  // layout C out: 8 consecutive coefficients = 4 base-case pairs
+            unpack8<12>(sk + 384 * i, lane, sh);  // s^[i] = ByteDecode12(dk_pke[i]) (ml_kem.c:996-998), no reduction
+#pragma unroll
+            for (int p = 0; p < 4; p++) basemul_acc(acc[2 * p], acc[2 * p + 1], sh[2 * p], sh[2 * p + 1], x[2 * p], x[2 * p + 1], gam[p]);
+        }
+        uint32_t x[8];
+#pragma unroll
+        for (int r = 0; r < 8; r++) x[r] = canon32(acc[r]);
+        intt_warp(x, scratch, lane, twi);
+        // w = v - x (ml_kem.c:1001-1003), m' bit = Compress_1(w) (:1009-1012); coefficient lane+32r is bit lane of word r
+        uint32_t myword = 0;
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+            uint32_t v = decompress<P::DV>(unpack1<P::DV>(ct + P::C1ROW * K, idxA(lane, r)));
+            uint32_t w = csubq(v + kQ - x[r]);
+            uint32_t word = __ballot_sync(kFullMask, compress_canon<1>(w) & 1u);
+            if (lane == r) myword = word;
+        }
+        if (lane < 8) reinterpret_cast<uint32_t *>(mout + 32 * (size_t)item)[lane] = myword;
         __syncwarp();
-        ntt_warp(x, scratch, lane, tw);  // layout C out: 8 consecutive coefficients = 4 base-case pairs
-        unpack8<12>(sk + 384 * i, lane, sh);  // s^[i] = ByteDecode12(dk_pke[i]) (ml_kem.c:996-998), no reduction
-#pragma unroll
-        for (int p = 0; p < 4; p++) basemul_acc(acc[2 * p], acc[2 * p + 1], sh[2 * p], sh[2 * p + 1], x[2 * p], x[2 * p + 1], gam[p]);
     }
-    uint32_t x[8];
-#pragma unroll
-    for (int r = 0; r < 8; r++) x[r] = canon32(acc[r]);
-    intt_warp(x, scratch, lane, twi);
-    // w = v - x (ml_kem.c:1001-1003), m' bit = Compress_1(w) (:1009-1012); coefficient lane+32r is bit lane of word r
-    uint32_t myword = 0;
-#pragma unroll
-    for (int r = 0; r < 8; r++) {
-        uint32_t v = decompress<P::DV>(unpack1<P::DV>(ct + P::C1ROW * K, idxA(lane, r)));
-        uint32_t w = csubq(v + kQ - x[r]);
-        uint32_t word = __ballot_sync(kFullMask, compress_canon<1>(w) & 1u);
-        if (lane == r) myword = word;
-    }
-    if (lane < 8) reinterpret_cast<uint32_t *>(mout + 32 * (size_t)item)[lane] = myword;
-    __syncwarp();
-  }
+    cp_async_wait<0>();
 }
 
 // KeyGen: dk_pke rows = ByteEncode12(s^[i]) (ml_kem.c:750-756), plus the rho / ek-tail copies.
