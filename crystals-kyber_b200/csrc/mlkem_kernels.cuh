@@ -903,11 +903,21 @@ __global__ void __launch_bounds__(kPrimTPB) k_ntt_batch(int n, const uint16_t *_
     uint16_t *scratch = s_scratch + warp * kScratchU16;
     LaneTwiddles tw;
     load_lane_twiddles(tw, lane);
-    for (long long p = (long long)blockIdx.x * (kPrimTPB / 32) + warp; p < n; p += (long long)gridDim.x * (kPrimTPB / 32)) {
-        const uint16_t *src = in + 256 * p;
+    const long long stride = (long long)gridDim.x * (kPrimTPB / 32);
+    long long p = (long long)blockIdx.x * (kPrimTPB / 32) + warp;
+    uint32_t nxt[8];  // the next polynomial of this warp is in flight while the current one is transformed
+    if (p < n) {
+#pragma unroll
+        for (int r = 0; r < 8; r++) nxt[r] = __ldg(in + 256 * p + idxA(lane, r));
+    }
+    for (; p < n; p += stride) {
         uint32_t x[8];
 #pragma unroll
-        for (int r = 0; r < 8; r++) x[r] = __ldg(src + idxA(lane, r)) & 0xFFFu;
+        for (int r = 0; r < 8; r++) x[r] = nxt[r] & 0xFFFu;
+        if (p + stride < n) {
+#pragma unroll
+            for (int r = 0; r < 8; r++) nxt[r] = __ldg(in + 256 * (p + stride) + idxA(lane, r));
+        }
         ntt_warp(x, scratch, lane, tw);
         store_layoutC_global(x, lane, out + 256 * p);
     }
@@ -919,9 +929,14 @@ __global__ void __launch_bounds__(kPrimTPB) k_intt_batch(int n, const uint16_t *
     uint16_t *scratch = s_scratch + warp * kScratchU16;
     LaneTwiddles tw;
     load_lane_twiddles_inv(tw, lane);
-    for (long long p = (long long)blockIdx.x * (kPrimTPB / 32) + warp; p < n; p += (long long)gridDim.x * (kPrimTPB / 32)) {
+    const long long stride = (long long)gridDim.x * (kPrimTPB / 32);
+    long long p = (long long)blockIdx.x * (kPrimTPB / 32) + warp;
+    uint4 nxt = make_uint4(0, 0, 0, 0);
+    if (p < n) nxt = __ldg(reinterpret_cast<const uint4 *>(in + 256 * p) + lane);
+    for (; p < n; p += stride) {
         uint32_t x[8];
-        load_layoutC_global(x, lane, in + 256 * p);
+        unpack_pairs(nxt, x);
+        if (p + stride < n) nxt = __ldg(reinterpret_cast<const uint4 *>(in + 256 * (p + stride)) + lane);
 #pragma unroll
         for (int r = 0; r < 8; r++) x[r] &= 0xFFFu;
         intt_warp(x, scratch, lane, tw);
@@ -1057,8 +1072,13 @@ __global__ void __launch_bounds__(kPrimTPB) k_encode_batch(int n, const uint16_t
     __shared__ __align__(16) uint8_t s_stage[(kPrimTPB / 32) * 32 * D];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint8_t *stage = s_stage + warp * 32 * D;
-    for (long long p = (long long)blockIdx.x * (kPrimTPB / 32) + warp; p < n; p += (long long)gridDim.x * (kPrimTPB / 32)) {
-        uint4 q4 = __ldg(reinterpret_cast<const uint4 *>(in + 256 * p) + lane);  // coefficients 8 lane .. 8 lane + 7
+    const long long stride = (long long)gridDim.x * (kPrimTPB / 32);
+    long long p = (long long)blockIdx.x * (kPrimTPB / 32) + warp;
+    uint4 nxt = make_uint4(0, 0, 0, 0);
+    if (p < n) nxt = __ldg(reinterpret_cast<const uint4 *>(in + 256 * p) + lane);  // coefficients 8 lane .. 8 lane + 7
+    for (; p < n; p += stride) {
+        uint4 q4 = nxt;
+        if (p + stride < n) nxt = __ldg(reinterpret_cast<const uint4 *>(in + 256 * (p + stride)) + lane);  // next polynomial in flight
         uint32_t w[4] = {q4.x, q4.y, q4.z, q4.w}, v[8];
 #pragma unroll
         for (int i = 0; i < 8; i++) {
