@@ -99,15 +99,19 @@ unsigned pow17(unsigned e) {
     return z;
 }
 uint2 shoup_pair(unsigned w) { return make_uint2(w, (w << 16) / kQ); }
+uint2 shoup_pair32(unsigned w) { return make_uint2(w, (unsigned)(((unsigned long long)w << 32) / kQ)); }
 
 void build_tables(TwiddleTables &t, uint2 rc[24]) {
     for (unsigned i = 0; i < 128; i++) {
         t.zeta[i] = shoup_pair(pow17(bitrev7(i)));           // ml_kem.c:300-307
         t.gamma[i] = shoup_pair(pow17(2 * bitrev7(i) + 1));  // ml_kem.c:424-433
-        t.gamma32[i] = make_uint2(t.gamma[i].x, (unsigned)(((unsigned long long)t.gamma[i].x << 32) / kQ));
+        t.gamma32[i] = shoup_pair32(t.gamma[i].x);
+        t.zeta32[i] = shoup_pair32(t.zeta[i].x);
     }
     t.zeta_inv_last[0] = shoup_pair((t.zeta[1].x * 3303u) % kQ);  // ml_kem.c:378-381 folded into the last layer
     t.zeta_inv_last[1] = shoup_pair(3303u);
+    t.zeta_inv_last32[0] = shoup_pair32(t.zeta_inv_last[0].x);
+    t.zeta_inv_last32[1] = shoup_pair32(3303u);
     // Keccak round constants from the LFSR of FIPS 202 Alg. 5 (what sha3.c:148-205 recomputes every round)
     uint8_t lfsr = 1;
     for (int round = 0; round < 24; round++) {
@@ -165,6 +169,9 @@ int allow_smem_matvec() {
     if (int rc = allow_smem(k_sample_matvec<P, kModeKeyGen>, b)) return rc;
     if (int rc = allow_smem(k_sample_matvec<P, kModeEncrypt>, b)) return rc;
     if (int rc = allow_smem(k_sample_matvec<P, kModeEncryptCompare>, b)) return rc;
+    if (int rc = allow_smem(k_sample_matvec_list<P, kModeKeyGen>, b)) return rc;
+    if (int rc = allow_smem(k_sample_matvec_list<P, kModeEncrypt>, b)) return rc;
+    if (int rc = allow_smem(k_sample_matvec_list<P, kModeEncryptCompare>, b)) return rc;
     return 0;
 }
 
@@ -186,6 +193,9 @@ int acquire(const mlkem_b200_opts *o, int *dev, DeviceCtx **ctx) {
         CU(cudaMemcpyToSymbol(c_tw, &t, sizeof t));
         CU(cudaMemcpyToSymbol(g_tw, &t, sizeof t));
         CU(cudaMemcpyToSymbol(c_keccak_rc, rc, sizeof rc));
+        uint32_t pow2[32];
+        for (int k = 0; k < 32; k++) pow2[k] = 1u << k;
+        CU(cudaMemcpyToSymbol(c_pow2, pow2, sizeof pow2));
         for (int s = 0; s < kSlots; s++) CU(cudaStreamCreateWithFlags(&c.stream[s], cudaStreamNonBlocking));
         CU(cudaEventCreateWithFlags(&c.ev_fork, cudaEventDisableTiming));
         for (int s = 0; s < kSlots; s++) CU(cudaEventCreateWithFlags(&c.ev_join[s], cudaEventDisableTiming));
@@ -217,8 +227,8 @@ struct Arena {
 template <class P>
 constexpr size_t ws_bytes_per_item() {
     // keygen: rs 64 + 2K polys ; encrypt: K polys + (K+1) code rows ; decaps adds m' 32 + K'r' 64 + flag 4
-    size_t kg = 64 + 2 * P::K * 512;
-    size_t enc = P::K * 512 + (P::K + 1) * 128 + 32;
+    size_t kg = 64 + 2 * P::K * 512 + 4 * P::K;
+    size_t enc = P::K * 512 + (P::K + 1) * 128 + 32 + 4 * P::K;
     size_t dec = enc + 32 + 64 + 4;
     size_t m = kg > dec ? kg : dec;
     return m + 64;
@@ -228,6 +238,28 @@ constexpr size_t kWsSlack = 16 * 256;
 // ------------------------------------------------------------------------------------------------
 // Pipelines on device pointers.  Every function only enqueues work on `st`.
 // ------------------------------------------------------------------------------------------------
+
+// The fused matrix kernel and its clean-up pass.  With the reference's group limit (278 >= 168 = three blocks) the
+// straight-line kernel runs first and appends the rows it could not complete to a list that the general kernel
+// then works off; a lowered limit (test hook) sends every row through the general kernel.
+template <class P, int MODE>
+int launch_matvec(cudaStream_t st, Arena &ws, MatvecArgs a) {
+    constexpr int K = P::K;
+    const size_t rows = (size_t)a.n * K, smem = matvec_smem_bytes<P>();
+    const unsigned blocks = cdiv(rows, 32), list_grid = std::min<unsigned>(blocks, 148 * 4);
+    if (a.group_limit >= 168) {
+        a.defer_list = ws.take<int>(rows);
+        a.defer_count = ws.take<int>(1);
+        CU(cudaMemsetAsync(a.defer_count, 0, sizeof(int), st));
+        LAUNCH((k_sample_matvec<P, MODE>), blocks, 32 * K, smem, st, a);
+        LAUNCH((k_sample_matvec_list<P, MODE>), list_grid, 32 * K, smem, st, a);
+    } else {
+        a.defer_list = nullptr;
+        a.defer_count = nullptr;
+        LAUNCH((k_sample_matvec_list<P, MODE>), list_grid, 32 * K, smem, st, a);
+    }
+    return 0;
+}
 
 // K-PKE.Encrypt (ml_kem.c:776) for n items; `seed` = 32-byte PRF key r per item.
 // Stores c, or (cmp != nullptr) ORs the mismatch of the re-encryption against cmp into flags.
@@ -264,8 +296,6 @@ int enqueue_encrypt(cudaStream_t st, Arena &ws, int n, const uint8_t *ek, size_t
     a.out_stride = P::C;
     a.cmp = cmp;
     a.flags = flags;
-    const unsigned grid = cdiv((size_t)n * K, 32);
-    const size_t smem = matvec_smem_bytes<P>();
     EncVArgs v{};
     v.n = n;
     v.ek = ek;
@@ -280,10 +310,10 @@ int enqueue_encrypt(cudaStream_t st, Arena &ws, int n, const uint8_t *ek, size_t
     v.cmp = cmp;
     v.flags = flags;
     if (cmp) {
-        LAUNCH((k_sample_matvec<P, kModeEncryptCompare>), grid, 32 * K, smem, st, a);
+        if (int rc = launch_matvec<P, kModeEncryptCompare>(st, ws, a)) return rc;
         LAUNCH((k_encrypt_v<P, true>), warp_grid(n, kWarpTPB / 32), kWarpTPB, 0, st, v);
     } else {
-        LAUNCH((k_sample_matvec<P, kModeEncrypt>), grid, 32 * K, smem, st, a);
+        if (int rc = launch_matvec<P, kModeEncrypt>(st, ws, a)) return rc;
         LAUNCH((k_encrypt_v<P, false>), warp_grid(n, kWarpTPB / 32), kWarpTPB, 0, st, v);
     }
     return 0;
@@ -318,7 +348,7 @@ int enqueue_keygen(cudaStream_t st, Arena &ws, int n, const uint8_t *d, const ui
     a.out_stride = P::EK;
     a.out2 = full ? dk + 384 * K : nullptr;
     a.out2_stride = dk_stride;
-    LAUNCH((k_sample_matvec<P, kModeKeyGen>), cdiv((size_t)n * K, 32), 32 * K, matvec_smem_bytes<P>(), st, a);
+    if (int rc = launch_matvec<P, kModeKeyGen>(st, ws, a)) return rc;
     LAUNCH((k_keygen_encode_s<P>), cdiv((size_t)n * K, kWarpTPB / 32), kWarpTPB, 0, st, n, se, (size_t)2 * K * 256, rs, ek, dk, dk_stride, full);
     if (full) LAUNCH((k_keygen_H<P>), cdiv(n, kHashTPB), kHashTPB, 0, st, n, ek, z, dk);
     return 0;

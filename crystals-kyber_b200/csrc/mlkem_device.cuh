@@ -35,6 +35,8 @@ struct TwiddleTables {
     uint2 zeta_inv_last[2];  // {zeta[1] * 3303 mod q, 3303}
     uint2 gamma[128];        // {w, floor(w 2^16 / q)}
     uint2 gamma32[128];      // {w, floor(w 2^32 / q)} for mul_shoup_fma
+    uint2 zeta32[128];       // zeta as {w, floor(w 2^32 / q)}: the transforms that run next to Keccak (kFmaPipe variants)
+    uint2 zeta_inv_last32[2];
 };
 // The library is a single translation unit (mlkem_b200.cu), so the tables are defined right here.
 // c_tw (constant bank) serves the warp-uniform lookups; g_tw (global memory, read through L1 with __ldg) serves
@@ -43,7 +45,12 @@ struct TwiddleTables {
 __constant__ TwiddleTables c_tw;
 __device__ TwiddleTables g_tw;
 __constant__ uint2 c_keccak_rc[24];
+// c_pow2[k] = 2^k.  A left shift written as x * c_pow2[k] is an IMAD with a constant-bank operand: ptxas cannot see the
+// value, so it cannot turn the multiply back into a shift on the alu pipe (which it does for literal powers of two).
+__constant__ uint32_t c_pow2[32];
+__device__ __forceinline__ uint32_t shl_fma(uint32_t x, int k) { return x * c_pow2[k]; }
 __device__ __forceinline__ uint2 lane_zeta(int i) { return __ldg(&g_tw.zeta[i]); }
+__device__ __forceinline__ uint2 lane_zeta32(int i) { return __ldg(&g_tw.zeta32[i]); }
 __device__ __forceinline__ uint2 lane_gamma(int i) { return __ldg(&g_tw.gamma32[i]); }
 
 // ------------------------------------------------------------------------------------------------
@@ -61,6 +68,18 @@ __device__ __forceinline__ uint32_t mul_shoup_fma(uint32_t a, uint32_t w, uint32
     uint32_t qh = __umulhi(a, w32);
     return a * w - qh * kQ;
 }
+// Pipe policy of the transforms.  The hashing kernels saturate the alu pipe (LOP3 / SHF) and leave the fma pipe idle,
+// so every transform that shares an SM with Keccak (k_sample_matvec, k_noise) is instantiated with FMA = true: quotient
+// estimates by multiply-high (IMAD.HI, fma pipe, half rate) instead of multiply + shift (IMAD + SHF), exact
+// canonicalisation by multiply-high instead of Barrett + min.  The stand-alone transforms keep the balanced form.
+constexpr bool kFmaPipe = true, kBalanced = false;
+template <bool FMA>
+__device__ __forceinline__ uint32_t mulz(uint32_t a, uint2 z) {  // z from the zeta32 (FMA) or zeta (balanced) table; result < 2q
+    return FMA ? mul_shoup_fma(a, z.x, z.y) : mul_shoup(a, z);
+}
+// x mod q, exact, for x < 2^21 (1290168 = ceil(2^32 / q): the quotient is exact while x * 1976 < 2^32 * ... see
+// tests/test_abi_cpu.py::test_arithmetic_lemmas): two fma-pipe instructions, none on the alu pipe.
+__device__ __forceinline__ uint32_t canon_fma(uint32_t x) { return x - __umulhi(x, 1290168u) * kQ; }
 // x mod q for x < 2^16, result in [0, q].
 __device__ __forceinline__ uint32_t barrett16(uint32_t x) {
     uint32_t qh = (x * 40317u) >> 27;  // floor(2^27 / q) = 40317
@@ -97,6 +116,15 @@ __device__ __forceinline__ uint32_t compress_canon(uint32_t x) {
     static_assert(D == 1 || D == 4 || D == 5 || D == 10 || D == 11, "no verified constants for this d");
     constexpr uint32_t c = (D >= 10) ? 1664u : 1665u, M = (D >= 10) ? 1290168u : 1290167u;
     return __umulhi(x * (1u << D) + c, M) & ((1u << D) - 1u);
+}
+
+// Compress_d of a RESIDUE x < 4q (any representative of the coefficient) for d <= 5: for these d the single
+// multiply-high stays exact far beyond q (exhaustive check in tests/test_abi_cpu.py::test_arithmetic_lemmas), and a
+// multiple of q added to x only adds a multiple of 2^d to the quotient.  Not valid for d = 10, 11.
+template <int D>
+__device__ __forceinline__ uint32_t compress_resid(uint32_t x) {
+    static_assert(D == 1 || D == 4 || D == 5, "single multiply-high is not exact on residues for this d");
+    return __umulhi(x * (1u << D) + 1664u, 1290168u) & ((1u << D) - 1u);
 }
 
 // ml_kem.c:104 Decompress_d: (q y + 2^(d-1)) >> d.
@@ -254,26 +282,32 @@ struct LaneTwiddles {
     uint2 z2[2];  // len 2 : block = 2 lane + (r >> 2)         (layout C)
 };
 // Forward: block `blk` of the layer with n blocks uses zeta[n + blk] (ml_kem.c:296-308, i counts up from 1).
+template <bool FMA = false>
+__device__ __forceinline__ uint2 lane_z(int i) { return FMA ? lane_zeta32(i) : lane_zeta(i); }
+template <bool FMA = false>
+__device__ __forceinline__ uint2 uniform_z(int i) { return FMA ? c_tw.zeta32[i] : c_tw.zeta[i]; }
+template <bool FMA = false>
 __device__ __forceinline__ void load_lane_twiddles(LaneTwiddles &t, int lane) {
     int g = lane >> 2;
-    t.z16 = lane_zeta(8 + g);
+    t.z16 = lane_z<FMA>(8 + g);
 #pragma unroll
-    for (int i = 0; i < 2; i++) t.z8[i] = lane_zeta(16 + 2 * g + i);
+    for (int i = 0; i < 2; i++) t.z8[i] = lane_z<FMA>(16 + 2 * g + i);
 #pragma unroll
-    for (int i = 0; i < 4; i++) t.z4[i] = lane_zeta(32 + 4 * g + i);
+    for (int i = 0; i < 4; i++) t.z4[i] = lane_z<FMA>(32 + 4 * g + i);
 #pragma unroll
-    for (int i = 0; i < 2; i++) t.z2[i] = lane_zeta(64 + 2 * lane + i);
+    for (int i = 0; i < 2; i++) t.z2[i] = lane_z<FMA>(64 + 2 * lane + i);
 }
 // Inverse: block `blk` of the layer with n blocks uses zeta[2n - 1 - blk] (ml_kem.c:345-357, i counts down from 127).
+template <bool FMA = false>
 __device__ __forceinline__ void load_lane_twiddles_inv(LaneTwiddles &t, int lane) {
     int g = lane >> 2;
-    t.z16 = lane_zeta(15 - g);
+    t.z16 = lane_z<FMA>(15 - g);
 #pragma unroll
-    for (int i = 0; i < 2; i++) t.z8[i] = lane_zeta(31 - (2 * g + i));
+    for (int i = 0; i < 2; i++) t.z8[i] = lane_z<FMA>(31 - (2 * g + i));
 #pragma unroll
-    for (int i = 0; i < 4; i++) t.z4[i] = lane_zeta(63 - (4 * g + i));
+    for (int i = 0; i < 4; i++) t.z4[i] = lane_z<FMA>(63 - (4 * g + i));
 #pragma unroll
-    for (int i = 0; i < 2; i++) t.z2[i] = lane_zeta(127 - (2 * lane + i));
+    for (int i = 0; i < 2; i++) t.z2[i] = lane_z<FMA>(127 - (2 * lane + i));
 }
 
 // Transposes between layouts through the swizzled scratch.  Values must be < 2^16.
@@ -295,7 +329,7 @@ __device__ __forceinline__ void load_scratch_B(uint32_t x[8], const uint16_t *s,
 }
 // Layout C is one 16-byte vector per lane (8 consecutive coefficients).
 __device__ __forceinline__ uint4 pack_pairs(const uint32_t x[8]) {
-    return make_uint4(x[0] | (x[1] << 16), x[2] | (x[3] << 16), x[4] | (x[5] << 16), x[6] | (x[7] << 16));
+    return make_uint4(x[0] + x[1] * 65536u, x[2] + x[3] * 65536u, x[4] + x[5] * 65536u, x[6] + x[7] * 65536u);  // IMAD, fma pipe
 }
 __device__ __forceinline__ void unpack_pairs(uint4 v, uint32_t x[8]) {
     x[0] = v.x & 0xFFFFu; x[1] = v.x >> 16; x[2] = v.y & 0xFFFFu; x[3] = v.y >> 16;
@@ -309,37 +343,39 @@ __device__ __forceinline__ void load_scratch_C(uint32_t x[8], const uint16_t *s,
 }
 
 // Cooley-Tukey butterfly, lazy: inputs < 2^16 - 2q, outputs grow by at most 2q.
+template <bool FMA = false>
 __device__ __forceinline__ void ct_bfly(uint32_t &a, uint32_t &b, uint2 z) {
-    uint32_t t = mul_shoup(b, z);
+    uint32_t t = mulz<FMA>(b, z);
     b = a - t + 2 * kQ;
     a = a + t;
 }
 
 // ml_kem.c:287 NTT.  x in layout A with values < 4096 (values >= q are treated as residues).  Returns the
-// transform in layout C, canonical.  `scratch` = this warp's 512-byte scratch; tw from load_lane_twiddles.
+// transform in layout C, canonical.  `scratch` = this warp's 512-byte scratch; tw from load_lane_twiddles<FMA>.
+template <bool FMA = false>
 __device__ __forceinline__ void ntt_warp(uint32_t x[8], uint16_t *scratch, int lane, const LaneTwiddles &tw) {
     // pass A -- len = 128, 64, 32: register index bits 2, 1, 0
 #pragma unroll
-    for (int r = 0; r < 4; r++) ct_bfly(x[r], x[r + 4], c_tw.zeta[1]);
+    for (int r = 0; r < 4; r++) ct_bfly<FMA>(x[r], x[r + 4], uniform_z<FMA>(1));
 #pragma unroll
     for (int h = 0; h < 2; h++)
 #pragma unroll
-        for (int r = 0; r < 2; r++) ct_bfly(x[4 * h + r], x[4 * h + r + 2], c_tw.zeta[2 + h]);
+        for (int r = 0; r < 2; r++) ct_bfly<FMA>(x[4 * h + r], x[4 * h + r + 2], uniform_z<FMA>(2 + h));
 #pragma unroll
-    for (int h = 0; h < 4; h++) ct_bfly(x[2 * h], x[2 * h + 1], c_tw.zeta[4 + h]);
+    for (int h = 0; h < 4; h++) ct_bfly<FMA>(x[2 * h], x[2 * h + 1], uniform_z<FMA>(4 + h));
     store_scratch_A(x, scratch, lane);  // values < 4096 + 6q < 2^16
     __syncwarp();
     load_scratch_B(x, scratch, lane);
     __syncwarp();
     // pass B -- len = 16, 8, 4
 #pragma unroll
-    for (int r = 0; r < 4; r++) ct_bfly(x[r], x[r + 4], tw.z16);
+    for (int r = 0; r < 4; r++) ct_bfly<FMA>(x[r], x[r + 4], tw.z16);
 #pragma unroll
     for (int h = 0; h < 2; h++)
 #pragma unroll
-        for (int r = 0; r < 2; r++) ct_bfly(x[4 * h + r], x[4 * h + r + 2], tw.z8[h]);
+        for (int r = 0; r < 2; r++) ct_bfly<FMA>(x[4 * h + r], x[4 * h + r + 2], tw.z8[h]);
 #pragma unroll
-    for (int h = 0; h < 4; h++) ct_bfly(x[2 * h], x[2 * h + 1], tw.z4[h]);
+    for (int h = 0; h < 4; h++) ct_bfly<FMA>(x[2 * h], x[2 * h + 1], tw.z4[h]);
     store_scratch_B(x, scratch, lane);  // values < 4096 + 12q < 2^16
     __syncwarp();
     load_scratch_C(x, scratch, lane);
@@ -348,45 +384,51 @@ __device__ __forceinline__ void ntt_warp(uint32_t x[8], uint16_t *scratch, int l
 #pragma unroll
     for (int h = 0; h < 2; h++)
 #pragma unroll
-        for (int r = 0; r < 2; r++) ct_bfly(x[4 * h + r], x[4 * h + r + 2], tw.z2[h]);
+        for (int r = 0; r < 2; r++) ct_bfly<FMA>(x[4 * h + r], x[4 * h + r + 2], tw.z2[h]);
 #pragma unroll
-    for (int r = 0; r < 8; r++) x[r] = canon16(x[r]);  // < 4096 + 14q < 2^16
+    for (int r = 0; r < 8; r++) x[r] = FMA ? canon_fma(x[r]) : canon16(x[r]);  // < 4096 + 14q < 2^16
 }
 
 // Gentleman-Sande butterfly for the inverse transform (ml_kem.c:359-373): a' = a + b, b' = zeta (b - a).
 // `bias` is a multiple of q not smaller than the bound of a.
+template <bool FMA = false>
 __device__ __forceinline__ void gs_bfly(uint32_t &a, uint32_t &b, uint2 z, uint32_t bias) {
     uint32_t t = a;
     a = t + b;
-    b = mul_shoup(b - t + bias, z);
+    b = mulz<FMA>(b - t + bias, z);
 }
 
 // ml_kem.c:336 InverseNTT including the final multiplication by 3303 (:378-381).
-// x in layout C, values < 4096.  Returns layout A, canonical.  tw from load_lane_twiddles_inv.
+// x in layout C; returns layout A.  tw from load_lane_twiddles_inv<FMA>.
+//   balanced form: inputs < 4096, output canonical.
+//   FMA form:      inputs < 8192 (so the lazily reduced sums of the base-case products, < 2q, can be fed directly);
+//                  output canonical when CANON, else in [0, 2q) for a consumer that reduces anyway.
+template <bool FMA = false, bool CANON = true>
 __device__ __forceinline__ void intt_warp(uint32_t x[8], uint16_t *scratch, int lane, const LaneTwiddles &tw) {
-    // pass C -- len = 2.  inputs < 4096 <= 2q: sums < 8192, products < 2q
+    // pass C -- len = 2.  inputs < 4096 <= 2q (FMA: < 8192 <= 3q): sums < 8192 (16384), products < 2q
 #pragma unroll
     for (int h = 0; h < 2; h++)
 #pragma unroll
-        for (int r = 0; r < 2; r++) gs_bfly(x[4 * h + r], x[4 * h + r + 2], tw.z2[h], 2 * kQ);
+        for (int r = 0; r < 2; r++) gs_bfly<FMA>(x[4 * h + r], x[4 * h + r + 2], tw.z2[h], (FMA ? 3 : 2) * kQ);
     store_scratch_C(x, scratch, lane);
     __syncwarp();
     load_scratch_B(x, scratch, lane);
     __syncwarp();
-    // pass B -- len = 4: inputs < 8192, sums < 16384; the bias must be a multiple of q >= 8191: 3q
+    // pass B -- len = 4: inputs < 8192 (16384), sums < 16384 (16384 + 2q < 2^16); the bias must be a multiple of q
+    // >= 8191 (16383): 3q (5q)
 #pragma unroll
     for (int h = 0; h < 4; h++) {
-        gs_bfly(x[2 * h], x[2 * h + 1], tw.z4[h], 3 * kQ);
-        x[2 * h] = barrett16(x[2 * h]);  // <= q, keeps the later sums below 2^16
+        gs_bfly<FMA>(x[2 * h], x[2 * h + 1], tw.z4[h], (FMA ? 5 : 3) * kQ);
+        x[2 * h] = FMA ? barrett32(x[2 * h]) : barrett16(x[2 * h]);  // <= q (FMA: < 2q), keeps the later sums below 2^16
     }
     // len = 8: inputs < 2q: sums < 4q, bias 2q
 #pragma unroll
     for (int h = 0; h < 2; h++)
 #pragma unroll
-        for (int r = 0; r < 2; r++) gs_bfly(x[4 * h + r], x[4 * h + r + 2], tw.z8[h], 2 * kQ);
+        for (int r = 0; r < 2; r++) gs_bfly<FMA>(x[4 * h + r], x[4 * h + r + 2], tw.z8[h], 2 * kQ);
     // len = 16: inputs < 4q: sums < 8q, bias 4q
 #pragma unroll
-    for (int r = 0; r < 4; r++) gs_bfly(x[r], x[r + 4], tw.z16, 4 * kQ);
+    for (int r = 0; r < 4; r++) gs_bfly<FMA>(x[r], x[r + 4], tw.z16, 4 * kQ);
     store_scratch_B(x, scratch, lane);  // < 8q = 26632
     __syncwarp();
     load_scratch_A(x, scratch, lane);
@@ -394,20 +436,25 @@ __device__ __forceinline__ void intt_warp(uint32_t x[8], uint16_t *scratch, int 
     // pass A -- len = 32: inputs < 8q: sums < 16q = 53264 < 2^16, bias 8q; reduce the sums
 #pragma unroll
     for (int h = 0; h < 4; h++) {
-        gs_bfly(x[2 * h], x[2 * h + 1], c_tw.zeta[7 - h], 8 * kQ);
-        x[2 * h] = barrett16(x[2 * h]);
+        gs_bfly<FMA>(x[2 * h], x[2 * h + 1], uniform_z<FMA>(7 - h), 8 * kQ);
+        x[2 * h] = FMA ? barrett32(x[2 * h]) : barrett16(x[2 * h]);
     }
     // len = 64: inputs < 2q: sums < 4q, bias 2q
 #pragma unroll
     for (int h = 0; h < 2; h++)
 #pragma unroll
-        for (int r = 0; r < 2; r++) gs_bfly(x[4 * h + r], x[4 * h + r + 2], c_tw.zeta[3 - h], 2 * kQ);
+        for (int r = 0; r < 2; r++) gs_bfly<FMA>(x[4 * h + r], x[4 * h + r + 2], uniform_z<FMA>(3 - h), 2 * kQ);
     // len = 128 with the 128^-1 scaling folded in: a' = 3303 (a + b), b' = 3303 zeta (b - a); inputs < 4q
+    const uint2 zs = FMA ? c_tw.zeta_inv_last32[1] : c_tw.zeta_inv_last[1], zl = FMA ? c_tw.zeta_inv_last32[0] : c_tw.zeta_inv_last[0];
 #pragma unroll
     for (int r = 0; r < 4; r++) {
         uint32_t t = x[r];
-        x[r] = csubq(mul_shoup(t + x[r + 4], c_tw.zeta_inv_last[1]));
-        x[r + 4] = csubq(mul_shoup(x[r + 4] - t + 4 * kQ, c_tw.zeta_inv_last[0]));
+        x[r] = mulz<FMA>(t + x[r + 4], zs);
+        x[r + 4] = mulz<FMA>(x[r + 4] - t + 4 * kQ, zl);
+        if (CANON) {
+            x[r] = csubq(x[r]);
+            x[r + 4] = csubq(x[r + 4]);
+        }
     }
 }
 
@@ -487,6 +534,17 @@ __device__ __forceinline__ uint32_t unpack1(const uint8_t *src, int c) {
     if (D > 9 && sh + D > 16) w |= (uint32_t)src[byte + 2] << 16;
     return (w >> sh) & ((1u << D) - 1u);
 }
+
+// x >> S as a multiply-high (IMAD.HI, fma pipe) -- inline PTX so that the compiler does not turn it back into a shift.
+template <int S>
+__device__ __forceinline__ uint32_t shr_fma(uint32_t x) {
+    uint32_t d;
+    asm("mul.hi.u32 %0, %1, %2;" : "=r"(d) : "r"(x), "n"(1u << (32 - S)));
+    return d;
+}
+// Nibble j of w, given pw = 1 << (28 - 4 j): IMAD + IMAD.HI, nothing on the alu pipe.
+__device__ __forceinline__ uint32_t nibble_fma(uint32_t w, uint32_t pw) { return shr_fma<28>(w * pw); }
+__device__ __forceinline__ uint32_t nibble_weight(int j) { return 1u << (28 - 4 * j); }
 
 // Noise polynomials travel between kernels as 4-bit codes (coefficient + 3), 8 per 32-bit word.
 __device__ __forceinline__ uint32_t noise_code_to_coeff(uint32_t code) {  // code in 0..6 -> canonical

@@ -363,18 +363,16 @@ __global__ void __launch_bounds__(kNoiseTPB) k_noise(int n, const uint8_t *__res
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
         uint16_t *scratch = s_scratch + warp * kScratchU16;
         LaneTwiddles tw;
-        load_lane_twiddles(tw, lane);
+        load_lane_twiddles<kFmaPipe>(tw, lane);  // this kernel's alu pipe belongs to Keccak
+        const uint32_t pw = nibble_weight(lane & 7);
         for (int t = 0; t < 32; t++) {
             int it = blockIdx.x * kNoiseTPB + warp * 32 + t;
             if (it >= n) break;
-            const uint32_t *codes = s_codes + 33 * (warp * 32 + t);
+            const uint32_t *codes = s_codes + 33 * (warp * 32 + t) + (lane >> 3);
             uint32_t x[8];
 #pragma unroll
-            for (int r = 0; r < 8; r++) {
-                int c = idxA(lane, r);
-                x[r] = noise_code_to_coeff((codes[c >> 3] >> (4 * (c & 7))) & 15u);
-            }
-            ntt_warp(x, scratch, lane, tw);
+            for (int r = 0; r < 8; r++) x[r] = nibble_fma(codes[4 * r], pw) + (kQ - 3);  // coefficient lane + 32 r as a residue <= q + 3
+            ntt_warp<kFmaPipe>(x, scratch, lane, tw);
             store_layoutC_global(x, lane, out16 + out16_stride * it + 256 * p);
         }
     } else {
@@ -480,6 +478,83 @@ __device__ __forceinline__ void sample_ntt_thread(const Lane rho[4], uint32_t &b
 }
 
 // =================================================================================================
+// SampleNTT, fast path: exactly three squeezed blocks per sponge, parsing on the fma pipe
+// =================================================================================================
+// 99.1 % of all sponges are complete after three blocks (336 candidates, 256 needed, acceptance 0.813).  A warp
+// that waits for its slowest lane pays a fourth permutation in one case out of four, and its block mates wait at
+// the barrier meanwhile.  The fused kernel therefore runs EXACTLY three blocks per sponge, marks the rows that own
+// an incomplete sponge and leaves them to a dense clean-up pass (k_sample_matvec_list) that re-runs them through
+// the general sampler.  Straight-line code, no votes in the first two blocks, every warp does identical work.
+//
+// The candidate loop is kept off the alu pipe, which belongs to Keccak (LOP3 / SHF): the 12-bit field is brought
+// to the top of a register by multiplies (a straddling field by multiply-high + multiply-add), d = field >> 20 is
+// a multiply-high, the rejection bit is floor(d * ceil(2^32 / q) / 2^32) (exactly d >= q for d < 4096), every
+// candidate is stored unconditionally at the running position and the position advances by 2 - 2 * rejected
+// (one multiply-add).  A rejected value is overwritten by the next candidate.  Blocks 1 and 2 cannot overflow the
+// slot (2 * 112 < 256); in block 3 a 16-candidate chunk runs unchecked while every lane of the warp still has room
+// for 16 coefficients and otherwise clamps the position to the end of the slot (one add-min per candidate), where
+// the slot's spare 129th word absorbs the stores of lanes that are already complete.
+__device__ __forceinline__ uint32_t mulhi_rt(uint32_t x, uint32_t m) {  // IMAD.HI with a multiplier that is constant after unrolling
+    uint32_t d;
+    asm("mul.hi.u32 %0, %1, %2;" : "=r"(d) : "r"(x), "r"(m));
+    return d;
+}
+__device__ __forceinline__ uint32_t madlo_rt(uint32_t a, uint32_t b, uint32_t c) {  // IMAD
+    uint32_t d;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+template <bool CHECKED>
+__device__ __forceinline__ void parse_chunk_fma(const uint32_t w[7], uint32_t &addr, uint32_t end_addr) {
+#pragma unroll
+    for (int m = 0; m < 16; m++) {  // candidate m = bits [12 m, 12 m + 12): d1 / d2 of group m / 2 (ml_kem.c:208-209)
+        const int bit = 12 * m, wi = bit >> 5, sh = bit & 31;
+        uint32_t t;  // the field in bits [20, 32), don't-care bits below
+        if (sh == 20) t = w[wi];
+        else if (sh < 20) t = shl_fma(w[wi], 20 - sh);
+        else t = madlo_rt(w[wi + 1], c_pow2[52 - sh], mulhi_rt(w[wi], 1u << (52 - sh)));  // (w[wi] >> (sh - 20)) + (w[wi+1] << (52 - sh))
+        const uint32_t d = mulhi_rt(t, 4096u);           // t >> 20
+        const uint32_t rej = __umulhi(d, 1290168u);      // d >= q  (:211, :216), exact for d < 4096
+        if (CHECKED) {
+            asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"((uint16_t)d) : "memory");
+            addr = min(madlo_rt(rej, 0xFFFFFFFEu, addr) + 2u, end_addr);  // j < N  (:203, :216)
+        } else {
+            asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr + 2 * m), "h"((uint16_t)d) : "memory");
+            addr = madlo_rt(rej, 0xFFFFFFFEu, addr);  // biased position: the true one is addr + 2 (m + 1)
+        }
+    }
+    if (!CHECKED) addr += 32;
+}
+template <int MODE_CHECK>  // 0: never checked (blocks 1, 2), 1: decide per chunk (block 3)
+__device__ __forceinline__ void parse_block_fma(const Lane a[25], uint32_t &addr, uint32_t end_addr) {
+#pragma unroll
+    for (int ch = 0; ch < 7; ch++) {  // 3 lanes = 6 words = 16 candidates
+        const uint32_t w[7] = {a[3 * ch].lo, a[3 * ch].hi, a[3 * ch + 1].lo, a[3 * ch + 1].hi, a[3 * ch + 2].lo, a[3 * ch + 2].hi, 0u};
+        if (MODE_CHECK == 0 || __all_sync(kFullMask, addr + 32 <= end_addr)) parse_chunk_fma<false>(w, addr, end_addr);
+        else parse_chunk_fma<true>(w, addr, end_addr);
+    }
+}
+// Returns true when the slot holds the complete polynomial.  No group limit applies: three blocks are 168 of the 278
+// groups a run may consume (ml_kem.c:221-227), so the fast path is only used with group_limit >= 168.
+__device__ __forceinline__ bool sample_ntt_three_blocks(const Lane rho[4], uint32_t b32, uint32_t b33, uint16_t *slot) {
+    Lane a[25];
+    const uint32_t base = (uint32_t)__cvta_generic_to_shared(slot), end_addr = base + 2 * kN;
+    uint32_t addr = base;
+    keccak_zero(a);
+#pragma unroll
+    for (int w = 0; w < 4; w++) a[w] = rho[w];
+    a[4].lo = (b32 & 0xFFu) | ((b33 & 0xFFu) << 8) | (kSfxXof << 16);  // XOF.Init + Absorb(rho || b32 || b33), ml_kem.c:200-201
+    a[kRateShake128 - 1].hi ^= 0x80000000u;
+#pragma unroll 1
+    for (int blk = 0; blk < 3; blk++) {
+        keccak_f1600(a);  // one 168-byte block = 56 three-byte groups = 112 candidates
+        if (blk < 2) parse_block_fma<0>(a, addr, end_addr);
+        else parse_block_fma<1>(a, addr, end_addr);
+    }
+    return addr >= end_addr;
+}
+
+// =================================================================================================
 // Fused matrix expansion + matrix-vector product (the heavy kernel of KeyGen and Encrypt)
 // =================================================================================================
 enum MatvecMode { kModeKeyGen = 0, kModeEncrypt = 1, kModeEncryptCompare = 2 };
@@ -501,56 +576,49 @@ struct MatvecArgs {
     size_t out2_stride;
     const uint8_t *cmp;      // EncryptCompare: the received ciphertext, addressed like out
     uint32_t *flags;         // EncryptCompare: flags[i] |= 1 when a re-encrypted row differs
+    int *defer_list;         // rows (item * K + row) left to the clean-up pass; nullptr for the list kernel = all rows
+    int *defer_count;        // number of entries in defer_list (zeroed by the host before the fused kernel)
 };
 
-// Dynamic shared memory of k_sample_matvec: 32 K sampling slots, then per warp a 512-byte transform scratch
-// and a 384-byte staging row for the packed output.
+// Dynamic shared memory of the matvec kernels: 32 K sampling slots, then per warp a 512-byte transform scratch and a
+// 384-byte staging row for the packed output, then the row index of each of the 32 groups (-1 = nothing to do) and
+// one "incomplete" byte per sponge.
 constexpr int kMatvecWarpBytes = 512 + 384;
 template <class P>
+__host__ __device__ constexpr size_t matvec_slots_bytes() {
+    return ((size_t)32 * P::K * kSlotWords * 4 + 15) & ~(size_t)15;
+}
+template <class P>
 constexpr size_t matvec_smem_bytes() {
-    return (size_t)32 * P::K * kSlotWords * 4 + 16 + (size_t)P::K * kMatvecWarpBytes;
+    return matvec_slots_bytes<P>() + (size_t)P::K * kMatvecWarpBytes + 32 * 4 + 32 * P::K;
 }
 
-// Block = 32 K threads = 32 (item,row) groups x K matrix columns.  Phase 1: each thread samples one matrix
-// entry into its slot.  Phase 2: each warp takes groups round-robin and finishes the row.
+// Phase 2 of the matvec kernels: the warps of the block take the 32 groups round-robin and finish the rows whose
+// K sampled entries sit in the slots grp*K .. grp*K+K-1.  s_gg[grp] = item * K + row, or -1 to skip the group.
+// (Tried and measured slower, 31.7 vs 32.4 M pairs/s: giving every warp the groups sampled by its own lanes, with
+// named barriers for the two groups that straddle a warp boundary at K = 3, so that no block-wide barrier separates
+// the phases.  The barrier wait it removes -- 9 % of the warp samples -- is not on the critical path: the alu pipe is.)
 template <class P, int MODE>
-__global__ void __launch_bounds__(32 * P::K) k_sample_matvec(MatvecArgs g) {
+__device__ __forceinline__ void matvec_finish_rows(const MatvecArgs &g, uint32_t *s_slots, const int *s_gg, int lane, int warp) {
     constexpr int K = P::K;
-    extern __shared__ __align__(16) uint32_t s_slots[];  // 32 K slots of kSlotWords words, then the per-warp areas
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    {
-        const int grp = tid / K, col = tid - grp * K;
-        const long long gg = (long long)blockIdx.x * 32 + grp;
-        const int item = (int)(gg / K), row = (int)(gg - (long long)item * K);
-        const bool active = item < g.n;
-        Lane rho[4];
-#pragma unroll
-        for (int w = 0; w < 4; w++) rho[w] = active ? load_lane(g.rho + g.rho_stride * item + 8 * w) : Lane{0u, 0u};
-        // KeyGen: A[row][col] = SampleNTT(rho || col || row)      (ml_kem.c:686-693)
-        // Encrypt: At[row][col] = SampleNTT(rho || row || col)    (ml_kem.c:817-823, stored transposed)
-        uint32_t b32 = MODE == kModeKeyGen ? col : row, b33 = MODE == kModeKeyGen ? row : col;
-        sample_ntt_thread(rho, b32, b33, reinterpret_cast<uint16_t *>(s_slots + kSlotWords * tid), active, g.group_limit);
-    }
-    __syncthreads();
-
-    uint8_t *warp_area = reinterpret_cast<uint8_t *>(s_slots) + (((size_t)32 * K * kSlotWords * 4 + 15) & ~(size_t)15) + warp * kMatvecWarpBytes;
+    uint8_t *warp_area = reinterpret_cast<uint8_t *>(s_slots) + matvec_slots_bytes<P>() + warp * kMatvecWarpBytes;
     uint16_t *scratch = reinterpret_cast<uint16_t *>(warp_area);
     uint8_t *stage = warp_area + 512;
     uint2 gam[4];
 #pragma unroll
     for (int r = 0; r < 4; r++) gam[r] = lane_gamma(lane + 32 * r);
     LaneTwiddles tw;
-    if (MODE != kModeKeyGen) load_lane_twiddles_inv(tw, lane);
+    if (MODE != kModeKeyGen) load_lane_twiddles_inv<kFmaPipe>(tw, lane);
+    const uint32_t pw = nibble_weight(lane & 7);
 
     // The vector operand of a group is fetched one group ahead (software pipelining in registers): its global-load
     // latency was the largest exposed stall of phase 2 in the ncu source view.
     // (16-bit loads instead of 32-bit loads + mask/shift: the load/store pipe has slack, the alu pipe does not.)
     uint32_t vnext[8 * K];
     auto fetch_vec = [&](int grp, uint32_t *dst) {
-        const long long gg = (long long)blockIdx.x * 32 + grp;
-        const int item = (int)(gg / K);
-        if (grp < 32 && item < g.n) {
-            const uint16_t *vec = g.vec + g.vec_stride * item;
+        const int gg = grp < 32 ? s_gg[grp] : -1;
+        if (gg >= 0) {
+            const uint16_t *vec = g.vec + g.vec_stride * (gg / K);
 #pragma unroll
             for (int j = 0; j < K; j++)
 #pragma unroll
@@ -564,14 +632,14 @@ __global__ void __launch_bounds__(32 * P::K) k_sample_matvec(MatvecArgs g) {
     fetch_vec(warp, vnext);
 
     for (int grp = warp; grp < 32; grp += K) {
-        const long long gg = (long long)blockIdx.x * 32 + grp;
-        const int item = (int)(gg / K), row = (int)(gg - (long long)item * K);
-        if (item >= g.n) break;  // groups are ordered by item
-        const uint32_t *slot0 = s_slots + kSlotWords * (grp * K);
+        const int gg = s_gg[grp];
         uint32_t vcur[8 * K];
 #pragma unroll
         for (int i = 0; i < 8 * K; i++) vcur[i] = vnext[i];
         fetch_vec(grp + K, vnext);
+        if (gg < 0) continue;  // beyond the batch, or left to the clean-up pass
+        const int item = gg / K, row = gg - item * K;
+        const uint32_t *slot0 = s_slots + kSlotWords * (grp * K);
         // compare mode: the received ciphertext row is needed only at the very end of the iteration -- load it now
         constexpr int kCmpWords = (8 * P::DU + 31) / 32;
         uint32_t cmpw[kCmpWords];
@@ -579,6 +647,12 @@ __global__ void __launch_bounds__(32 * P::K) k_sample_matvec(MatvecArgs g) {
             const uint32_t *cw = reinterpret_cast<const uint32_t *>(g.cmp + g.out_stride * item + (size_t)P::C1ROW * row);
 #pragma unroll
             for (int i = 0; i < kCmpWords; i++) cmpw[i] = (lane + 32 * i < 8 * P::DU) ? __ldg(cw + lane + 32 * i) : 0u;
+        }
+        uint32_t cw8[8];  // likewise the noise codes of the row (Encrypt) 
+        if (MODE != kModeKeyGen) {
+            const uint32_t *codes = g.addc + g.addc_stride * item + 32 * row + (lane >> 3);
+#pragma unroll
+            for (int r = 0; r < 8; r++) cw8[r] = __ldg(codes + 4 * r);
         }
         // ---- row . vector in the NTT domain (ml_kem.c:618 VectorMultiply), lazily accumulated.
         // Lane handles coefficient pairs t = lane + 32 r (conflict-free slot reads, coalesced vector reads).
@@ -616,18 +690,17 @@ __global__ void __launch_bounds__(32 * P::K) k_sample_matvec(MatvecArgs g) {
 #pragma unroll
             for (int r = 0; r < 4; r++) {
                 int t = lane + 32 * r;
-                sw[sidx(2 * t) >> 1] = canon32(acc[2 * r]) | (canon32(acc[2 * r + 1]) << 16);
+                sw[sidx(2 * t) >> 1] = barrett32(acc[2 * r]) + barrett32(acc[2 * r + 1]) * 65536u;  // < 2q each
             }
             __syncwarp();
             uint32_t x[8];
             load_scratch_C(x, scratch, lane);
             __syncwarp();
-            intt_warp(x, scratch, lane, tw);
-            const uint32_t *codes = g.addc + g.addc_stride * item + 32 * row;
+            intt_warp<kFmaPipe, false>(x, scratch, lane, tw);  // [0, 2q)
 #pragma unroll
-            for (int r = 0; r < 8; r++) {
-                uint32_t code = (__ldg(codes + (lane >> 3) + 4 * r) >> (4 * (lane & 7))) & 15u;
-                x[r] = compress_canon<P::DU>(add_noise_code(x[r], code));
+            for (int r = 0; r < 8; r++) {  // (x + e1) mod q, exact, then Compress_du: everything but the final mask on the fma pipe
+                uint32_t y = x[r] + nibble_fma(cw8[r], pw) + (kQ - 3);  // < 3q + 4
+                x[r] = compress_canon<P::DU>(canon_fma(y));
             }
             store_scratch_A(x, scratch, lane);
             __syncwarp();
@@ -654,6 +727,79 @@ __global__ void __launch_bounds__(32 * P::K) k_sample_matvec(MatvecArgs g) {
             }
         }
         __syncwarp();
+    }
+}
+
+template <class P>
+__device__ __forceinline__ int *matvec_gg(uint32_t *s_slots) {
+    return reinterpret_cast<int *>(reinterpret_cast<uint8_t *>(s_slots) + matvec_slots_bytes<P>() + P::K * kMatvecWarpBytes);
+}
+
+// The fused kernel.  Block = 32 K threads = 32 (item,row) groups x K matrix columns.  Phase 1: each thread samples one
+// matrix entry into its slot with the three-block sampler.  Phase 2: the warps finish the complete rows; rows with an
+// incomplete entry (2.7 % at K = 3) are appended to g.defer_list for k_sample_matvec_list.
+template <class P, int MODE>
+__global__ void __launch_bounds__(32 * P::K) k_sample_matvec(MatvecArgs g) {
+    constexpr int K = P::K;
+    extern __shared__ __align__(16) uint32_t s_slots[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int *s_gg = matvec_gg<P>(s_slots);
+    uint8_t *s_inc = reinterpret_cast<uint8_t *>(s_gg + 32);
+    {
+        const int grp = tid / K, col = tid - grp * K;
+        const int gg = blockIdx.x * 32 + grp;
+        const int item = gg / K, row = gg - item * K;
+        const bool active = item < g.n;
+        Lane rho[4];
+#pragma unroll
+        for (int w = 0; w < 4; w++) rho[w] = active ? load_lane(g.rho + g.rho_stride * item + 8 * w) : Lane{0u, 0u};
+        // KeyGen: A[row][col] = SampleNTT(rho || col || row)      (ml_kem.c:686-693)
+        // Encrypt: At[row][col] = SampleNTT(rho || row || col)    (ml_kem.c:817-823, stored transposed)
+        const uint32_t b32 = MODE == kModeKeyGen ? col : row, b33 = MODE == kModeKeyGen ? row : col;
+        // threads beyond the batch sample a dummy sponge into their own slot (the straight-line sampler has no idle mode)
+        const bool complete = sample_ntt_three_blocks(rho, b32, b33, reinterpret_cast<uint16_t *>(s_slots + kSlotWords * tid));
+        s_inc[tid] = active && !complete;
+    }
+    __syncthreads();
+    if (tid < 32) {
+        const int gg = blockIdx.x * 32 + tid;
+        bool deferred = false;
+#pragma unroll
+        for (int j = 0; j < K; j++) deferred |= s_inc[tid * K + j] != 0;
+        const bool active = gg / K < g.n;
+        s_gg[tid] = (active && !deferred) ? gg : -1;
+        if (active && deferred) g.defer_list[atomicAdd(g.defer_count, 1)] = gg;
+    }
+    __syncthreads();
+    matvec_finish_rows<P, MODE>(g, s_slots, s_gg, lane, warp);
+}
+
+// The general kernel: rows taken from g.defer_list (or all rows of the batch when it is nullptr), sampled with the
+// general sampler (any number of blocks, give-up rule and restart of ml_kem.c:221-242).  Persistent blocks.
+template <class P, int MODE>
+__global__ void __launch_bounds__(32 * P::K) k_sample_matvec_list(MatvecArgs g) {
+    constexpr int K = P::K;
+    extern __shared__ __align__(16) uint32_t s_slots[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int *s_gg = matvec_gg<P>(s_slots);
+    const int count = g.defer_list ? *g.defer_count : g.n * K;
+    for (int base = blockIdx.x * 32; base < count; base += gridDim.x * 32) {
+        {
+            const int grp = tid / K, col = tid - grp * K;
+            const int e = base + grp;
+            const int gg = e < count ? (g.defer_list ? g.defer_list[e] : e) : -1;
+            const bool active = gg >= 0;
+            const int item = active ? gg / K : 0, row = gg - item * K;
+            if (col == 0) s_gg[grp] = gg;
+            Lane rho[4];
+#pragma unroll
+            for (int w = 0; w < 4; w++) rho[w] = active ? load_lane(g.rho + g.rho_stride * item + 8 * w) : Lane{0u, 0u};
+            uint32_t b32 = MODE == kModeKeyGen ? col : row, b33 = MODE == kModeKeyGen ? row : col;
+            sample_ntt_thread(rho, b32, b33, reinterpret_cast<uint16_t *>(s_slots + kSlotWords * tid), active, g.group_limit);
+        }
+        __syncthreads();
+        matvec_finish_rows<P, MODE>(g, s_slots, s_gg, lane, warp);
+        __syncthreads();  // the slots are reused by the next batch of rows
     }
 }
 
@@ -718,7 +864,8 @@ __global__ void __launch_bounds__(kWarpTPB, 8) k_encrypt_v(EncVArgs g) {
 #pragma unroll
     for (int i = 0; i < 4; i++) gam[i] = lane_gamma(4 * lane + i);
     LaneTwiddles tw;
-    load_lane_twiddles_inv(tw, lane);
+    load_lane_twiddles_inv<kFmaPipe>(tw, lane);
+    const uint32_t pw = nibble_weight(lane & 7);
     auto fetch = [&](int item, uint8_t *buf) {
         stage_row_async(buf, g.ek + g.ek_stride * item, kRowsBytes, lane);
         stage_row_async(buf + kRowsBytes, reinterpret_cast<const uint8_t *>(g.yhat + g.yhat_stride * item), kVecBytes, lane);
@@ -756,13 +903,13 @@ __global__ void __launch_bounds__(kWarpTPB, 8) k_encrypt_v(EncVArgs g) {
         }
         uint32_t x[8];
 #pragma unroll
-        for (int r = 0; r < 8; r++) x[r] = canon32(acc[r]);
-        intt_warp(x, scratch, lane, tw);  // layout C in, layout A out
+        for (int r = 0; r < 8; r++) x[r] = barrett32(acc[r]);  // < 2q
+        intt_warp<kFmaPipe, false>(x, scratch, lane, tw);  // layout C in, layout A out, [0, 2q)
 #pragma unroll
         for (int r = 0; r < 8; r++) {
-            uint32_t code = (cw8[r] >> (4 * (lane & 7))) & 15u;
             uint32_t mu = ((mw8[r] >> lane) & 1u) * 1665u;  // Decompress_1(bit) = 1665 bit (ml_kem.c:867-870)
-            x[r] = compress_canon<P::DV>(csubq(add_noise_code(x[r], code) + mu));
+            // v = x + e2 + mu as a residue < 4q: Compress_dv is exact on residues for d <= 5 (compress_resid)
+            x[r] = compress_resid<P::DV>(x[r] + nibble_fma(cw8[r], pw) + (kQ - 3) + mu);
         }
         store_scratch_A(x, scratch, lane);
         __syncwarp();
