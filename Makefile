@@ -15,6 +15,12 @@ lib: $(LIB)
 $(LIB): $(CSRC)/mlkem_b200.cu $(CSRC)/mlkem_kernels.cuh $(CSRC)/mlkem_device.cuh $(CSRC)/ml_kem_compat.inl $(CSRC)/mlkem_profile.inl $(CSRC)/sha3_compat.inl include/mlkem_b200.h include/ml_kem.h include/sha3.h
 	$(NVCC) $(NVFLAGS) -shared -o $@ $(CSRC)/mlkem_b200.cu
 
+# experiment build of the library (timing experiments that break the results on purpose: tools/time_encaps.py)
+exp: build/libmlkem_b200_exp.so
+build/libmlkem_b200_exp.so: $(CSRC)/mlkem_b200.cu $(CSRC)/mlkem_kernels.cuh $(CSRC)/mlkem_device.cuh
+	mkdir -p build
+	$(NVCC) $(NVFLAGS) -DMLKEM_B200_EXPERIMENT -shared -o $@ $(CSRC)/mlkem_b200.cu
+
 tools: build/microbench build/keccak_bench
 
 build/microbench: $(CSRC)/microbench.cu
@@ -33,4 +39,4 @@ clean:
 	rm -f $(LIB) build/microbench build/keccak_bench
 	$(MAKE) -C oracle clean
 
-.PHONY: all lib tools oracle clean
+.PHONY: all lib exp tools oracle clean

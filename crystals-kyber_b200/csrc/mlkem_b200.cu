@@ -247,6 +247,10 @@ int launch_matvec(cudaStream_t st, Arena &ws, MatvecArgs a) {
     constexpr int K = P::K;
     const size_t rows = (size_t)a.n * K, smem = matvec_smem_bytes<P>();
     const unsigned blocks = cdiv(rows, 32), list_grid = std::min<unsigned>(blocks, 148 * 4);
+#ifdef MLKEM_B200_EXPERIMENT
+    static const int env_exp = env_int("MLKEM_B200_EXPERIMENT", 0);
+    a.experiment = env_exp;
+#endif
     if (a.group_limit >= 168) {
         a.defer_list = ws.take<int>(rows);
         a.defer_count = ws.take<int>(1);

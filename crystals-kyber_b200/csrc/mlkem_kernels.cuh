@@ -536,7 +536,7 @@ __device__ __forceinline__ void parse_block_fma(const Lane a[25], uint32_t &addr
 }
 // Returns true when the slot holds the complete polynomial.  No group limit applies: three blocks are 168 of the 278
 // groups a run may consume (ml_kem.c:221-227), so the fast path is only used with group_limit >= 168.
-__device__ __forceinline__ bool sample_ntt_three_blocks(const Lane rho[4], uint32_t b32, uint32_t b33, uint16_t *slot) {
+__device__ __forceinline__ bool sample_ntt_three_blocks(const Lane rho[4], uint32_t b32, uint32_t b33, uint16_t *slot, int experiment = 0) {
     Lane a[25];
     const uint32_t base = (uint32_t)__cvta_generic_to_shared(slot), end_addr = base + 2 * kN;
     uint32_t addr = base;
@@ -548,6 +548,12 @@ __device__ __forceinline__ bool sample_ntt_three_blocks(const Lane rho[4], uint3
 #pragma unroll 1
     for (int blk = 0; blk < 3; blk++) {
         keccak_f1600(a);  // one 168-byte block = 56 three-byte groups = 112 candidates
+#ifdef MLKEM_B200_EXPERIMENT
+        if (experiment & 2) {
+            addr += a[0].lo & 2;
+            continue;
+        }
+#endif
         if (blk < 2) parse_block_fma<0>(a, addr, end_addr);
         else parse_block_fma<1>(a, addr, end_addr);
     }
@@ -578,6 +584,9 @@ struct MatvecArgs {
     uint32_t *flags;         // EncryptCompare: flags[i] |= 1 when a re-encrypted row differs
     int *defer_list;         // rows (item * K + row) left to the clean-up pass; nullptr for the list kernel = all rows
     int *defer_count;        // number of entries in defer_list (zeroed by the host before the fused kernel)
+#ifdef MLKEM_B200_EXPERIMENT
+    int experiment;          // build/libmlkem_b200_exp.so only (make exp): 1 = skip phase 2, 2 = skip parsing, 4 = phase 2 twice
+#endif
 };
 
 // Dynamic shared memory of the matvec kernels: 32 K sampling slots, then per warp a 512-byte transform scratch and a
@@ -611,11 +620,12 @@ __device__ __forceinline__ void matvec_finish_rows(const MatvecArgs &g, uint32_t
     if (MODE != kModeKeyGen) load_lane_twiddles_inv<kFmaPipe>(tw, lane);
     const uint32_t pw = nibble_weight(lane & 7);
 
-    // The vector operand of a group is fetched one group ahead (software pipelining in registers): its global-load
-    // latency was the largest exposed stall of phase 2 in the ncu source view.
+    // The vector operand of the NEXT group is fetched into the same registers as soon as the products of the current
+    // group have consumed them: the loads have the whole inverse transform and epilogue to land (their latency was the
+    // largest exposed stall of phase 2 in the first ncu source view), and no register copies are needed.
     // (16-bit loads instead of 32-bit loads + mask/shift: the load/store pipe has slack, the alu pipe does not.)
-    uint32_t vnext[8 * K];
-    auto fetch_vec = [&](int grp, uint32_t *dst) {
+    uint32_t v[8 * K];
+    auto fetch_vec = [&](int grp) {
         const int gg = grp < 32 ? s_gg[grp] : -1;
         if (gg >= 0) {
             const uint16_t *vec = g.vec + g.vec_stride * (gg / K);
@@ -624,22 +634,21 @@ __device__ __forceinline__ void matvec_finish_rows(const MatvecArgs &g, uint32_t
 #pragma unroll
                 for (int r = 0; r < 4; r++) {
                     int t = lane + 32 * r;
-                    dst[8 * j + 2 * r] = __ldg(vec + 256 * j + 2 * t);
-                    dst[8 * j + 2 * r + 1] = __ldg(vec + 256 * j + 2 * t + 1);
+                    v[8 * j + 2 * r] = __ldg(vec + 256 * j + 2 * t);
+                    v[8 * j + 2 * r + 1] = __ldg(vec + 256 * j + 2 * t + 1);
                 }
         }
     };
-    fetch_vec(warp, vnext);
+    fetch_vec(warp);
 
     for (int grp = warp; grp < 32; grp += K) {
         const int gg = s_gg[grp];
-        uint32_t vcur[8 * K];
-#pragma unroll
-        for (int i = 0; i < 8 * K; i++) vcur[i] = vnext[i];
-        fetch_vec(grp + K, vnext);
-        if (gg < 0) continue;  // beyond the batch, or left to the clean-up pass
+        if (gg < 0) {  // beyond the batch, or left to the clean-up pass
+            fetch_vec(grp + K);
+            continue;
+        }
         const int item = gg / K, row = gg - item * K;
-        const uint32_t *slot0 = s_slots + kSlotWords * (grp * K);
+        const uint32_t slot0 = (uint32_t)__cvta_generic_to_shared(s_slots + kSlotWords * (grp * K));
         // compare mode: the received ciphertext row is needed only at the very end of the iteration -- load it now
         constexpr int kCmpWords = (8 * P::DU + 31) / 32;
         uint32_t cmpw[kCmpWords];
@@ -648,7 +657,7 @@ __device__ __forceinline__ void matvec_finish_rows(const MatvecArgs &g, uint32_t
 #pragma unroll
             for (int i = 0; i < kCmpWords; i++) cmpw[i] = (lane + 32 * i < 8 * P::DU) ? __ldg(cw + lane + 32 * i) : 0u;
         }
-        uint32_t cw8[8];  // likewise the noise codes of the row (Encrypt) 
+        uint32_t cw8[8];  // likewise the noise codes of the row (Encrypt)
         if (MODE != kModeKeyGen) {
             const uint32_t *codes = g.addc + g.addc_stride * item + 32 * row + (lane >> 3);
 #pragma unroll
@@ -661,14 +670,18 @@ __device__ __forceinline__ void matvec_finish_rows(const MatvecArgs &g, uint32_t
         for (int r = 0; r < 8; r++) acc[r] = 0;
 #pragma unroll
         for (int j = 0; j < K; j++) {
-            const uint16_t *aw = reinterpret_cast<const uint16_t *>(slot0 + kSlotWords * j);
 #pragma unroll
             for (int r = 0; r < 4; r++) {
-                int t = lane + 32 * r;
-                uint32_t a0 = aw[2 * t], a1 = aw[2 * t + 1];
-                basemul_acc(acc[2 * r], acc[2 * r + 1], a0, a1, vcur[8 * j + 2 * r], vcur[8 * j + 2 * r + 1], gam[r]);
+                // two 16-bit shared loads (inline PTX: the compiler would merge them into one 32-bit load plus a mask
+                // and a shift on the alu pipe)
+                uint16_t a0, a1;
+                const uint32_t ad = slot0 + 4 * (kSlotWords * j + lane + 32 * r);
+                asm volatile("ld.shared.u16 %0, [%1];" : "=h"(a0) : "r"(ad));
+                asm volatile("ld.shared.u16 %0, [%1+2];" : "=h"(a1) : "r"(ad));
+                basemul_acc(acc[2 * r], acc[2 * r + 1], a0, a1, v[8 * j + 2 * r], v[8 * j + 2 * r + 1], gam[r]);
             }
         }
+        fetch_vec(grp + K);
         int nwords;
         if (MODE == kModeKeyGen) {
             // t^[row] = A[row] . s^ + e^[row]   (ml_kem.c:723-727), then ByteEncode12 (:736-742)
@@ -757,7 +770,11 @@ __global__ void __launch_bounds__(32 * P::K) k_sample_matvec(MatvecArgs g) {
         // Encrypt: At[row][col] = SampleNTT(rho || row || col)    (ml_kem.c:817-823, stored transposed)
         const uint32_t b32 = MODE == kModeKeyGen ? col : row, b33 = MODE == kModeKeyGen ? row : col;
         // threads beyond the batch sample a dummy sponge into their own slot (the straight-line sampler has no idle mode)
+#ifdef MLKEM_B200_EXPERIMENT
+        const bool complete = sample_ntt_three_blocks(rho, b32, b33, reinterpret_cast<uint16_t *>(s_slots + kSlotWords * tid), g.experiment);
+#else
         const bool complete = sample_ntt_three_blocks(rho, b32, b33, reinterpret_cast<uint16_t *>(s_slots + kSlotWords * tid));
+#endif
         s_inc[tid] = active && !complete;
     }
     __syncthreads();
@@ -771,6 +788,10 @@ __global__ void __launch_bounds__(32 * P::K) k_sample_matvec(MatvecArgs g) {
         if (active && deferred) g.defer_list[atomicAdd(g.defer_count, 1)] = gg;
     }
     __syncthreads();
+#ifdef MLKEM_B200_EXPERIMENT
+    if (g.experiment & 1) return;
+    if (g.experiment & 4) matvec_finish_rows<P, MODE>(g, s_slots, s_gg, lane, warp);
+#endif
     matvec_finish_rows<P, MODE>(g, s_slots, s_gg, lane, warp);
 }
 
