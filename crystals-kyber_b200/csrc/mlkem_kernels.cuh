@@ -828,6 +828,13 @@ __global__ void __launch_bounds__(32 * P::K) k_sample_matvec_list(MatvecArgs g) 
 // Remaining K-PKE pieces, one item per warp
 // =================================================================================================
 constexpr int kWarpTPB = 128;  // 4 items per block
+// Transform variant of k_decrypt and of the stand-alone NTT / InverseNTT kernels.  No Keccak runs next to them, so the
+// balanced form (quotient by multiply + shift) wins: measured 3.28 vs 2.97 G NTT/s and 1.81 vs 1.95 ms per 2^20
+// decryptions against the multiply-high form (IMAD.HI issues at half the IMAD rate; tools/time_prims.py).
+#ifndef MLKEM_B200_PRIM_PIPE
+#define MLKEM_B200_PRIM_PIPE false
+#endif
+constexpr bool kPrimPipe = MLKEM_B200_PRIM_PIPE;
 
 struct EncVArgs {
     int n;
@@ -970,8 +977,8 @@ __global__ void __launch_bounds__(kWarpTPB) k_decrypt(int n, const uint8_t *__re
 #pragma unroll
     for (int i = 0; i < 4; i++) gam[i] = lane_gamma(4 * lane + i);
     LaneTwiddles tw, twi;
-    load_lane_twiddles(tw, lane);
-    load_lane_twiddles_inv(twi, lane);
+    load_lane_twiddles<kPrimPipe>(tw, lane);
+    load_lane_twiddles_inv<kPrimPipe>(twi, lane);
     auto fetch = [&](int item, uint8_t *buf) {
         stage_row_async(buf, c + (size_t)P::C * item, P::C, lane);
         stage_row_async(buf + P::C, dk + dk_stride * item, kSkBytes, lane);
@@ -999,15 +1006,15 @@ __global__ void __launch_bounds__(kWarpTPB) k_decrypt(int n, const uint8_t *__re
             __syncwarp();
             load_scratch_A(x, scratch, lane);
             __syncwarp();
-            ntt_warp(x, scratch, lane, tw);  // layout C out: 8 consecutive coefficients = 4 base-case pairs
+            ntt_warp<kPrimPipe>(x, scratch, lane, tw);  // layout C out: 8 consecutive coefficients = 4 base-case pairs
             unpack8<12>(sk + 384 * i, lane, sh);  // s^[i] = ByteDecode12(dk_pke[i]) (ml_kem.c:996-998), no reduction
 #pragma unroll
             for (int p = 0; p < 4; p++) basemul_acc(acc[2 * p], acc[2 * p + 1], sh[2 * p], sh[2 * p + 1], x[2 * p], x[2 * p + 1], gam[p]);
         }
         uint32_t x[8];
 #pragma unroll
-        for (int r = 0; r < 8; r++) x[r] = canon32(acc[r]);
-        intt_warp(x, scratch, lane, twi);
+        for (int r = 0; r < 8; r++) x[r] = kPrimPipe ? barrett32(acc[r]) : canon32(acc[r]);
+        intt_warp<kPrimPipe>(x, scratch, lane, twi);
         // w = v - x (ml_kem.c:1001-1003), m' bit = Compress_1(w) (:1009-1012); coefficient lane+32r is bit lane of word r
         uint32_t myword = 0;
 #pragma unroll
@@ -1070,7 +1077,7 @@ __global__ void __launch_bounds__(kPrimTPB) k_ntt_batch(int n, const uint16_t *_
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint16_t *scratch = s_scratch + warp * kScratchU16;
     LaneTwiddles tw;
-    load_lane_twiddles(tw, lane);
+    load_lane_twiddles<kPrimPipe>(tw, lane);
     const long long stride = (long long)gridDim.x * (kPrimTPB / 32);
     long long p = (long long)blockIdx.x * (kPrimTPB / 32) + warp;
     uint32_t nxt[8];  // the next polynomial of this warp is in flight while the current one is transformed
@@ -1086,7 +1093,7 @@ __global__ void __launch_bounds__(kPrimTPB) k_ntt_batch(int n, const uint16_t *_
 #pragma unroll
             for (int r = 0; r < 8; r++) nxt[r] = __ldg(in + 256 * (p + stride) + idxA(lane, r));
         }
-        ntt_warp(x, scratch, lane, tw);
+        ntt_warp<kPrimPipe>(x, scratch, lane, tw);
         store_layoutC_global(x, lane, out + 256 * p);
     }
 }
@@ -1096,7 +1103,7 @@ __global__ void __launch_bounds__(kPrimTPB) k_intt_batch(int n, const uint16_t *
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint16_t *scratch = s_scratch + warp * kScratchU16;
     LaneTwiddles tw;
-    load_lane_twiddles_inv(tw, lane);
+    load_lane_twiddles_inv<kPrimPipe>(tw, lane);
     const long long stride = (long long)gridDim.x * (kPrimTPB / 32);
     long long p = (long long)blockIdx.x * (kPrimTPB / 32) + warp;
     uint4 nxt = make_uint4(0, 0, 0, 0);
@@ -1107,7 +1114,7 @@ __global__ void __launch_bounds__(kPrimTPB) k_intt_batch(int n, const uint16_t *
         if (p + stride < n) nxt = __ldg(reinterpret_cast<const uint4 *>(in + 256 * (p + stride)) + lane);
 #pragma unroll
         for (int r = 0; r < 8; r++) x[r] &= 0xFFFu;
-        intt_warp(x, scratch, lane, tw);
+        intt_warp<kPrimPipe>(x, scratch, lane, tw);
         uint16_t *dst = out + 256 * p;
 #pragma unroll
         for (int r = 0; r < 8; r++) dst[idxA(lane, r)] = (uint16_t)x[r];
