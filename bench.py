@@ -339,9 +339,10 @@ def main():
         "peak_source": "measured live: mlkem_b200_int32_peak (LOP3/SHF issue rate, alu pipe); MEASURED_PEAKS.json has no integer figure",
         "algorithmic_ops_per_item": ops["matvec_encrypt"], "items_per_launch": items_per_launch,
         "avg_launch_ms": mv_ms / max(mv_launches, 1), "share_of_step_kernel_time": mv_ms / total_kernel_ms if total_kernel_ms else None,
-        # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed ncu --set full capture
-        # (profiles/ncu_kem_kernels_r01_summary.csv: 373.5 MB for a 131 072-item launch = 2 849 B/item), scaled to this run's launch
-        "traffic": 2849.0 * items_per_launch, "traffic_bytes_per_item": 2849, "algorithmic_bytes_per_item": 32 + 1536 + 384 + 960,
+        # dram__bytes_read.sum + dram__bytes_write.sum from the committed ncu --set full capture
+        # (profiles/ncu_kem_kernels_r01_final_summary.csv, one 65 536-item launch: fused kernel 133.7 + 38.8 MB, clean-up pass
+        # 8.5 MB = 2 762 B/item), scaled to this run's launch
+        "traffic": 2762.0 * items_per_launch, "traffic_bytes_per_item": 2762, "algorithmic_bytes_per_item": 32 + 1536 + 384 + 960,
         "whole_step": {"algorithmic_ops_per_pair": ops["encaps"] + ops["decaps"],
                        "achieved": (ops["encaps"] + ops["decaps"]) * value / world / 1e12, "frac": (ops["encaps"] + ops["decaps"]) * value / world / peak},
         "peaks_tera_ops": {k: v / 1e12 for k, v in peaks.items()},
