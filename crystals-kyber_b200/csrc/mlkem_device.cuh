@@ -77,7 +77,7 @@ template <bool FMA>
 __device__ __forceinline__ uint32_t mulz(uint32_t a, uint2 z) {  // z from the zeta32 (FMA) or zeta (balanced) table; result < 2q
     return FMA ? mul_shoup_fma(a, z.x, z.y) : mul_shoup(a, z);
 }
-// x mod q, exact, for x < 2^21 (1290168 = ceil(2^32 / q): the quotient is exact while x * 1976 < 2^32 * ... see
+// x mod q, exact, for x < 2^21 (1290168 = ceil(2^32 / q); checked exhaustively in
 // tests/test_abi_cpu.py::test_arithmetic_lemmas): two fma-pipe instructions, none on the alu pipe.
 __device__ __forceinline__ uint32_t canon_fma(uint32_t x) { return x - __umulhi(x, 1290168u) * kQ; }
 // x mod q for x < 2^16, result in [0, q].

@@ -111,3 +111,41 @@ def test_product_does_not_import_oracle():
     mk = open(os.path.join(ROOT, "Makefile")).read()
     lib_rule = mk[mk.index("$(LIB):"):].split("\n\n")[0]
     assert "oracle" not in lib_rule
+
+
+def test_arithmetic_lemmas():
+    """Exhaustive checks of the integer identities the kernels rely on (csrc/mlkem_device.cuh, mlkem_kernels.cuh).
+    The reference's own formulas are ml_kem.c:83 (Compress) and the plain `% q` of its ring arithmetic."""
+    q = 3329
+    M = 1290168  # ceil(2^32 / q)
+    u = lambda a: np.asarray(a, dtype=np.uint64)
+    mulhi = lambda a, b: (u(a) * u(b)) >> np.uint64(32)
+    # canon_fma: x - floor(x M / 2^32) q == x mod q for x < 2^21
+    x = np.arange(1 << 21, dtype=np.uint64)
+    assert (x - mulhi(x, M) * u(q) == x % u(q)).all()
+    # the rejection bit of the three-block sampler: floor(d M / 2^32) == (d >= q) for every 12-bit d
+    d = np.arange(4096, dtype=np.uint64)
+    assert (mulhi(d, M) == (d >= q)).all()
+    # Shoup multiplication with the quotient by multiply-high: result congruent and < 2q for any 32-bit a
+    rng = np.random.default_rng(5)
+    a = np.concatenate([np.arange(1 << 17, dtype=np.uint64), rng.integers(0, 1 << 32, 1 << 18, dtype=np.uint64)])
+    for w in (1, 17, 1729, 3303, 3328):
+        w32 = (w << 32) // q
+        r = a * u(w) - mulhi(a, w32) * u(q)
+        assert (r < 2 * q).all() and (r % u(q) == a * u(w) % u(q)).all()
+    # Compress_d by one multiply-high: canonical inputs for the d of the parameter sets (compress_canon) ...
+    xc = np.arange(q, dtype=np.uint64)
+    for dd, c, m in ((1, 1665, 1290167), (4, 1665, 1290167), (5, 1665, 1290167), (10, 1664, 1290168), (11, 1664, 1290168)):
+        want = ((xc << np.uint64(dd)) + u(1664)) // u(q) % u(1 << dd)
+        assert (mulhi((xc << np.uint64(dd)) + u(c), m) % u(1 << dd) == want).all()
+    # ... and any residue below 4q for d <= 5 (compress_resid); the same form is NOT exact for d = 10, 11
+    xr = np.arange(4 * q, dtype=np.uint64)
+    for dd in (1, 4, 5, 10, 11):
+        want = (((xr % u(q)) << np.uint64(dd)) + u(1664)) // u(q) % u(1 << dd)
+        exact = (mulhi((xr << np.uint64(dd)) + u(1664), M) % u(1 << dd) == want).all()
+        assert exact == (dd <= 5)
+    # nibble j of a word by multiply (2^(28-4j)) and multiply-high (2^4)
+    w = rng.integers(0, 1 << 32, 4096, dtype=np.uint64)
+    for j in range(8):
+        top = (w << np.uint64(28 - 4 * j)) & u(0xFFFFFFFF)
+        assert (mulhi(top, 16) == (w >> np.uint64(4 * j)) & u(15)).all()
