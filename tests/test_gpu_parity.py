@@ -221,6 +221,38 @@ def test_kem_vs_oracle(mlkem, oracle, ps, n):
     assert (mlkem.pke_decrypt(ps, dk, cp, dk_stride=dk.shape[1]) == m).all()
 
 
+@pytest.mark.parametrize("ps", SETS)
+def test_kem_with_lowered_group_limit(oracle, ps):
+    """The fused matrix kernel samples exactly three XOF blocks (168 groups) and leaves incomplete rows to the clean-up
+    pass, which runs the general sampler with the give-up / restart rule of ml_kem.c:221-242.  Limits below 168 send
+    every row through the general kernel; 168 and 170 keep the fused kernel and make its deferred rows restart."""
+    import crystals_kyber_b200 as ck
+
+    n = 700
+    rng = np.random.default_rng(ps + 77)
+    d, z, m = (rng.integers(0, 256, (n, 32), dtype=np.uint8) for _ in range(3))
+    for limit in (158, 168, 170):  # 158: about half of the sponges restart (a much lower limit could cycle through all 256 seeds)
+        gpu = ck.MLKEM(sample_group_limit=limit)
+        oracle.set_sample_group_limit(limit)
+        try:
+            ek, dk = gpu.keygen(ps, d, z)
+            oek, odk = oracle.keygen(ps, d, z)
+            assert (ek == oek).all() and (dk == odk).all()
+            c, K = gpu.encaps(ps, ek, m)
+            oc, oK = oracle.encaps(ps, ek, m)
+            assert (c == oc).all() and (K == oK).all()
+            bad, sel = tamper(c)
+            Kd = gpu.decaps(ps, dk, bad)
+            assert (Kd == oracle.decaps(ps, dk, bad)).all()
+            ok = np.ones(n, bool)
+            ok[sel] = False
+            assert (Kd[ok] == K[ok]).all() and (Kd[~ok] != K[~ok]).any(axis=1).all()
+        finally:
+            oracle.set_sample_group_limit(0)
+    ek_ref, _ = oracle.keygen(ps, d, z)
+    assert (ek_ref != oek).any(), "the lowered limit must change some matrix entries for the test to mean anything"
+
+
 def test_kem_chunked_host_pipeline(oracle):
     """Host-memory path with several chunks alternating between the two pipeline slots."""
     import crystals_kyber_b200 as ck
