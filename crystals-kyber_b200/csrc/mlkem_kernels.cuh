@@ -515,6 +515,12 @@ __device__ __forceinline__ void parse_chunk_fma(const uint32_t w[7], uint32_t &a
         else t = madlo_rt(w[wi + 1], c_pow2[52 - sh], mulhi_rt(w[wi], 1u << (52 - sh)));  // (w[wi] >> (sh - 20)) + (w[wi+1] << (52 - sh))
         const uint32_t d = mulhi_rt(t, 4096u);           // t >> 20
         const uint32_t rej = __umulhi(d, 1290168u);      // d >= q  (:211, :216), exact for d < 4096
+#ifdef MLKEM_B200_EXPERIMENT  // own bounds check (compute-sanitizer is not available on the pool): slot .. slot + 512 (the spare word)
+        {
+            const uint32_t st = CHECKED ? addr : addr + 2 * m;
+            if (st + 512 < end_addr || st > end_addr || (!CHECKED && st >= end_addr)) __trap();
+        }
+#endif
         if (CHECKED) {
             asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"((uint16_t)d) : "memory");
             addr = min(madlo_rt(rej, 0xFFFFFFFEu, addr) + 2u, end_addr);  // j < N  (:203, :216)
