@@ -74,10 +74,28 @@ template<int UU,int NI,int TPB,int MINB> void run(const char* name, uint2* d, in
   int nb=0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kk<UU,NI,TPB,MINB>, TPB, 0);
   printf("{\"variant\":\"%s\",\"unroll\":%d,\"imad_rot_lanes\":%d,\"tpb\":%d,\"blocks_per_sm\":%d,\"ms\":%.3f,\"gperm_per_s\":%.3f,\"tera_alg_ops\":%.3f}\n",name,UU,NI,TPB,nb,best,perms/best/1e6,perms*4320/best/1e9);
 }
-int main(){
+// Occupancy forced by dynamic shared memory: `bps` blocks of 128 threads per SM = `bps` warps per scheduler.  Answers how many
+// Keccak warps a scheduler needs to keep its alu pipe full (the fused matrix kernel has 3 resident, ~2 of them in Keccak).
+template<int UU> void run_occ(const char* name, uint2* d, int sms, int bps){
+  const int TPB=128; int iters=200; int blocks=sms*bps*4;
+  size_t smem = (size_t)(220*1024/bps) & ~(size_t)1023; if(smem>200*1024) smem=200*1024;
+  CK(cudaFuncSetAttribute(kk<UU,0,TPB,1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaEvent_t e0,e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  kk<UU,0,TPB,1><<<blocks,TPB,smem>>>(d,2); CK(cudaDeviceSynchronize());
+  float best=1e30f;
+  for(int rep=0;rep<3;rep++){ CK(cudaEventRecord(e0)); kk<UU,0,TPB,1><<<blocks,TPB,smem>>>(d,iters); CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1)); float ms; CK(cudaEventElapsedTime(&ms,e0,e1)); if(ms<best)best=ms; }
+  double perms=(double)blocks*TPB*iters;
+  int nb=0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kk<UU,0,TPB,1>, TPB, smem);
+  printf("{\"variant\":\"%s\",\"unroll\":%d,\"tpb\":%d,\"blocks_per_sm\":%d,\"warps_per_scheduler\":%d,\"ms\":%.3f,\"gperm_per_s\":%.3f,\"tera_alg_ops\":%.3f}\n",name,UU,TPB,nb,nb,best,perms/best/1e6,perms*4320/best/1e9);
+}
+int main(int argc, char** argv){
   cudaDeviceProp p; CK(cudaGetDeviceProperties(&p,0)); int sms=p.multiProcessorCount;
   uint32_t h[32]; for(int i=0;i<32;i++)h[i]=1u<<i; CK(cudaMemcpyToSymbol(POW2,h,sizeof h));
   uint2* d; size_t n=(size_t)sms*16*1024*25; CK(cudaMalloc(&d,n*sizeof(uint2))); CK(cudaMemset(d,0x5a,n*sizeof(uint2)));
+  if(argc>1){  // occupancy study only
+    for(int bps=1;bps<=4;bps++){ run_occ<1>("occ_loop1",d,sms,bps); run_occ<2>("occ_loop2",d,sms,bps); }
+    return 0;
+  }
   run<1,0,256,2>("loop1",d,sms);
   run<2,0,256,2>("loop2",d,sms);
   run<24,0,256,2>("full",d,sms);
