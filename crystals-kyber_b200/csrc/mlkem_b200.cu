@@ -24,7 +24,7 @@ using namespace mlkem;
 
 thread_local char tl_error[512] = "";
 std::atomic<unsigned long long> g_launches{0};
-std::atomic<int> g_streams{2};  // streams that device-memory calls interleave their chunks on (1 = serial)
+std::atomic<int> g_streams{4};  // streams that device-memory calls interleave their chunks on (1 = serial; measured 31.3 / 32.4 / 32.5 / 32.5 M pairs/s with 1 / 2 / 3 / 4)
 int env_int(const char *name, int dflt) {
     const char *v = getenv(name);
     return v && *v ? atoi(v) : dflt;
@@ -431,10 +431,10 @@ int drive(const mlkem_b200_opts *o, size_t n, size_t ws_per_item, std::vector<Bu
         // NULL is the CUDA default stream (what torch hands over for its default stream), not a library stream:
         // the caller orders its own work against ours through the stream it names.
         cudaStream_t st = static_cast<cudaStream_t>(o->stream);
-        // Large batches are cut into chunks that alternate between the library's two streams (forked from and
-        // joined back into the caller's stream): the kernels of a chunk are a dependent chain that alternates
-        // between alu-bound hashing and fma-heavy polynomial arithmetic, so two chains in flight fill both pipes
-        // and each other's tails.
+        // Large batches are cut into chunks that take turns on the library's streams (forked from and joined back
+        // into the caller's stream): the kernels of a chunk are a dependent chain that alternates between alu-bound
+        // hashing and fma-heavy polynomial arithmetic, so several chains in flight fill each other's tails (the
+        // clean-up pass of the matrix kernel, for one, fills barely more than one wave of blocks).
         if (!(o && o->chunk_items > 0) && n >= ((size_t)1 << 16) && nchunks < 2 && g_streams.load() > 1) {
             chunk = ((n + 1) / 2 + 1023) & ~(size_t)1023;
         }

@@ -187,8 +187,9 @@ int mlkem_b200_sha3_bits_batch(size_t n, const uint8_t *msgs, size_t nbits, cons
  * ({"kernel name": {"launches": L, "ms": total}, ...}) into buf, clears the records and returns the number of
  * bytes written (0 when nothing was recorded). */
 void mlkem_b200_profile(int enable);
-/* Device-memory calls interleave their chunks on 2 internal streams by default (kernels of different chunks
- * overlap).  n = 1 serialises them on the caller's stream, which is what per-kernel timing needs. */
+/* Device-memory calls interleave their chunks on 4 internal streams by default (kernels of different chunks
+ * overlap).  n = 1 serialises them on the caller's stream, which is what per-kernel timing needs; n < 1 restores
+ * the default. */
 void mlkem_b200_set_streams(int n);
 int mlkem_b200_profile_report(char *buf, int cap);
 
