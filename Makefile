@@ -21,9 +21,13 @@ build/libmlkem_b200_exp.so: $(CSRC)/mlkem_b200.cu $(CSRC)/mlkem_kernels.cuh $(CS
 	mkdir -p build
 	$(NVCC) $(NVFLAGS) -DMLKEM_B200_EXPERIMENT -shared -o $@ $(CSRC)/mlkem_b200.cu
 
-tools: build/microbench build/keccak_bench
+tools: build/microbench build/keccak_bench build/coissue_bench
 
 build/microbench: $(CSRC)/microbench.cu
+	mkdir -p build
+	$(NVCC) $(ARCH) -O3 -lineinfo -o $@ $<
+
+build/coissue_bench: $(CSRC)/coissue_bench.cu
 	mkdir -p build
 	$(NVCC) $(ARCH) -O3 -lineinfo -o $@ $<
 
@@ -36,7 +40,7 @@ oracle: lib
 	$(MAKE) -C oracle drivers
 
 clean:
-	rm -f $(LIB) build/microbench build/keccak_bench
+	rm -f $(LIB) build/microbench build/keccak_bench build/coissue_bench
 	$(MAKE) -C oracle clean
 
 .PHONY: all lib exp tools oracle clean

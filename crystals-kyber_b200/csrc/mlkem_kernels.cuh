@@ -478,7 +478,7 @@ __device__ __forceinline__ void sample_ntt_thread(const Lane rho[4], uint32_t &b
 }
 
 // =================================================================================================
-// SampleNTT, fast path: exactly three squeezed blocks per sponge, parsing on the fma pipe
+// SampleNTT, fast path: exactly three squeezed blocks per sponge
 // =================================================================================================
 // 99.1 % of all sponges are complete after three blocks (336 candidates, 256 needed, acceptance 0.813).  A warp
 // that waits for its slowest lane pays a fourth permutation in one case out of four, and its block mates wait at
@@ -486,58 +486,48 @@ __device__ __forceinline__ void sample_ntt_thread(const Lane rho[4], uint32_t &b
 // an incomplete sponge and leaves them to a dense clean-up pass (k_sample_matvec_list) that re-runs them through
 // the general sampler.  Straight-line code, no votes in the first two blocks, every warp does identical work.
 //
-// The candidate loop is kept off the alu pipe, which belongs to Keccak (LOP3 / SHF): the 12-bit field is brought
-// to the top of a register by multiplies (a straddling field by multiply-high + multiply-add), d = field >> 20 is
-// a multiply-high, the rejection bit is floor(d * ceil(2^32 / q) / 2^32) (exactly d >= q for d < 4096), every
-// candidate is stored unconditionally at the running position and the position advances by 2 - 2 * rejected
-// (one multiply-add).  A rejected value is overwritten by the next candidate.  Blocks 1 and 2 cannot overflow the
-// slot (2 * 112 < 256); in block 3 a 16-candidate chunk runs unchecked while every lane of the warp still has room
-// for 16 coefficients and otherwise clamps the position to the end of the slot (one add-min per candidate), where
-// the slot's spare 129th word absorbs the stores of lanes that are already complete.
-__device__ __forceinline__ uint32_t mulhi_rt(uint32_t x, uint32_t m) {  // IMAD.HI with a multiplier that is constant after unrolling
-    uint32_t d;
-    asm("mul.hi.u32 %0, %1, %2;" : "=r"(d) : "r"(x), "r"(m));
-    return d;
-}
-__device__ __forceinline__ uint32_t madlo_rt(uint32_t a, uint32_t b, uint32_t c) {  // IMAD
-    uint32_t d;
-    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
-    return d;
-}
+// Candidate loop: the 12-bit field is brought to the top of a register (multiply by a constant-bank power of two --
+// ptxas would turn a literal one into a shift -- or a funnel shift when the field straddles two words), compared there
+// against q << 20 without masking, shifted down and stored UNCONDITIONALLY at the running position, which advances
+// under the predicate; a rejected value is overwritten by the next candidate.  Blocks 1 and 2 cannot overflow the slot
+// (2 * 112 < 256); in block 3 a 16-candidate chunk runs unchecked while every lane of the warp still has room for 16
+// coefficients and otherwise also tests the position, the slot's spare 129th word absorbing the stores of lanes that
+// are already complete.
+// (Measured alternatives, 2^20 Encaps, fused kernel: rejection bit and position by multiply-high / multiply-add, value
+// by multiply-high, i.e. nothing on the alu pipe: 9.50 ms; value by shift: 9.40 ms; this form: 9.31 ms.  IMAD.HI is
+// the costliest neighbour a LOP3 stream can have: profiles/coissue_r01.jsonl.)
+#ifdef MLKEM_B200_EXPERIMENT
+#define MLKEM_CHECK_SLOT_STORE(st, lim) \
+    if ((st) + 512 < end_addr || (st) > (lim)) __trap();  // own bounds check: compute-sanitizer is not available on the pool
+#else
+#define MLKEM_CHECK_SLOT_STORE(st, lim)
+#endif
 template <bool CHECKED>
-__device__ __forceinline__ void parse_chunk_fma(const uint32_t w[7], uint32_t &addr, uint32_t end_addr) {
+__device__ __forceinline__ void parse_chunk3(const uint32_t w[7], uint32_t &addr, uint32_t end_addr) {
 #pragma unroll
     for (int m = 0; m < 16; m++) {  // candidate m = bits [12 m, 12 m + 12): d1 / d2 of group m / 2 (ml_kem.c:208-209)
         const int bit = 12 * m, wi = bit >> 5, sh = bit & 31;
         uint32_t t;  // the field in bits [20, 32), don't-care bits below
         if (sh == 20) t = w[wi];
         else if (sh < 20) t = shl_fma(w[wi], 20 - sh);
-        else t = madlo_rt(w[wi + 1], c_pow2[52 - sh], mulhi_rt(w[wi], 1u << (52 - sh)));  // (w[wi] >> (sh - 20)) + (w[wi+1] << (52 - sh))
-        const uint32_t d = mulhi_rt(t, 4096u);           // t >> 20
-        const uint32_t rej = __umulhi(d, 1290168u);      // d >= q  (:211, :216), exact for d < 4096
-#ifdef MLKEM_B200_EXPERIMENT  // own bounds check (compute-sanitizer is not available on the pool): slot .. slot + 512 (the spare word)
-        {
-            const uint32_t st = CHECKED ? addr : addr + 2 * m;
-            if (st + 512 < end_addr || st > end_addr || (!CHECKED && st >= end_addr)) __trap();
-        }
-#endif
+        else t = __funnelshift_r(w[wi], w[wi + 1], sh - 20);
+        const bool ok = t < (kQ << 20);  // d < q  (:211, :216)
+        MLKEM_CHECK_SLOT_STORE(addr, CHECKED ? end_addr : end_addr - 2)
+        asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"((uint16_t)(t >> 20)) : "memory");
         if (CHECKED) {
-            asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"((uint16_t)d) : "memory");
-            addr = min(madlo_rt(rej, 0xFFFFFFFEu, addr) + 2u, end_addr);  // j < N  (:203, :216)
+            if (ok && addr < end_addr) addr += 2;  // j < N  (:203, :216)
         } else {
-            asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr + 2 * m), "h"((uint16_t)d) : "memory");
-            addr = madlo_rt(rej, 0xFFFFFFFEu, addr);  // biased position: the true one is addr + 2 (m + 1)
+            if (ok) addr += 2;
         }
     }
-    if (!CHECKED) addr += 32;
 }
 template <int MODE_CHECK>  // 0: never checked (blocks 1, 2), 1: decide per chunk (block 3)
-__device__ __forceinline__ void parse_block_fma(const Lane a[25], uint32_t &addr, uint32_t end_addr) {
+__device__ __forceinline__ void parse_block3(const Lane a[25], uint32_t &addr, uint32_t end_addr) {
 #pragma unroll
     for (int ch = 0; ch < 7; ch++) {  // 3 lanes = 6 words = 16 candidates
         const uint32_t w[7] = {a[3 * ch].lo, a[3 * ch].hi, a[3 * ch + 1].lo, a[3 * ch + 1].hi, a[3 * ch + 2].lo, a[3 * ch + 2].hi, 0u};
-        if (MODE_CHECK == 0 || __all_sync(kFullMask, addr + 32 <= end_addr)) parse_chunk_fma<false>(w, addr, end_addr);
-        else parse_chunk_fma<true>(w, addr, end_addr);
+        if (MODE_CHECK == 0 || __all_sync(kFullMask, addr + 32 <= end_addr)) parse_chunk3<false>(w, addr, end_addr);
+        else parse_chunk3<true>(w, addr, end_addr);
     }
 }
 // Returns true when the slot holds the complete polynomial.  No group limit applies: three blocks are 168 of the 278
@@ -560,8 +550,8 @@ __device__ __forceinline__ bool sample_ntt_three_blocks(const Lane rho[4], uint3
             continue;
         }
 #endif
-        if (blk < 2) parse_block_fma<0>(a, addr, end_addr);
-        else parse_block_fma<1>(a, addr, end_addr);
+        if (blk < 2) parse_block3<0>(a, addr, end_addr);
+        else parse_block3<1>(a, addr, end_addr);
     }
     return addr >= end_addr;
 }
