@@ -22,8 +22,8 @@
         }                                                                                            \
     } while (0)
 
-enum B { B_NONE = 0, B_IMAD, B_IMAD_CONST, B_IMADHI, B_IADD3, B_LDS, B_BUTTERFLY, B_LOP3, B_COUNT };
-static const char *kName[B_COUNT] = {"none", "imad(3 regs)", "imad(const operand)", "imad.hi", "iadd3", "lds.u16", "lazy butterfly (IMAD.HI, 2 IMAD, 2 IADD)", "lop3"};
+enum B { B_NONE = 0, B_IMAD, B_IMAD_CONST, B_IMADHI, B_IADD3, B_LDS, B_BUTTERFLY, B_LOP3, B_FFMA, B_FFMA_CONST, B_FADD, B_IMADWIDE, B_STS, B_ISETP_SEL, B_COUNT };
+static const char *kName[B_COUNT] = {"none", "imad(3 regs)", "imad(const operand)", "imad.hi", "iadd3", "lds.u16", "lazy butterfly (IMAD.HI, 2 IMAD, 2 IADD)", "lop3", "ffma(3 regs)", "ffma(const operand)", "fadd", "imad.wide", "sts.u16", "isetp+sel"};
 
 __constant__ uint32_t c_k[4];
 
@@ -70,6 +70,24 @@ __global__ void __launch_bounds__(256, 1) k(uint32_t *out, int iters, unsigned l
                 } else if (BOP == B_LDS) {
 #define LS(a) { uint16_t t_; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(t_) : "r"(sa + ((a) & 0)) : "memory"); a += t_; }
                     LS(x0) LS(x1) LS(x2) LS(x3) LS(x4) LS(x5) LS(x6) LS(x7)
+                } else if (BOP == B_FFMA) {
+#define FF(a) asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+r"(a) : "r"(m), "r"(s));
+                    FF(x0) FF(x1) FF(x2) FF(x3) FF(x4) FF(x5) FF(x6) FF(x7)
+                } else if (BOP == B_FFMA_CONST) {
+#define FC(a) a = __float_as_uint(fmaf(__uint_as_float(a), __uint_as_float(c_k[2]), 1.5f));
+                    FC(x0) FC(x1) FC(x2) FC(x3) FC(x4) FC(x5) FC(x6) FC(x7)
+                } else if (BOP == B_FADD) {
+#define FA(a) asm volatile("add.rn.f32 %0, %0, %1;" : "+r"(a) : "r"(m));
+                    FA(x0) FA(x1) FA(x2) FA(x3) FA(x4) FA(x5) FA(x6) FA(x7)
+                } else if (BOP == B_IMADWIDE) {
+#define IW(a) { uint32_t hi_; asm volatile("{.reg .b64 t; mul.wide.u32 t, %0, %2; mov.b64 {%0, %1}, t;}" : "+r"(a), "=r"(hi_) : "r"(m)); a ^= hi_ & 0; }
+                    IW(x0) IW(x1) IW(x2) IW(x3) IW(x4) IW(x5) IW(x6) IW(x7)
+                } else if (BOP == B_STS) {
+#define SS(a) asm volatile("st.shared.u16 [%0], %1;" ::"r"(sa), "h"((uint16_t)(a)) : "memory");
+                    SS(x0) SS(x1) SS(x2) SS(x3) SS(x4) SS(x5) SS(x6) SS(x7)
+                } else if (BOP == B_ISETP_SEL) {
+#define IS(a) asm volatile("{.reg .pred p; setp.lt.u32 p, %0, %1; @p add.u32 %0, %0, %2;}" : "+r"(a) : "r"(m), "r"(s));
+                    IS(x0) IS(x1) IS(x2) IS(x3) IS(x4) IS(x5) IS(x6) IS(x7)
                 } else if (BOP == B_LOP3) {
                     L3(x0) L3(x1) L3(x2) L3(x3) L3(x4) L3(x5) L3(x6) L3(x7)
                 } else if (BOP == B_BUTTERFLY) {
@@ -87,7 +105,7 @@ __global__ void __launch_bounds__(256, 1) k(uint32_t *out, int iters, unsigned l
                     BF(x0, x2) BF(x1, x3) BF(x4, x6) BF(x5, x7)
                 }
             }
-            count += (BOP == B_BUTTERFLY) ? 4 * 40 : 32;
+            count += (BOP == B_BUTTERFLY) ? 4 * 40 : (BOP == B_ISETP_SEL) ? 64 : 32;
         }
     }
     unsigned long long t1 = clock64();
@@ -139,5 +157,11 @@ int main() {
     run<B_IADD3>(prop.multiProcessorCount, d_out, d_res);
     run<B_LDS>(prop.multiProcessorCount, d_out, d_res);
     run<B_BUTTERFLY>(prop.multiProcessorCount, d_out, d_res);
+    run<B_FFMA>(prop.multiProcessorCount, d_out, d_res);
+    run<B_FFMA_CONST>(prop.multiProcessorCount, d_out, d_res);
+    run<B_FADD>(prop.multiProcessorCount, d_out, d_res);
+    run<B_IMADWIDE>(prop.multiProcessorCount, d_out, d_res);
+    run<B_STS>(prop.multiProcessorCount, d_out, d_res);
+    run<B_ISETP_SEL>(prop.multiProcessorCount, d_out, d_res);
     return 0;
 }

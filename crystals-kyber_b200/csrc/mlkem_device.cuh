@@ -57,6 +57,21 @@ __device__ __forceinline__ uint2 lane_gamma(int i) { return __ldg(&g_tw.gamma32[
 // 1. Field arithmetic
 // ------------------------------------------------------------------------------------------------
 
+// High half of a 32 x 32-bit product: IMAD.HI.  (The co-issue microbenchmark prices an IMAD.HI next to a LOP3 stream at
+// 1.71 lost LOP3 issues and an IMAD.WIDE at 0.29, profiles/coissue_r01.jsonl, but in the kernels the IMAD.WIDE form --
+// -DMLKEM_B200_MULHI_WIDE, inline PTX so that ptxas keeps it -- is slower: fused kernel 9.42 vs 9.29 ms, k_noise 1.58 vs
+// 1.55 ms per 2^20 items.  It needs an aligned register pair per product.)
+__device__ __forceinline__ uint32_t mulhi(uint32_t a, uint32_t b) {
+#ifndef MLKEM_B200_MULHI_WIDE
+    return __umulhi(a, b);
+#else
+    [[maybe_unused]] uint32_t lo;
+    uint32_t hi;
+    asm volatile("{.reg .b64 t; mul.wide.u32 t, %2, %3; mov.b64 {%0, %1}, t;}" : "=r"(lo), "=r"(hi) : "r"(a), "r"(b));
+    return hi;
+#endif
+}
+
 // a * w mod q for a < 2^16 and a constant w given as {w, floor(w 2^16 / q)}; result in [0, 2q).
 __device__ __forceinline__ uint32_t mul_shoup(uint32_t a, uint2 w) {
     uint32_t qh = (a * w.y) >> 16;
@@ -65,7 +80,7 @@ __device__ __forceinline__ uint32_t mul_shoup(uint32_t a, uint2 w) {
 // Same product with the quotient estimate taken by a high multiply (a < 2^32, w32 = floor(w 2^32 / q)): three
 // fma-pipe instructions and none on the alu pipe.  Used where the alu pipe is the bottleneck (next to Keccak).
 __device__ __forceinline__ uint32_t mul_shoup_fma(uint32_t a, uint32_t w, uint32_t w32) {
-    uint32_t qh = __umulhi(a, w32);
+    uint32_t qh = mulhi(a, w32);
     return a * w - qh * kQ;
 }
 // Pipe policy of the transforms.  The hashing kernels saturate the alu pipe (LOP3 / SHF) and leave the fma pipe idle,
@@ -79,7 +94,7 @@ __device__ __forceinline__ uint32_t mulz(uint32_t a, uint2 z) {  // z from the z
 }
 // x mod q, exact, for x < 2^21 (1290168 = ceil(2^32 / q); checked exhaustively in
 // tests/test_abi_cpu.py::test_arithmetic_lemmas): two fma-pipe instructions, none on the alu pipe.
-__device__ __forceinline__ uint32_t canon_fma(uint32_t x) { return x - __umulhi(x, 1290168u) * kQ; }
+__device__ __forceinline__ uint32_t canon_fma(uint32_t x) { return x - mulhi(x, 1290168u) * kQ; }
 // x mod q for x < 2^16, result in [0, q].
 __device__ __forceinline__ uint32_t barrett16(uint32_t x) {
     uint32_t qh = (x * 40317u) >> 27;  // floor(2^27 / q) = 40317
@@ -87,7 +102,7 @@ __device__ __forceinline__ uint32_t barrett16(uint32_t x) {
 }
 // x mod q for any x < 2^32, result in [0, 2q).
 __device__ __forceinline__ uint32_t barrett32(uint32_t x) {
-    uint32_t qh = __umulhi(x, 1290167u);  // floor(2^32 / q)
+    uint32_t qh = mulhi(x, 1290167u);  // floor(2^32 / q)
     return x - qh * kQ;
 }
 // r in [0, 2q) -> [0, q)
@@ -103,7 +118,7 @@ template <int D>
 __device__ __forceinline__ uint32_t compress(uint32_t x) {
     if (D >= 12) return x;
     uint32_t t = (x << D) + 1664u;  // < 2^23
-    uint32_t qh = __umulhi(t, 1290167u);
+    uint32_t qh = mulhi(t, 1290167u);
     uint32_t r = t - qh * kQ;  // [0, 2q)
     qh += (r >= kQ);
     return qh & ((1u << D) - 1u);
@@ -115,7 +130,7 @@ template <int D>
 __device__ __forceinline__ uint32_t compress_canon(uint32_t x) {
     static_assert(D == 1 || D == 4 || D == 5 || D == 10 || D == 11, "no verified constants for this d");
     constexpr uint32_t c = (D >= 10) ? 1664u : 1665u, M = (D >= 10) ? 1290168u : 1290167u;
-    return __umulhi(x * (1u << D) + c, M) & ((1u << D) - 1u);
+    return mulhi(x * (1u << D) + c, M) & ((1u << D) - 1u);
 }
 
 // Compress_d of a RESIDUE x < 4q (any representative of the coefficient) for d <= 5: for these d the single
@@ -124,7 +139,7 @@ __device__ __forceinline__ uint32_t compress_canon(uint32_t x) {
 template <int D>
 __device__ __forceinline__ uint32_t compress_resid(uint32_t x) {
     static_assert(D == 1 || D == 4 || D == 5, "single multiply-high is not exact on residues for this d");
-    return __umulhi(x * (1u << D) + 1664u, 1290168u) & ((1u << D) - 1u);
+    return mulhi(x * (1u << D) + 1664u, 1290168u) & ((1u << D) - 1u);
 }
 
 // ml_kem.c:104 Decompress_d: (q y + 2^(d-1)) >> d.
@@ -538,9 +553,7 @@ __device__ __forceinline__ uint32_t unpack1(const uint8_t *src, int c) {
 // x >> S as a multiply-high (IMAD.HI, fma pipe) -- inline PTX so that the compiler does not turn it back into a shift.
 template <int S>
 __device__ __forceinline__ uint32_t shr_fma(uint32_t x) {
-    uint32_t d;
-    asm("mul.hi.u32 %0, %1, %2;" : "=r"(d) : "r"(x), "n"(1u << (32 - S)));
-    return d;
+    return mulhi(x, 1u << (32 - S));
 }
 // Nibble j of w, given sel = nibble_weight(j).
 #ifndef MLKEM_B200_NIBBLE_ALU  // multiply + multiply-high with sel = 1 << (28 - 4 j): nothing on the alu pipe (measured: k_noise
