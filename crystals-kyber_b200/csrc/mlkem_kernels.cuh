@@ -774,16 +774,19 @@ __global__ void __launch_bounds__(32 * P::K) k_sample_matvec(MatvecArgs g) {
         s_inc[tid] = active && !complete;
     }
     __syncthreads();
-    if (tid < 32) {
-        const int gg = blockIdx.x * 32 + tid;
-        bool deferred = false;
+    {  // every warp resolves the groups it is going to finish itself (warp, warp + K, ...): no second block barrier
+        const int grp = warp + K * lane;
+        if (grp < 32) {
+            const int gg = blockIdx.x * 32 + grp;
+            bool deferred = false;
 #pragma unroll
-        for (int j = 0; j < K; j++) deferred |= s_inc[tid * K + j] != 0;
-        const bool active = gg / K < g.n;
-        s_gg[tid] = (active && !deferred) ? gg : -1;
-        if (active && deferred) g.defer_list[atomicAdd(g.defer_count, 1)] = gg;
+            for (int j = 0; j < K; j++) deferred |= s_inc[grp * K + j] != 0;
+            const bool active = gg / K < g.n;
+            s_gg[grp] = (active && !deferred) ? gg : -1;
+            if (active && deferred) g.defer_list[atomicAdd(g.defer_count, 1)] = gg;
+        }
+        __syncwarp();
     }
-    __syncthreads();
 #ifdef MLKEM_B200_EXPERIMENT
     if (g.experiment & 1) return;
     if (g.experiment & 4) matvec_finish_rows<P, MODE>(g, s_slots, s_gg, lane, warp);
