@@ -418,6 +418,7 @@ int drive(const mlkem_b200_opts *o, size_t n, size_t ws_per_item, std::vector<Bu
     if (env_streams > 0) g_streams.store(env_streams > kSlots ? kSlots : env_streams);
     size_t chunk = (o && o->chunk_items > 0) ? (size_t)o->chunk_items
                    : (on_device ? (env_chunk > 0 ? (size_t)env_chunk : (size_t)1 << 18) : (env_hchunk > 0 ? (size_t)env_hchunk : (size_t)1 << 16));
+    if (chunk > ((size_t)1 << 26)) chunk = (size_t)1 << 26;  // the kernels index rows (items x k) and list entries with int
     if (chunk > n) chunk = n;
     const size_t nchunks = (n + chunk - 1) / chunk;
     std::vector<void *> ptrs(bufs.size());
