@@ -439,6 +439,62 @@ def test_full_size_properties(mlkem, oracle):
     assert (Kd[sl].cpu().numpy() == oracle.decaps(768, dk[sl].cpu().numpy(), c[sl].cpu().numpy())).all()
 
 
+@pytest.mark.parametrize("ps", SETS)
+def test_baseline_config3_keygen_full_size(mlkem, oracle, ps):
+    """BASELINE configs[2]: batched KeyGen for 2^20 keys per parameter set, seeds from the global index (workload.py).
+    Size-independent properties over the whole batch -- dk embeds dk_pke || ek || H(ek) || z (ml_kem.c:1050-1077), so
+    the embedded copy must equal ek, the device hash check (ml_kem.c:1336-1350) must pass for every key and fail when
+    a byte of the embedded ek is flipped, z must be in place -- plus bit-exactness against the oracle on slices."""
+    import torch
+
+    import crystals_kyber_b200 as ck
+    from crystals_kyber_b200 import workload as wl
+
+    n, k = 1 << 20, ck.PARAMS[ps][0]
+    d, z, _ = wl.derive_inputs(lambda msg, ln: mlkem.hash_batch(1, msg, ln), 0, n, torch.device("cuda"))
+    ek, dk = mlkem.keygen(ps, d, z)
+    assert torch.equal(dk[:, 384 * k : 768 * k + 32], ek)
+    assert torch.equal(dk[:, 768 * k + 64 :], z)
+    status = mlkem.check_dk(ps, dk)
+    assert int((status != 0).sum()) == 0
+    bad = dk[:4096].clone()
+    bad[:, 384 * k + 5] ^= 1
+    assert bool((mlkem.check_dk(ps, bad) == -5).all())
+    for lo in (0, 500_000, n - 257):
+        sl = slice(lo, lo + 257)
+        oek, odk = oracle.keygen(ps, d[sl].cpu().numpy(), z[sl].cpu().numpy())
+        assert (ek[sl].cpu().numpy() == oek).all() and (dk[sl].cpu().numpy() == odk).all()
+
+
+def test_baseline_config4_encaps_decaps_full_size(mlkem, oracle):
+    """BASELINE configs[3]: ML-KEM-768 Encaps + Decaps over 2^22 items, 10 % tampered (i % 10 == 3).  Properties over the
+    whole batch: every untampered item decapsulates to the encapsulated key, every tampered one does not; slices
+    (tampered items included) are bit-exact against the oracle, i.e. the rejection key is J(z || c') (ml_kem.c:1196-1215)."""
+    import torch
+
+    from crystals_kyber_b200 import workload as wl
+
+    n = 1 << 22
+    d, z, m = wl.derive_inputs(lambda msg, ln: mlkem.hash_batch(1, msg, ln), 0, n, torch.device("cuda"))
+    ek, dk = mlkem.keygen(768, d, z)
+    c, K = mlkem.encaps(768, ek, m)
+    sel = wl.tamper_inplace(c, 0)
+    Kd = mlkem.decaps(768, dk, c)
+    same = (Kd == K).all(dim=1)
+    tampered = torch.zeros(n, dtype=torch.bool, device="cuda")
+    tampered[sel] = True
+    assert int(sel.numel()) == (n + 6) // 10
+    assert bool(same[~tampered].all()) and not bool(same[tampered].any())
+    for lo in (0, 2_000_003, n - 300):
+        sl = slice(lo, lo + 300)
+        oc, oK = oracle.encaps(768, ek[sl].cpu().numpy(), m[sl].cpu().numpy())
+        assert (K[sl].cpu().numpy() == oK).all()
+        ct = c[sl].cpu().numpy()
+        loc = (np.arange(lo, lo + 300) % 10 == 3)
+        assert (ct[~loc] == oc[~loc]).all() and (ct[loc] != oc[loc]).any(axis=1).all()
+        assert (Kd[sl].cpu().numpy() == oracle.decaps(768, dk[sl].cpu().numpy(), ct)).all()
+
+
 # ------------------------------------------------------------------ the reference-signature API (include/ml_kem.h)
 def test_reference_signature_api(mlkem, oracle):
     """KEM_KeyGen -> KEM_Encaps -> KEM_Decaps through the drop-in C API with the reference's stride-4 unions
