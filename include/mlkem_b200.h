@@ -61,7 +61,13 @@ typedef struct mlkem_b200_opts {
     int sample_group_limit; /* test hook for the SampleNTT give-up rule (ml_kem.c:221-227); 0 = 278 (the reference) */
     int flags;              /* 0 = bit-exact to the reference; MLKEM_B200_FLAG_FIPS203 see below */
 } mlkem_b200_opts;
-/* A NULL opts pointer means {device -1, MEM_HOST, NULL, 0, 0, 0}. */
+/* A NULL opts pointer means {device -1, MEM_HOST, NULL, 0, 0, 0}.
+ *
+ * Tuning knobs read from the environment (defaults in brackets; measured on B200 in profiles/experiments_r01.txt):
+ *   MLKEM_B200_CHUNK       items per chunk of a device-memory call [262144]; workspace is about 4.3 KB per item and stream
+ *   MLKEM_B200_STREAMS     internal streams the chunks of a device-memory call take turns on [4]
+ *   MLKEM_B200_HOST_CHUNK  items per staged chunk of a host-memory call [65536]
+ *   MLKEM_B200_HOST_SLOTS  staging slots (H2D / kernels / D2H overlap) of a host-memory call [3] */
 
 /* FIPS 203 mode.  The reference deviates from FIPS 203: its PRF and J are SHAKE128
  * and its ByteDecode12 never reduces, so the modulus check of KEM_Encaps cannot fail (D4).  With this flag PRF and J are
