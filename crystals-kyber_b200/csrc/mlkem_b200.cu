@@ -277,15 +277,15 @@ int enqueue_encrypt(cudaStream_t st, Arena &ws, int n, const uint8_t *ek, size_t
     // (PRF = SHAKE128 as in the reference, or SHAKE256 in FIPS mode)
     if (!fips) {
         LAUNCH((k_noise<P::ETA1, true>), dim3(cdiv(n, kNoiseTPB), K), kNoiseTPB, 0, st, n, seed, seed_stride, 0, yhat, (size_t)K * 256,
-               (uint32_t *)nullptr, (size_t)0);
+               (uint32_t *)nullptr, (size_t)0, (uint8_t *)nullptr, (size_t)0, 0);
         // e1, e2 = CBD_eta2(PRF(r, K..2K))               ml_kem.c:839-851
         LAUNCH((k_noise<P::ETA2, false>), dim3(cdiv(n, kNoiseTPB), K + 1), kNoiseTPB, 0, st, n, seed, seed_stride, K, (uint16_t *)nullptr,
-               (size_t)0, codes, (size_t)(K + 1) * 32);
+               (size_t)0, codes, (size_t)(K + 1) * 32, (uint8_t *)nullptr, (size_t)0, 0);
     } else {
         LAUNCH((k_noise<P::ETA1, true, kRateSha3_256>), dim3(cdiv(n, kNoiseTPB), K), kNoiseTPB, 0, st, n, seed, seed_stride, 0, yhat,
-               (size_t)K * 256, (uint32_t *)nullptr, (size_t)0);
+               (size_t)K * 256, (uint32_t *)nullptr, (size_t)0, (uint8_t *)nullptr, (size_t)0, 0);
         LAUNCH((k_noise<P::ETA2, false, kRateSha3_256>), dim3(cdiv(n, kNoiseTPB), K + 1), kNoiseTPB, 0, st, n, seed, seed_stride, K,
-               (uint16_t *)nullptr, (size_t)0, codes, (size_t)(K + 1) * 32);
+               (uint16_t *)nullptr, (size_t)0, codes, (size_t)(K + 1) * 32, (uint8_t *)nullptr, (size_t)0, 0);
     }
     MatvecArgs a{};
     a.n = n;
@@ -331,14 +331,16 @@ int enqueue_keygen(cudaStream_t st, Arena &ws, int n, const uint8_t *d, const ui
     const size_t dk_stride = full ? P::DK : P::DKPKE;
     uint8_t *rs = ws.take<uint8_t>((size_t)n * 64);
     uint16_t *se = ws.take<uint16_t>((size_t)n * 2 * K * 256);
-    LAUNCH(k_keygen_G, cdiv(n, kHashTPB), kHashTPB, 0, st, n, d, (uint32_t)K, rs);
+    // G, and rho into the tail of ek and (full key) the ek copy inside dk
+    LAUNCH(k_keygen_G, cdiv(n, kHashTPB), kHashTPB, 0, st, n, d, (uint32_t)K, rs, ek + 384 * K, (size_t)P::EK,
+           full ? dk + 768 * K : (uint8_t *)nullptr, dk_stride);
     // s^ (nonces 0..K-1) and e^ (nonces K..2K-1), ml_kem.c:696-720; sigma = rs + 32
     if (!fips)
         LAUNCH((k_noise<P::ETA1, true>), dim3(cdiv(n, kNoiseTPB), 2 * K), kNoiseTPB, 0, st, n, rs + 32, (size_t)64, 0, se, (size_t)2 * K * 256,
-               (uint32_t *)nullptr, (size_t)0);
+               (uint32_t *)nullptr, (size_t)0, dk, dk_stride, K);  // dk_pke rows = ByteEncode12(s^) written on the way (:750-756)
     else
         LAUNCH((k_noise<P::ETA1, true, kRateSha3_256>), dim3(cdiv(n, kNoiseTPB), 2 * K), kNoiseTPB, 0, st, n, rs + 32, (size_t)64, 0, se,
-               (size_t)2 * K * 256, (uint32_t *)nullptr, (size_t)0);
+               (size_t)2 * K * 256, (uint32_t *)nullptr, (size_t)0, dk, dk_stride, K);
     MatvecArgs a{};
     a.n = n;
     a.group_limit = group_limit;
@@ -353,7 +355,6 @@ int enqueue_keygen(cudaStream_t st, Arena &ws, int n, const uint8_t *d, const ui
     a.out2 = full ? dk + 384 * K : nullptr;
     a.out2_stride = dk_stride;
     if (int rc = launch_matvec<P, kModeKeyGen>(st, ws, a)) return rc;
-    LAUNCH((k_keygen_encode_s<P>), cdiv((size_t)n * K, kWarpTPB / 32), kWarpTPB, 0, st, n, se, (size_t)2 * K * 256, rs, ek, dk, dk_stride, full);
     if (full) LAUNCH((k_keygen_H<P>), cdiv(n, kHashTPB), kHashTPB, 0, st, n, ek, z, dk);
     return 0;
 }

@@ -41,8 +41,11 @@ constexpr int kSlotWords = 129; // shared-memory words per sampled polynomial sl
 // =================================================================================================
 
 // (rho, sigma) = G(d || k)   (ml_kem.c:674-681).  33-byte message, SHA3-512: one permutation.
+// Also places rho at the tail of ek (ml_kem.c:745-747) and, for the full decapsulation key, inside dk (:1058-1062):
+// rho_out + i*rho_stride, rho_out2 + i*rho_stride2 (nullable).
 __global__ void __launch_bounds__(kHashTPB) k_keygen_G(int n, const uint8_t *__restrict__ d, uint32_t kbyte,
-                                                       uint8_t *__restrict__ rs) {
+                                                       uint8_t *__restrict__ rs, uint8_t *__restrict__ rho_out, size_t rho_stride,
+                                                       uint8_t *__restrict__ rho_out2, size_t rho_stride2) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     Lane a[25];
@@ -54,6 +57,11 @@ __global__ void __launch_bounds__(kHashTPB) k_keygen_G(int n, const uint8_t *__r
     keccak_f1600(a);
 #pragma unroll
     for (int w = 0; w < 8; w++) store_lane(rs + 64 * (size_t)i + 8 * w, a[w]);
+#pragma unroll
+    for (int w = 0; w < 4; w++) {
+        store_lane(rho_out + rho_stride * i + 8 * w, a[w]);
+        if (rho_out2) store_lane(rho_out2 + rho_stride2 * i + 8 * w, a[w]);
+    }
 }
 
 // SHA3-256 over `P::EK` bytes at `ek`; result in h[0..3].
@@ -344,11 +352,14 @@ __device__ __forceinline__ void load_layoutC_global(uint32_t x[8], int lane, con
 // so a block is uniform in eta and in whether its polynomials get transformed.
 //   seeds       : 32-byte PRF key of item i at seeds + i*seed_stride
 //   NTT_OUT     : out16 + i*out16_stride + p*256   <- NTT(CBD(...)) as uint16, natural order  (s^, e^, y^)
+//                 enc12 + i*enc12_stride + p*384   <- ByteEncode12 of the same polynomial for p < enc12_polys
+//                                                     (KeyGen: dk_pke rows = ByteEncode12(s^[p]), ml_kem.c:750-756)
 //   otherwise   : outc  + i*outc_stride  + p*32    <- 4-bit codes of CBD(...)                 (e1, e2)
 template <int ETA, bool NTT_OUT, int RATE = kRateShake128>
 __global__ void __launch_bounds__(kNoiseTPB) k_noise(int n, const uint8_t *__restrict__ seeds, size_t seed_stride, int nonce0,
                                                      uint16_t *__restrict__ out16, size_t out16_stride,
-                                                     uint32_t *__restrict__ outc, size_t outc_stride) {
+                                                     uint32_t *__restrict__ outc, size_t outc_stride,
+                                                     uint8_t *__restrict__ enc12, size_t enc12_stride, int enc12_polys) {
     __shared__ uint32_t s_codes[NTT_OUT ? kNoiseTPB * 33 : 1];
     __shared__ __align__(16) uint16_t s_scratch[NTT_OUT ? (kNoiseTPB / 32) * kScratchU16 : 2];
     const int p = blockIdx.y;
@@ -374,6 +385,13 @@ __global__ void __launch_bounds__(kNoiseTPB) k_noise(int n, const uint8_t *__res
             for (int r = 0; r < 8; r++) x[r] = nibble_fma(codes[4 * r], pw) + (kQ - 3);  // coefficient lane + 32 r as a residue <= q + 3
             ntt_warp<kFmaPipe>(x, scratch, lane, tw);
             store_layoutC_global(x, lane, out16 + out16_stride * it + 256 * p);
+            if (p < enc12_polys) {  // block-uniform: blockIdx.y selects the polynomial
+                // 8 consecutive 12-bit coefficients = 12 bytes = three words per lane, 384 contiguous bytes per warp
+                uint32_t *row = reinterpret_cast<uint32_t *>(enc12 + enc12_stride * it + 384 * p) + 3 * lane;
+                row[0] = x[0] | (x[1] << 12) | (x[2] << 24);
+                row[1] = (x[2] >> 8) | (x[3] << 4) | (x[4] << 16) | (x[5] << 28);
+                row[2] = (x[5] >> 4) | (x[6] << 8) | (x[7] << 20);
+            }
         }
     } else {
         if (item >= n) return;
@@ -1027,40 +1045,6 @@ __global__ void __launch_bounds__(kWarpTPB) k_decrypt(int n, const uint8_t *__re
         __syncwarp();
     }
     cp_async_wait<0>();
-}
-
-// KeyGen: dk_pke rows = ByteEncode12(s^[i]) (ml_kem.c:750-756), plus the rho / ek-tail copies.
-// One warp per (item, row); s^ as uint16 at shat + item*stride + 256 row.
-template <class P>
-__global__ void __launch_bounds__(kWarpTPB) k_keygen_encode_s(int n, const uint16_t *__restrict__ shat, size_t shat_stride,
-                                                              const uint8_t *__restrict__ rs, uint8_t *__restrict__ ek,
-                                                              uint8_t *__restrict__ dk, size_t dk_stride, bool full_dk) {
-    constexpr int K = P::K;
-    __shared__ __align__(16) uint8_t s_stage[(kWarpTPB / 32) * 384];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const long long gg = (long long)blockIdx.x * (kWarpTPB / 32) + warp;
-    const int item = (int)(gg / K), row = (int)(gg - (long long)item * K);
-    if (item >= n) return;
-    uint8_t *stage = s_stage + warp * 384;
-    const uint32_t *sv = reinterpret_cast<const uint32_t *>(shat + shat_stride * item + 256 * row);
-#pragma unroll
-    for (int r = 0; r < 4; r++) {
-        int t = lane + 32 * r;
-        uint32_t s = __ldg(sv + t);
-        uint32_t v = (s & 0xFFFFu) | ((s >> 16) << 12);
-        stage[3 * t] = (uint8_t)v;
-        stage[3 * t + 1] = (uint8_t)(v >> 8);
-        stage[3 * t + 2] = (uint8_t)(v >> 16);
-    }
-    __syncwarp();
-    const uint32_t *stw = reinterpret_cast<const uint32_t *>(stage);
-    uint32_t *ow = reinterpret_cast<uint32_t *>(dk + dk_stride * item + 384 * row);
-    for (int w = lane; w < 96; w += 32) ow[w] = stw[w];
-    if (row == 0 && lane < 8) {  // rho -> ek tail (ml_kem.c:745-747) and its copy inside dk (:1058-1062)
-        uint32_t v = reinterpret_cast<const uint32_t *>(rs + 64 * (size_t)item)[lane];
-        reinterpret_cast<uint32_t *>(ek + (size_t)P::EK * item + 384 * K)[lane] = v;
-        if (full_dk) reinterpret_cast<uint32_t *>(dk + dk_stride * item + 384 * K + 384 * K)[lane] = v;
-    }
 }
 
 // =================================================================================================
