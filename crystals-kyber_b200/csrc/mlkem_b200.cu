@@ -256,6 +256,9 @@ int launch_matvec(cudaStream_t st, Arena &ws, MatvecArgs a) {
         a.defer_count = ws.take<int>(1);
         CU(cudaMemsetAsync(a.defer_count, 0, sizeof(int), st));
         LAUNCH((k_sample_matvec<P, MODE>), blocks, 32 * K, smem, st, a);
+#ifdef MLKEM_B200_EXPERIMENT
+        if (env_exp & 16) return 0;  // what would a free clean-up pass buy?
+#endif
         LAUNCH((k_sample_matvec_list<P, MODE>), list_grid, 32 * K, smem, st, a);
     } else {
         a.defer_list = nullptr;

@@ -16,7 +16,7 @@ kem = ck.MLKEM()
 g = torch.Generator(device="cuda").manual_seed(1)
 d, z, m = (torch.randint(0, 256, (n, 32), dtype=torch.uint8, device="cuda", generator=g) for _ in range(3))
 ek, dk = kem.keygen(768, d, z)
-kem.set_streams(1)
+kem.set_streams(int(os.environ.get("STREAMS", "1")))
 for _ in range(2):
     kem.encaps(768, ek, m)
 torch.cuda.synchronize()
