@@ -183,7 +183,8 @@ __device__ __forceinline__ Lane chi3(Lane a, Lane b, Lane c) { return Lane{a.lo 
 // sha3.c:207 Keccak_f = 24 x Iota(Chi(Pi(Rho(Theta(S))))) (sha3.c:15,53,88,116,182).
 // Kept as a loop of two rounds per iteration: 360 instructions fit the instruction cache even with several inlined
 // call sites, ptxas renames registers across the back edge without moves, and the loop overhead is halved
-// (measured: +0.9 % over one round per iteration; 24 rounds unrolled overflow the instruction cache: -19 %).
+// (measured: +0.9 % over one round per iteration; three / four rounds per iteration cost the fused matrix kernel 0.8 % / 7 %;
+// 24 rounds unrolled overflow the instruction cache: -19 %).
 __device__ __forceinline__ void keccak_f1600(Lane a[25]) {
 #pragma unroll 2
     for (int rnd = 0; rnd < 24; rnd++) {

@@ -508,9 +508,10 @@ __device__ __forceinline__ void sample_ntt_thread(const Lane rho[4], uint32_t &b
 // ptxas would turn a literal one into a shift -- or a funnel shift when the field straddles two words), compared there
 // against q << 20 without masking, shifted down and stored UNCONDITIONALLY at the running position, which advances
 // under the predicate; a rejected value is overwritten by the next candidate.  Blocks 1 and 2 cannot overflow the slot
-// (2 * 112 < 256); in block 3 a 16-candidate chunk runs unchecked while every lane of the warp still has room for 16
-// coefficients and otherwise also tests the position, the slot's spare 129th word absorbing the stores of lanes that
-// are already complete.
+// (2 * 112 < 256); block 3 also tests the position, the slot's spare 129th word absorbing the stores of lanes that are
+// already complete.  (Running the chunks of block 3 unchecked while every lane still has room for 16 coefficients saves
+// instructions but doubles the code of that block: 9.27 vs 9.19 ms -- this kernel feels its instruction footprint,
+// unrolling Keccak four-fold costs 7 %.  One checked parser for all three blocks is smaller still but slower, 9.37 ms.)
 // (Measured alternatives, 2^20 Encaps, fused kernel: rejection bit and position by multiply-high / multiply-add, value
 // by multiply-high, i.e. nothing on the alu pipe: 9.50 ms; value by shift: 9.40 ms; this form: 9.31 ms.  IMAD.HI is
 // the costliest neighbour a LOP3 stream can have: profiles/coissue_r01.jsonl.)
@@ -539,13 +540,12 @@ __device__ __forceinline__ void parse_chunk3(const uint32_t w[7], uint32_t &addr
         }
     }
 }
-template <int MODE_CHECK>  // 0: never checked (blocks 1, 2), 1: decide per chunk (block 3)
+template <bool CHECKED>  // false: blocks 1 and 2 (cannot fill the slot), true: block 3
 __device__ __forceinline__ void parse_block3(const Lane a[25], uint32_t &addr, uint32_t end_addr) {
 #pragma unroll
     for (int ch = 0; ch < 7; ch++) {  // 3 lanes = 6 words = 16 candidates
         const uint32_t w[7] = {a[3 * ch].lo, a[3 * ch].hi, a[3 * ch + 1].lo, a[3 * ch + 1].hi, a[3 * ch + 2].lo, a[3 * ch + 2].hi, 0u};
-        if (MODE_CHECK == 0 || __all_sync(kFullMask, addr + 32 <= end_addr)) parse_chunk3<false>(w, addr, end_addr);
-        else parse_chunk3<true>(w, addr, end_addr);
+        parse_chunk3<CHECKED>(w, addr, end_addr);
     }
 }
 // Returns true when the slot holds the complete polynomial.  No group limit applies: three blocks are 168 of the 278
@@ -568,8 +568,8 @@ __device__ __forceinline__ bool sample_ntt_three_blocks(const Lane rho[4], uint3
             continue;
         }
 #endif
-        if (blk < 2) parse_block3<0>(a, addr, end_addr);
-        else parse_block3<1>(a, addr, end_addr);
+        if (blk < 2) parse_block3<false>(a, addr, end_addr);
+        else parse_block3<true>(a, addr, end_addr);
     }
     return addr >= end_addr;
 }
@@ -655,6 +655,7 @@ __device__ __forceinline__ void matvec_finish_rows(const MatvecArgs &g, uint32_t
     };
     fetch_vec(warp);
 
+#pragma unroll 1
     for (int grp = warp; grp < 32; grp += K) {
         const int gg = s_gg[grp];
         if (gg < 0) {  // beyond the batch, or left to the clean-up pass
