@@ -621,63 +621,86 @@ constexpr size_t matvec_smem_bytes() {
 // (Tried and measured slower, 31.7 vs 32.4 M pairs/s: giving every warp the groups sampled by its own lanes, with
 // named barriers for the two groups that straddle a warp boundary at K = 3, so that no block-wide barrier separates
 // the phases.  The barrier wait it removes -- 9 % of the warp samples -- is not on the critical path: the alu pipe is.)
+// Lane constants of phase 2.  Loaded BEFORE the block barrier that ends phase 1, so that the barrier wait hides their
+// latency (they used to be the first long-scoreboard stall of every block).
+struct MatvecLaneConsts {
+    uint2 gam[4];
+    LaneTwiddles tw;
+    uint32_t pw;
+};
+template <int MODE>
+__device__ __forceinline__ void matvec_load_consts(MatvecLaneConsts &c, int lane) {
+#pragma unroll
+    for (int r = 0; r < 4; r++) c.gam[r] = lane_gamma(lane + 32 * r);
+    if (MODE != kModeKeyGen) load_lane_twiddles_inv<kFmaPipe>(c.tw, lane);
+    c.pw = nibble_weight(lane & 7);
+}
 template <class P, int MODE>
-__device__ __forceinline__ void matvec_finish_rows(const MatvecArgs &g, uint32_t *s_slots, const int *s_gg, int lane, int warp) {
+__device__ __forceinline__ void matvec_finish_rows(const MatvecArgs &g, uint32_t *s_slots, const int *s_gg, int lane, int warp,
+                                                   const MatvecLaneConsts &lc) {
     constexpr int K = P::K;
     uint8_t *warp_area = reinterpret_cast<uint8_t *>(s_slots) + matvec_slots_bytes<P>() + warp * kMatvecWarpBytes;
     uint16_t *scratch = reinterpret_cast<uint16_t *>(warp_area);
     uint8_t *stage = warp_area + 512;
-    uint2 gam[4];
-#pragma unroll
-    for (int r = 0; r < 4; r++) gam[r] = lane_gamma(lane + 32 * r);
-    LaneTwiddles tw;
-    if (MODE != kModeKeyGen) load_lane_twiddles_inv<kFmaPipe>(tw, lane);
-    const uint32_t pw = nibble_weight(lane & 7);
+    const uint2 *gam = lc.gam;
+    const LaneTwiddles &tw = lc.tw;
+    const uint32_t pw = lc.pw;
 
-    // The vector operand of the NEXT group is fetched into the same registers as soon as the products of the current
-    // group have consumed them: the loads have the whole inverse transform and epilogue to land (their latency was the
-    // largest exposed stall of phase 2 in the first ncu source view), and no register copies are needed.
+    // Every global operand of a group -- the vector, the noise codes (Encrypt) or e^ (KeyGen), the received ciphertext row
+    // (compare mode) -- is fetched one group ahead into a second register set and copied over at the top of the iteration:
+    // one wait per iteration, for loads that were issued a whole iteration earlier.  (Loading the codes and the
+    // ciphertext row at the top of the iteration that uses them left 32 % of the phase-2 warp time in long-scoreboard
+    // stalls: consumers of early loads also wait for later loads that share their scoreboard.)
     // (16-bit loads instead of 32-bit loads + mask/shift: the load/store pipe has slack, the alu pipe does not.)
-    uint32_t v[8 * K];
-    auto fetch_vec = [&](int grp) {
+    constexpr int kCmpWords = (8 * P::DU + 31) / 32;
+    uint32_t vn[8 * K], cwn[8], cmpn[kCmpWords], evn[4];
+    auto fetch_next = [&](int grp) {
         const int gg = grp < 32 ? s_gg[grp] : -1;
         if (gg >= 0) {
-            const uint16_t *vec = g.vec + g.vec_stride * (gg / K);
+            const int item = gg / K, row = gg - item * K;
+            const uint16_t *vec = g.vec + g.vec_stride * item;
 #pragma unroll
             for (int j = 0; j < K; j++)
 #pragma unroll
                 for (int r = 0; r < 4; r++) {
                     int t = lane + 32 * r;
-                    v[8 * j + 2 * r] = __ldg(vec + 256 * j + 2 * t);
-                    v[8 * j + 2 * r + 1] = __ldg(vec + 256 * j + 2 * t + 1);
+                    vn[8 * j + 2 * r] = __ldg(vec + 256 * j + 2 * t);
+                    vn[8 * j + 2 * r + 1] = __ldg(vec + 256 * j + 2 * t + 1);
                 }
+            if (MODE == kModeEncryptCompare) {
+                const uint32_t *cw = reinterpret_cast<const uint32_t *>(g.cmp + g.out_stride * item + (size_t)P::C1ROW * row);
+#pragma unroll
+                for (int i = 0; i < kCmpWords; i++) cmpn[i] = (lane + 32 * i < 8 * P::DU) ? __ldg(cw + lane + 32 * i) : 0u;
+            }
+            if (MODE != kModeKeyGen) {
+                const uint32_t *codes = g.addc + g.addc_stride * item + 32 * row + (lane >> 3);
+#pragma unroll
+                for (int r = 0; r < 8; r++) cwn[r] = __ldg(codes + 4 * r);
+            } else {
+                const uint32_t *ev = reinterpret_cast<const uint32_t *>(g.add16 + g.add16_stride * item + 256 * row);
+#pragma unroll
+                for (int r = 0; r < 4; r++) evn[r] = __ldg(ev + lane + 32 * r);
+            }
         }
     };
-    fetch_vec(warp);
+    fetch_next(warp);
 
 #pragma unroll 1
     for (int grp = warp; grp < 32; grp += K) {
         const int gg = s_gg[grp];
-        if (gg < 0) {  // beyond the batch, or left to the clean-up pass
-            fetch_vec(grp + K);
-            continue;
-        }
+        uint32_t v[8 * K], cw8[8], cmpw[kCmpWords], ev4[4];
+#pragma unroll
+        for (int i = 0; i < 8 * K; i++) v[i] = vn[i];
+#pragma unroll
+        for (int i = 0; i < 8; i++) cw8[i] = cwn[i];
+#pragma unroll
+        for (int i = 0; i < kCmpWords; i++) cmpw[i] = cmpn[i];
+#pragma unroll
+        for (int i = 0; i < 4; i++) ev4[i] = evn[i];
+        fetch_next(grp + K);
+        if (gg < 0) continue;  // beyond the batch, or left to the clean-up pass
         const int item = gg / K, row = gg - item * K;
         const uint32_t slot0 = (uint32_t)__cvta_generic_to_shared(s_slots + kSlotWords * (grp * K));
-        // compare mode: the received ciphertext row is needed only at the very end of the iteration -- load it now
-        constexpr int kCmpWords = (8 * P::DU + 31) / 32;
-        uint32_t cmpw[kCmpWords];
-        if (MODE == kModeEncryptCompare) {
-            const uint32_t *cw = reinterpret_cast<const uint32_t *>(g.cmp + g.out_stride * item + (size_t)P::C1ROW * row);
-#pragma unroll
-            for (int i = 0; i < kCmpWords; i++) cmpw[i] = (lane + 32 * i < 8 * P::DU) ? __ldg(cw + lane + 32 * i) : 0u;
-        }
-        uint32_t cw8[8];  // likewise the noise codes of the row (Encrypt)
-        if (MODE != kModeKeyGen) {
-            const uint32_t *codes = g.addc + g.addc_stride * item + 32 * row + (lane >> 3);
-#pragma unroll
-            for (int r = 0; r < 8; r++) cw8[r] = __ldg(codes + 4 * r);
-        }
         // ---- row . vector in the NTT domain (ml_kem.c:618 VectorMultiply), lazily accumulated.
         // Lane handles coefficient pairs t = lane + 32 r (conflict-free slot reads, coalesced vector reads).
         uint32_t acc[8];
@@ -696,15 +719,13 @@ __device__ __forceinline__ void matvec_finish_rows(const MatvecArgs &g, uint32_t
                 basemul_acc(acc[2 * r], acc[2 * r + 1], a0, a1, v[8 * j + 2 * r], v[8 * j + 2 * r + 1], gam[r]);
             }
         }
-        fetch_vec(grp + K);
         int nwords;
         if (MODE == kModeKeyGen) {
             // t^[row] = A[row] . s^ + e^[row]   (ml_kem.c:723-727), then ByteEncode12 (:736-742)
-            const uint32_t *ev = reinterpret_cast<const uint32_t *>(g.add16 + g.add16_stride * item + 256 * row);
 #pragma unroll
             for (int r = 0; r < 4; r++) {
                 int t = lane + 32 * r;
-                uint32_t e = __ldg(ev + t);
+                uint32_t e = ev4[r];
                 uint32_t c0 = csubq(canon32(acc[2 * r]) + (e & 0xFFFFu)), c1 = csubq(canon32(acc[2 * r + 1]) + (e >> 16));
                 uint32_t v = c0 | (c1 << 12);
                 stage[3 * t] = (uint8_t)v;
@@ -792,6 +813,8 @@ __global__ void __launch_bounds__(32 * P::K) k_sample_matvec(MatvecArgs g) {
 #endif
         s_inc[tid] = active && !complete;
     }
+    MatvecLaneConsts lc;
+    matvec_load_consts<MODE>(lc, lane);
     __syncthreads();
     {  // every warp resolves the groups it is going to finish itself (warp, warp + K, ...): no second block barrier
         const int grp = warp + K * lane;
@@ -808,9 +831,9 @@ __global__ void __launch_bounds__(32 * P::K) k_sample_matvec(MatvecArgs g) {
     }
 #ifdef MLKEM_B200_EXPERIMENT
     if (g.experiment & 1) return;
-    if (g.experiment & 4) matvec_finish_rows<P, MODE>(g, s_slots, s_gg, lane, warp);
+    if (g.experiment & 4) matvec_finish_rows<P, MODE>(g, s_slots, s_gg, lane, warp, lc);
 #endif
-    matvec_finish_rows<P, MODE>(g, s_slots, s_gg, lane, warp);
+    matvec_finish_rows<P, MODE>(g, s_slots, s_gg, lane, warp, lc);
 }
 
 // The general kernel: rows taken from g.defer_list (or all rows of the batch when it is nullptr), sampled with the
@@ -821,6 +844,8 @@ __global__ void __launch_bounds__(32 * P::K) k_sample_matvec_list(MatvecArgs g) 
     extern __shared__ __align__(16) uint32_t s_slots[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     int *s_gg = matvec_gg<P>(s_slots);
+    MatvecLaneConsts lc;
+    matvec_load_consts<MODE>(lc, lane);
     const int count = g.defer_list ? *g.defer_count : g.n * K;
     for (int base = blockIdx.x * 32; base < count; base += gridDim.x * 32) {
         {
@@ -837,7 +862,7 @@ __global__ void __launch_bounds__(32 * P::K) k_sample_matvec_list(MatvecArgs g) 
             sample_ntt_thread(rho, b32, b33, reinterpret_cast<uint16_t *>(s_slots + kSlotWords * tid), active, g.group_limit);
         }
         __syncthreads();
-        matvec_finish_rows<P, MODE>(g, s_slots, s_gg, lane, warp);
+        matvec_finish_rows<P, MODE>(g, s_slots, s_gg, lane, warp, lc);
         __syncthreads();  // the slots are reused by the next batch of rows
     }
 }
