@@ -618,9 +618,10 @@ constexpr size_t matvec_smem_bytes() {
 
 // Phase 2 of the matvec kernels: the warps of the block take the 32 groups round-robin and finish the rows whose
 // K sampled entries sit in the slots grp*K .. grp*K+K-1.  s_gg[grp] = item * K + row, or -1 to skip the group.
-// (Tried and measured slower, 31.7 vs 32.4 M pairs/s: giving every warp the groups sampled by its own lanes, with
-// named barriers for the two groups that straddle a warp boundary at K = 3, so that no block-wide barrier separates
-// the phases.  The barrier wait it removes -- 9 % of the warp samples -- is not on the critical path: the alu pipe is.)
+// (Tried twice and measured slower both times, 31.7 vs 32.4 M pairs/s early on and 9.09 vs 9.03 ms per 2^20 Encaps with
+// the final phase 2: giving every warp the groups sampled by its own lanes, with named barriers for the two groups that
+// straddle a warp boundary at K = 3, so that no block-wide barrier separates the phases.  The barrier wait it removes
+// -- 9 % of the warp samples -- is not on the critical path.)
 // Lane constants of phase 2.  Loaded BEFORE the block barrier that ends phase 1, so that the barrier wait hides their
 // latency (they used to be the first long-scoreboard stall of every block).
 struct MatvecLaneConsts {

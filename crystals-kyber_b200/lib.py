@@ -72,11 +72,14 @@ COMPAT_SYMBOLS = ["ml_errno", "init", "KEM_KeyGen", "KEM_Encaps", "KEM_Decaps", 
                   "KeyGen_internal", "Encaps_internal", "Decaps_internal", "h2b", "b2h", "sha3_b", "sha3_h", "sha3_s"]
 
 
-def load(path: str = LIB_PATH):
-    """Load libmlkem_b200.so.  No fallback: a missing library is an error."""
+def load(path: str = None):
+    """Load libmlkem_b200.so.  No fallback: a missing library is an error.  MLKEM_B200_LIB names another build of the
+    same library (the A/B and experiment builds of tools/)."""
     global _lib
     if _lib is not None:
         return _lib
+    if path is None:
+        path = os.path.abspath(os.environ["MLKEM_B200_LIB"]) if os.environ.get("MLKEM_B200_LIB") else LIB_PATH
     if not os.path.exists(path):
         raise MlKemB200Error(
             f"{path} not found: build it with `make lib` (nvcc, sm_100a). There is no CPU fallback.")
