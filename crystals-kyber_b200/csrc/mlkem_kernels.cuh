@@ -636,9 +636,47 @@ __device__ __forceinline__ void matvec_load_consts(MatvecLaneConsts &c, int lane
     if (MODE != kModeKeyGen) load_lane_twiddles_inv<kFmaPipe>(c.tw, lane);
     c.pw = nibble_weight(lane & 7);
 }
+// The global operands of one group (row): the vector, the noise codes (Encrypt) or e^ (KeyGen), the received ciphertext
+// row (compare mode).  Fetched one group ahead (see matvec_finish_rows); the first group's before the block barrier.
+template <class P>
+struct MatvecOperands {
+    static constexpr int kCmpWords = (8 * P::DU + 31) / 32;
+    uint32_t v[8 * P::K], cw[8], cmp[kCmpWords], ev[4];
+};
+template <class P, int MODE>
+__device__ __forceinline__ void matvec_prefetch(MatvecOperands<P> &o, const MatvecArgs &g, int gg, int lane) {
+    constexpr int K = P::K;
+    if (gg < 0) return;
+    const int item = gg / K, row = gg - item * K;
+    const uint16_t *vec = g.vec + g.vec_stride * item;
+    // (16-bit loads instead of 32-bit loads + mask/shift: the load/store pipe has slack, the alu pipe does not.)
+#pragma unroll
+    for (int j = 0; j < K; j++)
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            int t = lane + 32 * r;
+            o.v[8 * j + 2 * r] = __ldg(vec + 256 * j + 2 * t);
+            o.v[8 * j + 2 * r + 1] = __ldg(vec + 256 * j + 2 * t + 1);
+        }
+    if (MODE == kModeEncryptCompare) {
+        const uint32_t *cw = reinterpret_cast<const uint32_t *>(g.cmp + g.out_stride * item + (size_t)P::C1ROW * row);
+#pragma unroll
+        for (int i = 0; i < MatvecOperands<P>::kCmpWords; i++) o.cmp[i] = (lane + 32 * i < 8 * P::DU) ? __ldg(cw + lane + 32 * i) : 0u;
+    }
+    if (MODE != kModeKeyGen) {
+        const uint32_t *codes = g.addc + g.addc_stride * item + 32 * row + (lane >> 3);
+#pragma unroll
+        for (int r = 0; r < 8; r++) o.cw[r] = __ldg(codes + 4 * r);
+    } else {
+        const uint32_t *ev = reinterpret_cast<const uint32_t *>(g.add16 + g.add16_stride * item + 256 * row);
+#pragma unroll
+        for (int r = 0; r < 4; r++) o.ev[r] = __ldg(ev + lane + 32 * r);
+    }
+}
+
 template <class P, int MODE>
 __device__ __forceinline__ void matvec_finish_rows(const MatvecArgs &g, uint32_t *s_slots, const int *s_gg, int lane, int warp,
-                                                   const MatvecLaneConsts &lc) {
+                                                   const MatvecLaneConsts &lc, MatvecOperands<P> &nx) {
     constexpr int K = P::K;
     uint8_t *warp_area = reinterpret_cast<uint8_t *>(s_slots) + matvec_slots_bytes<P>() + warp * kMatvecWarpBytes;
     uint16_t *scratch = reinterpret_cast<uint16_t *>(warp_area);
@@ -647,58 +685,25 @@ __device__ __forceinline__ void matvec_finish_rows(const MatvecArgs &g, uint32_t
     const LaneTwiddles &tw = lc.tw;
     const uint32_t pw = lc.pw;
 
-    // Every global operand of a group -- the vector, the noise codes (Encrypt) or e^ (KeyGen), the received ciphertext row
-    // (compare mode) -- is fetched one group ahead into a second register set and copied over at the top of the iteration:
-    // one wait per iteration, for loads that were issued a whole iteration earlier.  (Loading the codes and the
-    // ciphertext row at the top of the iteration that uses them left 32 % of the phase-2 warp time in long-scoreboard
-    // stalls: consumers of early loads also wait for later loads that share their scoreboard.)
-    // (16-bit loads instead of 32-bit loads + mask/shift: the load/store pipe has slack, the alu pipe does not.)
-    constexpr int kCmpWords = (8 * P::DU + 31) / 32;
-    uint32_t vn[8 * K], cwn[8], cmpn[kCmpWords], evn[4];
-    auto fetch_next = [&](int grp) {
-        const int gg = grp < 32 ? s_gg[grp] : -1;
-        if (gg >= 0) {
-            const int item = gg / K, row = gg - item * K;
-            const uint16_t *vec = g.vec + g.vec_stride * item;
-#pragma unroll
-            for (int j = 0; j < K; j++)
-#pragma unroll
-                for (int r = 0; r < 4; r++) {
-                    int t = lane + 32 * r;
-                    vn[8 * j + 2 * r] = __ldg(vec + 256 * j + 2 * t);
-                    vn[8 * j + 2 * r + 1] = __ldg(vec + 256 * j + 2 * t + 1);
-                }
-            if (MODE == kModeEncryptCompare) {
-                const uint32_t *cw = reinterpret_cast<const uint32_t *>(g.cmp + g.out_stride * item + (size_t)P::C1ROW * row);
-#pragma unroll
-                for (int i = 0; i < kCmpWords; i++) cmpn[i] = (lane + 32 * i < 8 * P::DU) ? __ldg(cw + lane + 32 * i) : 0u;
-            }
-            if (MODE != kModeKeyGen) {
-                const uint32_t *codes = g.addc + g.addc_stride * item + 32 * row + (lane >> 3);
-#pragma unroll
-                for (int r = 0; r < 8; r++) cwn[r] = __ldg(codes + 4 * r);
-            } else {
-                const uint32_t *ev = reinterpret_cast<const uint32_t *>(g.add16 + g.add16_stride * item + 256 * row);
-#pragma unroll
-                for (int r = 0; r < 4; r++) evn[r] = __ldg(ev + lane + 32 * r);
-            }
-        }
-    };
-    fetch_next(warp);
-
+    // Every global operand of a group is fetched one group ahead into a second register set (nx; the caller has already
+    // issued the loads of this warp's first group) and copied over at the top of the iteration: one wait per iteration,
+    // for loads that were issued a whole iteration earlier.  (Loading the codes and the ciphertext row at the top of the
+    // iteration that uses them left 32 % of the phase-2 warp time in long-scoreboard stalls: consumers of early loads
+    // also wait for later loads that share their scoreboard.)
+    constexpr int kCmpWords = MatvecOperands<P>::kCmpWords;
 #pragma unroll 1
     for (int grp = warp; grp < 32; grp += K) {
         const int gg = s_gg[grp];
         uint32_t v[8 * K], cw8[8], cmpw[kCmpWords], ev4[4];
 #pragma unroll
-        for (int i = 0; i < 8 * K; i++) v[i] = vn[i];
+        for (int i = 0; i < 8 * K; i++) v[i] = nx.v[i];
 #pragma unroll
-        for (int i = 0; i < 8; i++) cw8[i] = cwn[i];
+        for (int i = 0; i < 8; i++) cw8[i] = nx.cw[i];
 #pragma unroll
-        for (int i = 0; i < kCmpWords; i++) cmpw[i] = cmpn[i];
+        for (int i = 0; i < kCmpWords; i++) cmpw[i] = nx.cmp[i];
 #pragma unroll
-        for (int i = 0; i < 4; i++) ev4[i] = evn[i];
-        fetch_next(grp + K);
+        for (int i = 0; i < 4; i++) ev4[i] = nx.ev[i];
+        matvec_prefetch<P, MODE>(nx, g, grp + K < 32 ? s_gg[grp + K] : -1, lane);
         if (gg < 0) continue;  // beyond the batch, or left to the clean-up pass
         const int item = gg / K, row = gg - item * K;
         const uint32_t slot0 = (uint32_t)__cvta_generic_to_shared(s_slots + kSlotWords * (grp * K));
@@ -816,6 +821,13 @@ __global__ void __launch_bounds__(32 * P::K) k_sample_matvec(MatvecArgs g) {
     }
     MatvecLaneConsts lc;
     matvec_load_consts<MODE>(lc, lane);
+    // the operands of this warp's first group: their addresses do not depend on what the other warps sampled, so the loads
+    // go out before the barrier (if the row turns out to be deferred they were for nothing)
+    MatvecOperands<P> nx;
+    {
+        const int gg = blockIdx.x * 32 + warp;
+        matvec_prefetch<P, MODE>(nx, g, gg / K < g.n ? gg : -1, lane);
+    }
     __syncthreads();
     {  // every warp resolves the groups it is going to finish itself (warp, warp + K, ...): no second block barrier
         const int grp = warp + K * lane;
@@ -832,9 +844,12 @@ __global__ void __launch_bounds__(32 * P::K) k_sample_matvec(MatvecArgs g) {
     }
 #ifdef MLKEM_B200_EXPERIMENT
     if (g.experiment & 1) return;
-    if (g.experiment & 4) matvec_finish_rows<P, MODE>(g, s_slots, s_gg, lane, warp, lc);
+    if (g.experiment & 4) {
+        matvec_finish_rows<P, MODE>(g, s_slots, s_gg, lane, warp, lc, nx);
+        matvec_prefetch<P, MODE>(nx, g, s_gg[warp], lane);
+    }
 #endif
-    matvec_finish_rows<P, MODE>(g, s_slots, s_gg, lane, warp, lc);
+    matvec_finish_rows<P, MODE>(g, s_slots, s_gg, lane, warp, lc, nx);
 }
 
 // The general kernel: rows taken from g.defer_list (or all rows of the batch when it is nullptr), sampled with the
@@ -863,7 +878,9 @@ __global__ void __launch_bounds__(32 * P::K) k_sample_matvec_list(MatvecArgs g) 
             sample_ntt_thread(rho, b32, b33, reinterpret_cast<uint16_t *>(s_slots + kSlotWords * tid), active, g.group_limit);
         }
         __syncthreads();
-        matvec_finish_rows<P, MODE>(g, s_slots, s_gg, lane, warp, lc);
+        MatvecOperands<P> nx;
+        matvec_prefetch<P, MODE>(nx, g, s_gg[warp], lane);
+        matvec_finish_rows<P, MODE>(g, s_slots, s_gg, lane, warp, lc, nx);
         __syncthreads();  // the slots are reused by the next batch of rows
     }
 }
