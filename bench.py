@@ -343,9 +343,9 @@ def main():
         "algorithmic_ops_per_item": ops["matvec_encrypt"], "items_per_launch": items_per_launch,
         "avg_launch_ms": mv_ms / max(mv_launches, 1), "share_of_step_kernel_time": mv_ms / total_kernel_ms if total_kernel_ms else None,
         # dram__bytes_read.sum + dram__bytes_write.sum from the committed ncu --set full capture
-        # (profiles/ncu_kem_kernels_r01_final_summary.csv, one 65 536-item launch: fused kernel 133.7 + 38.8 MB, clean-up pass
-        # 8.5 MB = 2 762 B/item), scaled to this run's launch
-        "traffic": 2762.0 * items_per_launch, "traffic_bytes_per_item": 2762, "algorithmic_bytes_per_item": 32 + 1536 + 384 + 960,
+        # (profiles/ncu_kem_kernels_r01_final_summary.csv, one 65 536-item launch: fused kernel 133.7 + 40.6 MB, clean-up pass
+        # 8.5 MB = 2 790 B/item), scaled to this run's launch
+        "traffic": 2790.0 * items_per_launch, "traffic_bytes_per_item": 2790, "algorithmic_bytes_per_item": 32 + 1536 + 384 + 960,
         "whole_step": {"algorithmic_ops_per_pair": ops["encaps"] + ops["decaps"],
                        "achieved": (ops["encaps"] + ops["decaps"]) * value / world / 1e12, "frac": (ops["encaps"] + ops["decaps"]) * value / world / peak},
         "peaks_tera_ops": {k: v / 1e12 for k, v in peaks.items()},
