@@ -6,9 +6,10 @@
 //   * every polynomial operation (NTT, inverse NTT, multiply-accumulate, compress, pack) is run by ONE
 //     WARP per polynomial, 8 coefficients per lane.
 //   * the matrix expansion is fused with its consumer: k_sample_matvec samples the k entries of one matrix
-//     row with k threads straight into shared memory and the owning warp immediately multiplies them with
-//     the vector, accumulates, (inverse-)transforms, adds the noise, compresses and packs -- the matrix
-//     never exists in HBM.
+//     row with k threads straight into shared memory (exactly three XOF blocks per sponge, straight-line code) and
+//     the warps of the block then multiply them with the vector, accumulate, (inverse-)transform, add the noise,
+//     compress and pack -- the matrix never exists in HBM.  The 2.7 % of rows that own a sponge needing a fourth
+//     block go to a list that k_sample_matvec_list works off with the general sampler.
 //
 // All byte buffers are dense and item-major (item i of an array with per-item size S starts at i*S);
 // every per-item size on this path is a multiple of 16 bytes, so with 16-byte aligned bases every item,
