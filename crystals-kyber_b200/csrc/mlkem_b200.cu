@@ -129,7 +129,7 @@ void build_tables(TwiddleTables &t, uint2 rc[24]) {
 // ------------------------------------------------------------------------------------------------
 // Per-device context
 // ------------------------------------------------------------------------------------------------
-constexpr int kSlots = 4;   // streams / workspaces per device (host-memory calls use the first two)
+constexpr int kSlots = 4;   // streams / workspaces per device (host-memory calls use the first kHostSlots)
 constexpr int kHostSlots = 3;  // measured: 3 slots keep the H2D copy engine at ~50.7 GB/s (2 slots: 48 GB/s)
 constexpr int kMaxDevices = 64;
 
@@ -386,7 +386,7 @@ int enqueue_decaps(cudaStream_t st, Arena &ws, int n, const uint8_t *dk, const u
 }
 
 // ------------------------------------------------------------------------------------------------
-// Generic batched driver: handles host / device memory, chunking and the two-slot pipeline.
+// Generic batched driver: handles host / device memory, chunking and the multi-slot pipelines.
 // ------------------------------------------------------------------------------------------------
 struct Buf {
     const void *in;   // non-null for inputs
@@ -476,7 +476,7 @@ int drive(const mlkem_b200_opts *o, size_t n, size_t ws_per_item, std::vector<Bu
         return MLKEM_B200_OK;
     }
 
-    // host memory: stage each chunk through device buffers, alternate between two streams so that the
+    // host memory: stage each chunk through device buffers, rotating over the staging slots / streams so that the
     // copies of one chunk overlap the kernels of the other
     size_t io_per_item = 0;
     for (auto &b : bufs) io_per_item += (b.item_bytes + 15) & ~size_t(15);

@@ -24,7 +24,7 @@
  * Memory spaces (mlkem_b200_opts.mem)
  *   MLKEM_B200_MEM_HOST    pointers are host memory (pinned memory from mlkem_b200_host_alloc gives the
  *                          full PCIe rate).  The call stages chunks through device memory with copies and
- *                          kernels overlapped on two streams and returns when the results are in place.
+ *                          kernels overlapped on several streams and returns when the results are in place.
  *   MLKEM_B200_MEM_DEVICE  pointers are device memory on opts.device, 16-byte aligned.  The call enqueues
  *                          its kernels on opts.stream (NULL = the CUDA default stream) and returns
  *                          without synchronising; the caller orders its own work through that stream.
