@@ -149,3 +149,14 @@ def test_arithmetic_lemmas():
     for j in range(8):
         top = (w << np.uint64(28 - 4 * j)) & u(0xFFFFFFFF)
         assert (mulhi(top, 16) == (w >> np.uint64(4 * j)) & u(15)).all()
+
+
+def test_algorithmic_work_model_matches_the_scope_table():
+    """the per-operation work the roofline is computed from (bench.py uses workload.op_counts)."""
+    from crystals_kyber_b200 import workload as wl
+
+    kc = wl.keccak_calls(3, 2, 10, 4)
+    assert (kc["keygen"], kc["encaps"], kc["decaps"]) == (43, 44, 42)
+    ops = wl.op_counts(3, 2, 10, 4)
+    assert (ops["keygen"], ops["encaps"], ops["decaps"]) == (232_224, 250_624, 267_200)
+    assert ops["encaps"] + ops["decaps"] == 517_824 and ops["matvec_encrypt"] == 151_968
