@@ -10,7 +10,12 @@ index (crystals-kyber_b200/workload.py), keys are generated on the device before
 
   value     encaps+decaps pairs per second, whole job, inputs and outputs resident in HBM
   e2e       the same step through the C ABI with HOST buffers (pinned): H2D of ek, m, dk, c and D2H of
-            c, K, K' inside the timed region
+            c, K, K' inside the timed region; e2e.copy_ceiling = the same buffers through the same staging
+            pipeline with no kernels (mlkem_b200_copy_probe), measured in the same run on all ranks at once
+  e2e_keyed the same step with the keys resident on the GPU (mlkem_b200_keys_*): only m, c and K cross PCIe
+  cross_n_digest
+            a FIXED global range of 2^20 items split over the ranks; checksum of checksums of c, K, K'
+            compared with the oracle-derived fixture tests/golden/config4_digest.json at every rank count
   roofline  the dominant kernel (fused matrix expansion + matrix-vector product) against the INT32
             alu-pipe issue rate measured live on the same GPU (mlkem_b200_int32_peak)
   cpu_baseline / --impl reference
@@ -44,9 +49,10 @@ def emit(obj):
 # ----------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the reference's own CPU code on the host cores
 # ----------------------------------------------------------------------------------------------------
-def reference_pairs_per_s(threads: int, pairs_per_thread: int, steps: int, warmup: int):
+def reference_pairs_per_s(threads: int, pairs_per_thread: int, steps: int, warmup: int, detail: bool = False):
     """Times oracle/_ref (the unmodified reference behind ref_shim.c) on `threads` host threads.
-    Falls back to the oracle port when the compiled reference did not travel.  Returns a dict."""
+    Falls back to the oracle port when the compiled reference did not travel.  Returns a dict.
+    detail: also one thread alone (-O2), and the per-call times of NTT / InverseNTT / MultiplyNTTs."""
     import numpy as np
 
     from oracle.oracle import REF_G_SO, REF_SO, Oracle, Reference, build
@@ -60,8 +66,9 @@ def reference_pairs_per_s(threads: int, pairs_per_thread: int, steps: int, warmu
     out = {"cores": threads, "sample": f"{n} ML-KEM-768 encaps+decaps pairs per step on {threads} threads"}
     if os.path.exists(REF_SO):
         ref = Reference(REF_SO)
-        for _ in range(warmup):
+        for _ in range(warmup):  # a warm-up step is one pair per thread (28 ms per operation: nothing to warm but the caches)
             ref.time_pairs(PS, ek[:threads], dk[:threads], m[:threads], threads)
+        out["warmup_steps_run"] = warmup
         ts = [ref.time_pairs(PS, ek, dk, m, threads)[0] for _ in range(steps)]
         t = sum(ts) / len(ts)
         _, c, K = ref.time_pairs(PS, ek[:threads], dk[:threads], m[:threads], threads)
@@ -73,6 +80,14 @@ def reference_pairs_per_s(threads: int, pairs_per_thread: int, steps: int, warmu
             rg = Reference(REF_G_SO)
             tg, _, _ = rg.time_pairs(PS, ek[:2], dk[:2], m[:2], 1)
             out["makefile_flags_1thread_pairs_per_s"] = 2 / tg
+        if detail:
+            t1, _, _ = ref.time_pairs(PS, ek[:4], dk[:4], m[:4], 1)
+            out["O2_1thread_pairs_per_s"] = 4 / t1
+            f = rng.integers(0, 3329, 256, dtype=np.uint16)
+            g = rng.integers(0, 3329, 256, dtype=np.uint16)
+            tn, ti, tm = ref.time_ring(f, g, 2000)  # ml_kem.c:287, :336, :415 -- 2 000 calls each, one thread
+            out["ring_1thread"] = {"ntt_polys_per_s": 1 / tn, "intt_polys_per_s": 1 / ti, "multiply_ntts_polys_per_s": 1 / tm,
+                                   "sample": "2000 calls each of NTT / InverseNTT / MultiplyNTTs of the reference (-O2), one thread"}
     else:
         import ctypes
 
@@ -91,7 +106,8 @@ def run_reference_arm(args):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    r = reference_pairs_per_s(threads, 8, max(1, args.steps), max(0, min(args.warmup, 1)))
+    # 32 pairs per thread and step: about 2 s per step at 28 ms per operation, whatever the core count
+    r = reference_pairs_per_s(threads, 32, max(1, args.steps), max(0, args.warmup))
     emit({
         "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -101,7 +117,8 @@ def run_reference_arm(args):
                    "sample": r["sample"] + " (a bounded sample of that workload; the reference's Decaps_internal always re-encrypts and "
                                            "hashes, so its time does not depend on the tampered fraction)"},
         "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"],
-                         "build": r["build"], "makefile_flags_1thread_pairs_per_s": r.get("makefile_flags_1thread_pairs_per_s")},
+                         "build": r["build"], "makefile_flags_1thread_pairs_per_s": r.get("makefile_flags_1thread_pairs_per_s"),
+                         "warmup_steps_run": r.get("warmup_steps_run", 0)},
         "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     })
@@ -290,10 +307,32 @@ def main():
     # ---- e2e: host buffers through the C ABI (H2D + kernels + D2H per step)
     ne = 1 << (args.e2e_log2_items if args.e2e_log2_items is not None else args.log2_items)
     ne = min(ne, n)
+
     def pinned_copy(t):
         h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
         h.copy_(t)
         return h
+
+    def timed_host(step_fn):
+        """`steps` synchronous host-memory steps, all ranks at once, max over ranks; one untimed step first."""
+        step_fn()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            step_fn()  # synchronous: returns when the results are in host memory
+        barrier()
+        return max_over_ranks(time.perf_counter() - t0)
+
+    def copy_probe(ins, outs):
+        """mlkem_b200_copy_probe over the given pinned tensors: the copies of a real call, no kernels."""
+        ni, no = len(ins), len(outs)
+        ip = (C.c_void_p * ni)(*[t.data_ptr() for t in ins])
+        ib = (C.c_size_t * ni)(*[t.shape[1] * t.element_size() for t in ins])
+        op = (C.c_void_p * no)(*[t.data_ptr() for t in outs])
+        ob = (C.c_size_t * no)(*[t.shape[1] * t.element_size() for t in outs])
+        rc = lib.mlkem_b200_copy_probe(ins[0].shape[0], ni, ip, ib, no, op, ob, C.byref(o_host))
+        if rc:
+            raise RuntimeError(lib.mlkem_b200_last_error().decode())
 
     hek, hm, hdk, hct = (pinned_copy(t[:ne]) for t in (ek, m, dk, c_t))
     hc = torch.empty((ne, sz["c"]), dtype=torch.uint8, pin_memory=True)
@@ -307,19 +346,88 @@ def main():
         if rc:
             raise RuntimeError(lib.mlkem_b200_last_error().decode())
 
-    step_host()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        step_host()  # synchronous: returns when the results are in host memory
-    barrier()
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_s = timed_host(step_host)
     assert bool((hK == K0[:ne].cpu()).all()) and bool((hKd == Kd[:ne].cpu()).all()), "host-buffer path disagrees with device path"
     e2e_value = world * ne * steps / e2e_s
-    os.sched_setaffinity(0, all_cpus)  # the CPU baseline below uses every host core again
     h2d = ne * (sz["ek"] + 32 + sz["dk"] + sz["c"])
     d2h = ne * (sz["c"] + 32 + 32)
+    # the copy-only ceiling of exactly these calls, on this box, now, every rank at once
+    hscratch = [torch.empty_like(t) for t in (hc, hK, hKd)]
+    ceil_s = timed_host(lambda: (copy_probe([hek, hm], hscratch[:2]), copy_probe([hdk, hct], hscratch[2:])))
+    e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "items_per_gpu": ne,
+           "ms_per_step": 1e3 * e2e_s / steps, "h2d_GBps_per_gpu": h2d * steps / e2e_s / 1e9,
+           "path": "mlkem_b200_encaps_batch + mlkem_b200_decaps_batch with MLKEM_B200_MEM_HOST (pinned buffers), distinct keys per item",
+           "copy_ceiling": {"value": world * ne * steps / ceil_s, "unit": UNIT, "ms_per_step": 1e3 * ceil_s / steps,
+                            "h2d_GBps_per_gpu": h2d * steps / ceil_s / 1e9,
+                            "how": "mlkem_b200_copy_probe: the same buffers through the same chunks / staging slots / streams, no kernels; "
+                                   "all ranks concurrently, same run"},
+           "frac_of_copy_ceiling": ceil_s / e2e_s, "cpus_of_gpu_numa_node": numa_cpus}
+    del hdk  # (10 GB of pinned memory per rank; the buffers below are reused for the keyed legs)
+
+    # ---- e2e_keyed: the keys live on the GPU (SURVEY 8(d) config 4 allows 2^16 distinct keys reused cyclically); per step only
+    # m (32 B) in and c, K (1120 B) out for Encaps, c (1088 B) in and K' (32 B) out for Decaps cross PCIe.  The table is built
+    # from the 64-byte seeds once (set-up, like the pinned copies above).
+    nk = min(1 << 16, ne)
+    d16, z16, _ = wl.derive_inputs(lambda msg, ln: kem.hash_batch(1, msg, ln), begin, begin + nk, dev)
+    table = kem.keys_load(PS, seeds=(d16, z16))
+    hck, hKk, hKdk = hscratch  # outputs of the keyed calls
+
+    def step_keyed_encaps():
+        if lib.mlkem_b200_encaps_keyed_batch(table.handle, ne, None, P(hm), P(hck), P(hKk), C.byref(o_host)):
+            raise RuntimeError(lib.mlkem_b200_last_error().decode())
+
+    step_keyed_encaps()
+    hctk = hct  # the ciphertexts Decaps receives: those of the keyed Encaps, 10 % tampered
+    hctk.copy_(hck)
+    wl.tamper_inplace(hctk.numpy(), begin)
+
+    def step_keyed():
+        step_keyed_encaps()
+        if lib.mlkem_b200_decaps_keyed_batch(table.handle, ne, None, P(hctk), P(hKdk), C.byref(o_host)):
+            raise RuntimeError(lib.mlkem_b200_last_error().decode())
+
+    keyed_s = timed_host(step_keyed)
+    # parity of the keyed path: identical to the unkeyed device-memory calls with the keys gathered explicitly (a 2^17-item slice,
+    # two trips around the table), and the round trip holds on everything
+    nv = min(ne, 1 << 17)
+    ek16, dk16 = kem.keygen(PS, d16, z16)
+    gidx = torch.arange(nv, device=dev) % nk
+    cv, Kv = kem.encaps(PS, ek16[gidx], m[:nv])
+    Kdv = kem.decaps(PS, dk16[gidx], hctk[:nv].to(dev))
+    torch.cuda.synchronize()
+    assert bool((hck[:nv] == cv.cpu()).all()) and bool((hKk[:nv] == Kv.cpu()).all()) and bool((hKdk[:nv] == Kdv.cpu()).all()), \
+        "keyed calls disagree with the unkeyed calls"
+    same_k = (hKdk == hKk).all(dim=1)
+    tam_k = torch.zeros(ne, dtype=torch.bool)
+    tam_k[tampered[tampered < ne].cpu()] = True
+    assert bool(same_k[~tam_k].all()) and not bool(same_k[tam_k].any()), "keyed KEM round trip failed"
+    ceil_k_s = timed_host(lambda: (copy_probe([hm], [hc, hK]), copy_probe([hctk], [hKd])))
+    h2d_k, d2h_k = ne * (32 + sz["c"]), ne * (sz["c"] + 32 + 32)
+    e2e_keyed = {"value": world * ne * steps / keyed_s, "unit": UNIT, "h2d_bytes_per_step": h2d_k, "d2h_bytes_per_step": d2h_k,
+                 "items_per_gpu": ne, "distinct_keys_per_gpu": nk, "ms_per_step": 1e3 * keyed_s / steps,
+                 "path": "mlkem_b200_encaps_keyed_batch + mlkem_b200_decaps_keyed_batch with MLKEM_B200_MEM_HOST; key table built once by "
+                         "mlkem_b200_keys_from_seeds, key of item i = i mod 2^16; outputs checked against the unkeyed calls",
+                 "copy_ceiling": {"value": world * ne * steps / ceil_k_s, "unit": UNIT, "ms_per_step": 1e3 * ceil_k_s / steps},
+                 "frac_of_copy_ceiling": ceil_k_s / keyed_s, "vs_unkeyed_e2e": e2e_s / keyed_s}
+    # decaps keyed only (a server), encaps with one 1184-byte ek per item (clients with distinct keys)
+
+    def step_keyed_decaps_only():
+        rc = lib.mlkem_b200_encaps_batch(PS, ne, P(hek), P(hm), P(hc), P(hK), C.byref(o_host))
+        rc |= lib.mlkem_b200_decaps_keyed_batch(table.handle, ne, None, P(hctk), P(hKdk), C.byref(o_host))
+        if rc:
+            raise RuntimeError(lib.mlkem_b200_last_error().decode())
+
+    kd_s = timed_host(step_keyed_decaps_only)
+    e2e_keyed["decaps_keyed_only"] = {"value": world * ne * steps / kd_s, "unit": UNIT, "h2d_bytes_per_step": ne * (sz["ek"] + 32 + sz["c"]),
+                                      "d2h_bytes_per_step": d2h_k, "ms_per_step": 1e3 * kd_s / steps, "vs_unkeyed_e2e": e2e_s / kd_s}
+    table.free()
+    del hek, hck, hct, hctk, hc, hscratch, ek16, dk16, cv, Kv, Kdv
+    os.sched_setaffinity(0, all_cpus)  # the CPU baseline below uses every host core again
     sampler.stop()
+
+    # ---- cross-N byte identity: a FIXED global range of 2^20 items, contiguous shards over the ranks; per output a
+    # checksum of checksums over 2^14-item blocks, gathered on rank 0 and compared with the oracle-derived fixture
+    digest = cross_n_digest(kem, wl, torch, dist, dev, rank, world)
 
     # ---- roofline of the dominant kernel, INT32 alu pipe
     peaks = kem.int32_peak()
@@ -359,9 +467,7 @@ def main():
                                "(BASELINE configs[3]); 1 op = 1 encaps + 1 decaps",
                    "items_per_gpu": n, "distinct_keys": n, "tamper": "i % 10 == 3", "sharding": f"contiguous index shards x{world}, no collective",
                    "cache": "working set 20 GB per GPU >> 126 MB L2, no flush needed"},
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "items_per_gpu": ne,
-                "ms_per_step": 1e3 * e2e_s / steps, "path": "mlkem_b200_encaps_batch + mlkem_b200_decaps_batch with MLKEM_B200_MEM_HOST (pinned buffers)",
-                "cpus_of_gpu_numa_node": numa_cpus},
+        "e2e": e2e, "e2e_keyed": e2e_keyed, "cross_n_digest": digest,
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
         "kernel_ms_per_step": {k: v["ms"] / steps for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])},
         "serialized_ms_per_step": serial_ms / steps,
@@ -371,14 +477,52 @@ def main():
     if rank == 0 and not args.no_extras:
         line["extra"] = extras(kem, torch, dev, peaks)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        r = reference_pairs_per_s(os.cpu_count() or 1, 16, 1, 0)
-        line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "build") if k in r}
-        if "makefile_flags_1thread_pairs_per_s" in r:
-            line["cpu_baseline"]["makefile_flags_1thread_pairs_per_s"] = r["makefile_flags_1thread_pairs_per_s"]
+        r = reference_pairs_per_s(os.cpu_count() or 1, 32, 1, 1, detail=True)
+        line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "build", "makefile_flags_1thread_pairs_per_s",
+                                                  "O2_1thread_pairs_per_s", "ring_1thread") if k in r}
     if rank == 0:
         emit(line)
     if dist is not None:
         dist.destroy_process_group()
+
+
+def cross_n_digest(kem, wl, torch, dist, dev, rank, world):
+    """KeyGen -> Encaps -> Decaps(10 % tampered) over global items [0, 2^L) of the workload, rank r taking the contiguous shard
+    [r 2^L / W, (r+1) 2^L / W).  Returns {c, K, Kd: sha256 of the per-block sha256s} on rank 0, checked against
+    tests/golden/config4_digest.json (made by the ORACLE on the CPU: tests/golden/make_digest.py)."""
+    import hashlib
+
+    import crystals_kyber_b200 as ck
+
+    fixture = json.load(open(os.path.join(ROOT, "tests", "golden", "config4_digest.json")))
+    L, B = fixture["log2_items"], fixture["log2_block"]
+    total, blk = 1 << L, 1 << B
+    lo, hi = ck.shard_range(total, rank, world)
+    assert lo % blk == 0 and hi % blk == 0, "shard boundaries must be block boundaries"
+    d, z, m = wl.derive_inputs(lambda msg, ln: kem.hash_batch(1, msg, ln), lo, hi, dev)
+    ek, dk = kem.keygen(PS, d, z)
+    c, K = kem.encaps(PS, ek, m)
+    ct = c.clone()
+    wl.tamper_inplace(ct, lo)
+    Kd = kem.decaps(PS, dk, ct)
+    torch.cuda.synchronize()
+    mine = {}
+    for name, t in (("c", c), ("K", K), ("Kd", Kd)):
+        h = t.cpu().numpy()
+        mine[name] = b"".join(hashlib.sha256(h[b : b + blk].tobytes()).digest() for b in range(0, hi - lo, blk))
+    per_rank = {k: hashlib.sha256(v).hexdigest() for k, v in mine.items()}
+    if dist is not None:
+        parts = [None] * world
+        dist.all_gather_object(parts, mine)  # block hashes only (32 B per 2^14 items); not on the measured path
+    else:
+        parts = [mine]
+    if rank != 0:
+        return None
+    got = {k: hashlib.sha256(b"".join(p[k] for p in parts)).hexdigest() for k in ("c", "K", "Kd")}
+    ok = got == fixture["digest"]
+    assert ok, f"cross-N digest mismatch at {world} ranks: {got} != {fixture['digest']}"
+    return {"items_total": total, "ranks": world, "block_items": blk, "sha256_of_block_sha256s": got, "rank0_shard_sha256": per_rank,
+            "equals_oracle_fixture": ok, "fixture": "tests/golden/config4_digest.json (oracle/mlkem_oracle.c on the CPU, tests/golden/make_digest.py)"}
 
 
 def extras(kem, torch, dev, peaks):
@@ -425,6 +569,75 @@ def extras(kem, torch, dev, peaks):
         t = timeit(lambda: kem.keygen(ps, seeds[0], seeds[1]), reps=2)
         out[f"keygen_{ps}_per_s"] = nk / t
     out["hbm_peak_gbs"] = hbm
+    out.update(caller_view(kem))
+    return out
+
+
+def caller_view(kem):
+    """What a caller of the reference gets: the latency of KEM_KeyGen / KEM_Encaps / KEM_Decaps through
+    include/ml_kem.h (stride-4 unions, malloc'ed results, a batch of one on the GPU per call), and the throughput of the batched
+    host-memory entry points for batches of 2^0 .. 2^14 items in ordinary (pageable) host memory."""
+    import statistics
+
+    import numpy as np
+
+    lib = kem.lib
+
+    class PARAMS(C.Structure):
+        _fields_ = [("k", C.c_uint), ("n1", C.c_uint), ("n2", C.c_uint), ("du", C.c_uint), ("dv", C.c_uint)]
+
+    class PKE(C.Structure):
+        _fields_ = [("ek", C.POINTER(C.c_uint)), ("dk", C.POINTER(C.c_uint)), ("ek_len", C.c_uint), ("dk_len", C.c_uint)]
+
+    class KEM(C.Structure):
+        _fields_ = [("K", C.c_uint * 32), ("c", C.POINTER(C.c_uint)), ("c_len", C.c_uint)]
+
+    lib.init.restype, lib.init.argtypes = PARAMS, [C.c_int]
+    lib.KEM_KeyGen.restype, lib.KEM_KeyGen.argtypes = PKE, [C.POINTER(PARAMS)]
+    lib.KEM_Encaps.restype, lib.KEM_Encaps.argtypes = KEM, [C.POINTER(PARAMS), C.POINTER(C.c_uint), C.c_uint]
+    lib.KEM_Decaps.restype = C.POINTER(C.c_uint)
+    lib.KEM_Decaps.argtypes = [C.POINTER(PARAMS), C.POINTER(C.c_uint), C.c_uint, C.POINTER(C.c_uint), C.c_uint]
+    libc = C.CDLL(None)
+    libc.free.argtypes = [C.c_void_p]
+    p = lib.init(PS)
+    lat = {"KEM_KeyGen": [], "KEM_Encaps": [], "KEM_Decaps": []}
+    for it in range(23):
+        t0 = time.perf_counter()
+        keys = lib.KEM_KeyGen(C.byref(p))
+        t1 = time.perf_counter()
+        enc = lib.KEM_Encaps(C.byref(p), keys.ek, keys.ek_len)
+        t2 = time.perf_counter()
+        Kd = lib.KEM_Decaps(C.byref(p), keys.dk, keys.dk_len, enc.c, enc.c_len)
+        t3 = time.perf_counter()
+        assert bool(Kd) and all((Kd[i] & 0xFF) == (enc.K[i] & 0xFF) for i in range(32))
+        for ptr in (keys.ek, keys.dk, enc.c, Kd):
+            libc.free(ptr)
+        if it >= 3:
+            for name, dt in zip(lat, (t1 - t0, t2 - t1, t3 - t2)):
+                lat[name].append(dt * 1e6)
+    out = {"drop_in_api_latency_us": {k: {"median": statistics.median(v), "min": min(v)} for k, v in lat.items()},
+           "drop_in_api_note": "include/ml_kem.h entry points, one operation per call: layout conversion + H2D + the kernel chain of one item "
+                               "+ D2H + synchronise; the reference takes ~28 ms per operation at -O2 (cpu_baseline)"}
+    rng = np.random.default_rng(7)
+    nmax = 1 << 14
+    d, z, m = (rng.integers(0, 256, (nmax, 32), dtype=np.uint8) for _ in range(3))
+    ek, dk = kem.keygen(PS, d, z)
+    sweep = {}
+    for lg in range(0, 15, 2):
+        nb = 1 << lg
+        a_ek, a_dk, a_m = (np.ascontiguousarray(x[:nb]) for x in (ek, dk, m))
+        reps = 20 if lg <= 8 else 6
+        for _ in range(2):
+            c, K = kem.encaps(PS, a_ek, a_m)
+            kem.decaps(PS, a_dk, c)
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            c, K = kem.encaps(PS, a_ek, a_m)
+            Kd = kem.decaps(PS, a_dk, c)
+        dt = (time.perf_counter() - t0) / reps
+        assert (Kd == K).all()
+        sweep[str(nb)] = {"pairs_per_s": nb / dt, "us_per_pair_of_calls": dt * 1e6}
+    out["small_batch_host_memory"] = sweep
     return out
 
 

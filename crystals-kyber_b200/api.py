@@ -32,6 +32,27 @@ def _is_torch(x):
     return type(x).__module__.startswith("torch")
 
 
+class KeyTable:
+    """Owner of a mlkem_b200_keys handle (freed, and wiped, with the object)."""
+
+    def __init__(self, kem, handle, ps):
+        self.kem, self.handle, self.ps = kem, handle, ps
+
+    def __len__(self):
+        return int(self.kem.lib.mlkem_b200_keys_count(self.handle))
+
+    def free(self):
+        if self.handle:
+            self.kem.lib.mlkem_b200_keys_free(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
 class MLKEM:
     def __init__(self, chunk_items: int = 0, sample_group_limit: int = 0, fips203: bool = False):
         """fips203=True selects the conformant variant (SHAKE256 PRF/J, real modulus check) instead of the
@@ -105,6 +126,71 @@ class MLKEM:
     def check_dk(self, ps, dk):
         n = self._count(dk, sizes(ps)["dk"])
         return self._call("mlkem_b200_check_dk_batch", (ps, n), [(dk, np.uint8)], [((n,), np.int32)])
+
+    # ------------------------------------------------------------------ resident key tables (keyed Encaps / Decaps)
+    def _src_opts(self, *arrays, device=None):
+        """Options describing where `arrays` live: torch CUDA tensors -> device memory on their device and the current
+        torch stream; anything else -> host memory (on `device`, default: the current one)."""
+        t = next((a for a in arrays if a is not None and _is_torch(a)), None)
+        if t is not None:
+            import torch
+
+            return self._opts(True, t.device.index, torch.cuda.current_stream(t.device).cuda_stream), True
+        return self._opts(False, -1 if device is None else device), False
+
+    def keys_load(self, ps, dk=None, ek=None, seeds=None, device=None, return_status=False):
+        """A resident key table on the GPU from decapsulation keys `dk`, from encapsulation keys `ek` (Encaps only) or
+        from the 64-byte seeds `(d, z)` (KeyGen_internal on the device)."""
+        sz = sizes(ps)
+        handle = C.c_void_p()
+        prep = lambda a: a.contiguous() if _is_torch(a) else np.ascontiguousarray(a, np.uint8)
+        ptr = lambda a: C.c_void_p(a.data_ptr() if _is_torch(a) else a.ctypes.data)
+        status = None
+        if dk is not None:
+            dk = prep(dk)
+            n = self._count(dk, sz["dk"])
+            o, _ = self._src_opts(dk, device=device)
+            status = np.empty(n, np.int32)
+            rc = self.lib.mlkem_b200_keys_load(ps, n, ptr(dk), C.c_void_p(status.ctypes.data), C.byref(o), C.byref(handle))
+        elif ek is not None:
+            ek = prep(ek)
+            o, _ = self._src_opts(ek, device=device)
+            rc = self.lib.mlkem_b200_keys_load_ek(ps, self._count(ek, sz["ek"]), ptr(ek), C.byref(o), C.byref(handle))
+        else:
+            d, z = (prep(a) for a in seeds)
+            o, _ = self._src_opts(d, z, device=device)
+            rc = self.lib.mlkem_b200_keys_from_seeds(ps, self._count(d, 32), ptr(d), ptr(z), C.byref(o), C.byref(handle))
+        self._check(rc, "mlkem_b200_keys_load")
+        table = KeyTable(self, handle, ps)
+        return (table, status) if return_status else table
+
+    def _keyed(self, fname, table, key_index, data, item_bytes, out_shapes):
+        n = self._count(data, item_bytes)
+        if _is_torch(data):
+            import torch
+
+            data = data.contiguous()
+            idx = None if key_index is None else key_index.to(device=data.device, dtype=torch.int32).contiguous()
+            outs = [torch.empty((n, w), dtype=torch.uint8, device=data.device) for w in out_shapes]
+            o, _ = self._src_opts(data)
+            ptr = lambda t: None if t is None else C.c_void_p(t.data_ptr())
+        else:
+            data = np.ascontiguousarray(data, np.uint8)
+            idx = None if key_index is None else np.ascontiguousarray(key_index, np.uint32)
+            outs = [np.empty((n, w), np.uint8) for w in out_shapes]
+            o = self._opts(False)
+            ptr = lambda a: None if a is None else C.c_void_p(a.ctypes.data)
+        rc = getattr(self.lib, fname)(table.handle, n, ptr(idx), ptr(data), *[ptr(a) for a in outs], C.byref(o))
+        self._check(rc, fname)
+        return outs[0] if len(outs) == 1 else tuple(outs)
+
+    def encaps_keyed(self, table, key_index, m):
+        """Encaps_internal under table[key_index[i]] (key_index=None: key i mod n_keys).  Returns (c, K)."""
+        return self._keyed("mlkem_b200_encaps_keyed_batch", table, key_index, m, 32, [sizes(table.ps)["c"], 32])
+
+    def decaps_keyed(self, table, key_index, c):
+        """Decaps_internal under table[key_index[i]].  Returns K."""
+        return self._keyed("mlkem_b200_decaps_keyed_batch", table, key_index, c, sizes(table.ps)["c"], [32])
 
     # ------------------------------------------------------------------ public wrappers (entropy + checks), host memory
     def kem_keygen(self, ps, n):

@@ -248,7 +248,8 @@ union integer *BaseCaseMultiply(union integer a0, union integer a1, union intege
     int dev;
     DeviceCtx *ctx;
     union integer *C = (union integer *)calloc(2, sizeof(union integer));
-    if (int rc = acquire(nullptr, &dev, &ctx)) {
+    DeviceGuard guard;
+    if (int rc = acquire(nullptr, &dev, &ctx, guard)) {
         cuda_failure("BaseCaseMultiply", rc);
         return C;
     }

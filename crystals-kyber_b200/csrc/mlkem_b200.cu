@@ -24,11 +24,20 @@ using namespace mlkem;
 
 thread_local char tl_error[512] = "";
 std::atomic<unsigned long long> g_launches{0};
-std::atomic<int> g_streams{4};  // streams that device-memory calls interleave their chunks on (1 = serial; measured 31.3 / 32.4 / 32.5 / 32.5 M pairs/s with 1 / 2 / 3 / 4)
 int env_int(const char *name, int dflt) {
     const char *v = getenv(name);
     return v && *v ? atoi(v) : dflt;
 }
+constexpr int kSlots = 4;      // streams / workspaces per device (host-memory calls use the first kHostSlots)
+constexpr int kHostSlots = 3;  // measured: 3 slots keep the H2D copy engine at ~50.7 GB/s (2 slots: 48 GB/s)
+constexpr int kMaxDevices = 64;
+// Streams that device-memory calls interleave their chunks on (1 = serial; measured 31.3 / 32.4 / 32.5 / 32.5 M pairs/s with
+// 1 / 2 / 3 / 4).  MLKEM_B200_STREAMS sets the start value ONCE; mlkem_b200_set_streams() overrides it afterwards.
+int initial_streams() {
+    int v = env_int("MLKEM_B200_STREAMS", 0);
+    return v < 1 ? kSlots : (v > kSlots ? kSlots : v);
+}
+std::atomic<int> g_streams{initial_streams()};
 
 #define CU(call)                                                                                              \
     do {                                                                                                      \
@@ -129,10 +138,10 @@ void build_tables(TwiddleTables &t, uint2 rc[24]) {
 // ------------------------------------------------------------------------------------------------
 // Per-device context
 // ------------------------------------------------------------------------------------------------
-constexpr int kSlots = 4;   // streams / workspaces per device (host-memory calls use the first kHostSlots)
-constexpr int kHostSlots = 3;  // measured: 3 slots keep the H2D copy engine at ~50.7 GB/s (2 slots: 48 GB/s)
-constexpr int kMaxDevices = 64;
-
+// Slot k of a device = workspace ws[k] + staging buffer io[k] + library stream stream[k].  A slot may be used from the
+// library stream (chunks of large device-memory calls, every host-memory call) or from the CALLER's stream (a
+// device-memory call that stays on one stream), so stream order alone does not protect it: ev_slot[k] is recorded after
+// the last kernel of every use, and every user makes its stream wait for it first.  call_mutex serialises the enqueueing.
 struct DeviceCtx {
     bool ready = false;
     cudaStream_t stream[kSlots] = {};
@@ -140,15 +149,40 @@ struct DeviceCtx {
     size_t ws_bytes[kSlots] = {};
     void *io[kSlots] = {};  // device staging of host-resident inputs / outputs
     size_t io_bytes[kSlots] = {};
-    cudaEvent_t ev_fork = nullptr, ev_join[kSlots] = {};
+    cudaEvent_t ev_fork = nullptr, ev_join[kSlots] = {}, ev_slot[kSlots] = {};
+    void *misc = nullptr;  // small pooled device buffer: entropy seeds / status words of the public-wrapper batches
+    size_t misc_bytes = 0;
     std::mutex call_mutex;  // one call at a time enqueues on this device's streams / workspaces
+    std::mutex misc_mutex;  // one user of `misc` at a time (held until its stream has drained)
 };
 DeviceCtx g_ctx[kMaxDevices];
 std::mutex g_mutex;
 
-int ensure_buffer(void **p, size_t *have, size_t need) {
+// The calling thread's current device is switched for the duration of a call only (torch, for one, follows
+// cudaGetDevice): every entry point holds one of these.
+struct DeviceGuard {
+    int prev = -1;
+    bool changed = false;
+    int enter(int d) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev == d) return 0;
+        CU(cudaSetDevice(d));
+        changed = true;
+        return 0;
+    }
+    ~DeviceGuard() {
+        if (changed && prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+// Grow-only device buffer.  `last_use` (may be null) is the event after which nothing reads the old buffer any more.
+int ensure_buffer(void **p, size_t *have, size_t need, cudaEvent_t last_use = nullptr) {
     if (*have >= need) return 0;
-    if (*p) CU(cudaFree(*p));
+    if (*p) {
+        if (last_use) CU(cudaEventSynchronize(last_use));
+        CU(cudaMemset(*p, 0, *have));  // intermediates are secret-dependent (sigma, s^, m', K' || r')
+        CU(cudaFree(*p));
+    }
     *p = nullptr;
     *have = 0;
     size_t want = need + need / 8;
@@ -175,34 +209,52 @@ int allow_smem_matvec() {
     return 0;
 }
 
-// Select the device and make sure its context exists.  Returns the device ordinal through *dev.
-int acquire(const mlkem_b200_opts *o, int *dev, DeviceCtx **ctx) {
+// Select the device (for the lifetime of `guard`) and make sure its context exists.  Returns the ordinal through *dev.
+int acquire(const mlkem_b200_opts *o, int *dev, DeviceCtx **ctx, DeviceGuard &guard) {
     int d = o ? o->device : -1;
     if (d < 0) CU(cudaGetDevice(&d));
     if (d >= kMaxDevices) {
         snprintf(tl_error, sizeof tl_error, "device ordinal %d out of range", d);
         return MLKEM_B200_ERR_ARG;
     }
-    CU(cudaSetDevice(d));
+    if (int rc = guard.enter(d)) return rc;
     std::lock_guard<std::mutex> lock(g_mutex);
     DeviceCtx &c = g_ctx[d];
     if (!c.ready) {
-        TwiddleTables t;
-        uint2 rc[24];
-        build_tables(t, rc);
-        CU(cudaMemcpyToSymbol(c_tw, &t, sizeof t));
-        CU(cudaMemcpyToSymbol(g_tw, &t, sizeof t));
-        CU(cudaMemcpyToSymbol(c_keccak_rc, rc, sizeof rc));
-        uint32_t pow2[32];
-        for (int k = 0; k < 32; k++) pow2[k] = 1u << k;
-        CU(cudaMemcpyToSymbol(c_pow2, pow2, sizeof pow2));
-        for (int s = 0; s < kSlots; s++) CU(cudaStreamCreateWithFlags(&c.stream[s], cudaStreamNonBlocking));
-        CU(cudaEventCreateWithFlags(&c.ev_fork, cudaEventDisableTiming));
-        for (int s = 0; s < kSlots; s++) CU(cudaEventCreateWithFlags(&c.ev_join[s], cudaEventDisableTiming));
-        if (int r = allow_smem_matvec<P512>()) return r;
-        if (int r = allow_smem_matvec<P768>()) return r;
-        if (int r = allow_smem_matvec<P1024>()) return r;
-        if (int r = allow_smem(k_sample_ntt_batch, 128 * kSlotWords * 4)) return r;
+        // all or nothing: streams and events are created into locals and only published when everything succeeded
+        cudaStream_t st[kSlots] = {};
+        cudaEvent_t ev[2 * kSlots + 1] = {};
+        auto create = [&]() -> int {
+            TwiddleTables t;
+            uint2 rc[24];
+            build_tables(t, rc);
+            CU(cudaMemcpyToSymbol(c_tw, &t, sizeof t));
+            CU(cudaMemcpyToSymbol(g_tw, &t, sizeof t));
+            CU(cudaMemcpyToSymbol(c_keccak_rc, rc, sizeof rc));
+            uint32_t pow2[32];
+            for (int k = 0; k < 32; k++) pow2[k] = 1u << k;
+            CU(cudaMemcpyToSymbol(c_pow2, pow2, sizeof pow2));
+            for (int s = 0; s < kSlots; s++) CU(cudaStreamCreateWithFlags(&st[s], cudaStreamNonBlocking));
+            for (int e = 0; e < 2 * kSlots + 1; e++) CU(cudaEventCreateWithFlags(&ev[e], cudaEventDisableTiming));
+            if (int r = allow_smem_matvec<P512>()) return r;
+            if (int r = allow_smem_matvec<P768>()) return r;
+            if (int r = allow_smem_matvec<P1024>()) return r;
+            if (int r = allow_smem(k_sample_ntt_batch, 128 * kSlotWords * 4)) return r;
+            return 0;
+        };
+        if (int r = create()) {
+            for (auto s_ : st)
+                if (s_) cudaStreamDestroy(s_);
+            for (auto e_ : ev)
+                if (e_) cudaEventDestroy(e_);
+            return r;
+        }
+        for (int s = 0; s < kSlots; s++) {
+            c.stream[s] = st[s];
+            c.ev_join[s] = ev[s];
+            c.ev_slot[s] = ev[kSlots + s];
+        }
+        c.ev_fork = ev[2 * kSlots];
         c.ready = true;
     }
     *dev = d;
@@ -271,7 +323,7 @@ int launch_matvec(cudaStream_t st, Arena &ws, MatvecArgs a) {
 // K-PKE.Encrypt (ml_kem.c:776) for n items; `seed` = 32-byte PRF key r per item.
 // Stores c, or (cmp != nullptr) ORs the mismatch of the re-encryption against cmp into flags.
 template <class P>
-int enqueue_encrypt(cudaStream_t st, Arena &ws, int n, const uint8_t *ek, size_t ek_stride, const uint8_t *m,
+int enqueue_encrypt(cudaStream_t st, Arena &ws, int n, const uint8_t *ek, size_t ek_stride, KeySel keys, const uint8_t *m,
                     const uint8_t *seed, size_t seed_stride, uint8_t *c, const uint8_t *cmp, uint32_t *flags, int group_limit, bool fips) {
     constexpr int K = P::K;
     uint16_t *yhat = ws.take<uint16_t>((size_t)n * K * 256);
@@ -295,6 +347,7 @@ int enqueue_encrypt(cudaStream_t st, Arena &ws, int n, const uint8_t *ek, size_t
     a.group_limit = group_limit;
     a.rho = ek + 384 * K;
     a.rho_stride = ek_stride;
+    a.keys = keys;
     a.vec = yhat;
     a.vec_stride = (size_t)K * 256;
     a.addc = codes;
@@ -307,6 +360,7 @@ int enqueue_encrypt(cudaStream_t st, Arena &ws, int n, const uint8_t *ek, size_t
     v.n = n;
     v.ek = ek;
     v.ek_stride = ek_stride;
+    v.keys = keys;
     v.yhat = yhat;
     v.yhat_stride = (size_t)K * 256;
     v.addc = codes;
@@ -366,22 +420,31 @@ template <class P>
 int enqueue_encaps(cudaStream_t st, Arena &ws, int n, const uint8_t *ek, const uint8_t *m, uint8_t *c, uint8_t *Kout, int group_limit, bool fips) {
     uint8_t *r = ws.take<uint8_t>((size_t)n * 32);
     LAUNCH((k_encaps_HG<P>), cdiv(n, kHashTPB), kHashTPB, 0, st, n, ek, m, Kout, r);
-    return enqueue_encrypt<P>(st, ws, n, ek, P::EK, m, r, 32, c, nullptr, nullptr, group_limit, fips);
+    return enqueue_encrypt<P>(st, ws, n, ek, P::EK, KeySel{}, m, r, 32, c, nullptr, nullptr, group_limit, fips);
+}
+
+// Encaps_internal against a resident key table: ek rows at ek + key*ek_stride, their hashes H(ek) at hek + 32 key.
+template <class P>
+int enqueue_encaps_keyed(cudaStream_t st, Arena &ws, int n, const uint8_t *ek, size_t ek_stride, const uint8_t *hek, KeySel keys,
+                         const uint8_t *m, uint8_t *c, uint8_t *Kout, int group_limit, bool fips) {
+    uint8_t *r = ws.take<uint8_t>((size_t)n * 32);
+    LAUNCH(k_encaps_G_keyed, cdiv(n, kHashTPB), kHashTPB, 0, st, n, hek, keys, m, Kout, r);
+    return enqueue_encrypt<P>(st, ws, n, ek, ek_stride, keys, m, r, 32, c, nullptr, nullptr, group_limit, fips);
 }
 
 template <class P>
-int enqueue_decaps(cudaStream_t st, Arena &ws, int n, const uint8_t *dk, const uint8_t *c, uint8_t *Kout, int group_limit, bool fips) {
+int enqueue_decaps(cudaStream_t st, Arena &ws, int n, const uint8_t *dk, KeySel keys, const uint8_t *c, uint8_t *Kout, int group_limit, bool fips) {
     constexpr int K = P::K;
     uint8_t *mp = ws.take<uint8_t>((size_t)n * 32);
     uint8_t *Kr = ws.take<uint8_t>((size_t)n * 64);
     uint32_t *flags = ws.take<uint32_t>((size_t)n);
     CU(cudaMemsetAsync(flags, 0, (size_t)n * 4, st));
-    LAUNCH((k_decrypt<P>), warp_grid(n, kWarpTPB / 32), kWarpTPB, 0, st, n, dk, (size_t)P::DK, c, mp);
-    LAUNCH((k_decaps_G<P>), cdiv(n, kHashTPB), kHashTPB, 0, st, n, mp, dk, Kr);
+    LAUNCH((k_decrypt<P>), warp_grid(n, kWarpTPB / 32), kWarpTPB, 0, st, n, dk, (size_t)P::DK, keys, c, mp);
+    LAUNCH((k_decaps_G<P>), cdiv(n, kHashTPB), kHashTPB, 0, st, n, mp, dk, keys, Kr);
     // c' = K-PKE.Encrypt(ek_pke, m', r') compared on the fly (ml_kem.c:1206-1215)
-    if (int rc = enqueue_encrypt<P>(st, ws, n, dk + 384 * K, P::DK, mp, Kr + 32, 64, nullptr, c, flags, group_limit, fips)) return rc;
-    if (!fips) LAUNCH((k_decaps_J_select<P>), cdiv(n, kHashTPB), kHashTPB, 0, st, n, dk, c, Kr, flags, Kout);
-    else LAUNCH((k_decaps_J_select<P, kRateSha3_256>), cdiv(n, kHashTPB), kHashTPB, 0, st, n, dk, c, Kr, flags, Kout);
+    if (int rc = enqueue_encrypt<P>(st, ws, n, dk + 384 * K, P::DK, keys, mp, Kr + 32, 64, nullptr, c, flags, group_limit, fips)) return rc;
+    if (!fips) LAUNCH((k_decaps_J_select<P>), cdiv(n, kHashTPB), kHashTPB, 0, st, n, dk, keys, c, Kr, flags, Kout);
+    else LAUNCH((k_decaps_J_select<P, kRateSha3_256>), cdiv(n, kHashTPB), kHashTPB, 0, st, n, dk, keys, c, Kr, flags, Kout);
     return 0;
 }
 
@@ -396,7 +459,8 @@ struct Buf {
 
 bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
-// run(stream, arena, n_chunk, ptrs[]) where ptrs[i] is the device address of buffer i for this chunk.
+// run(stream, arena, n_chunk, ptrs[], first) where ptrs[i] is the device address of buffer i for this chunk and `first`
+// the index of the chunk's first item within the call.
 template <class Run>
 int drive(const mlkem_b200_opts *o, size_t n, size_t ws_per_item, std::vector<Buf> bufs, Run run) {
     if (n == 0) return MLKEM_B200_OK;
@@ -411,15 +475,15 @@ int drive(const mlkem_b200_opts *o, size_t n, size_t ws_per_item, std::vector<Bu
         }
     int dev;
     DeviceCtx *ctx;
-    if (int rc = acquire(o, &dev, &ctx)) return rc;
-    // Calls from several host threads are serialised per device while they enqueue: the workspaces and the
-    // library streams are shared, and stream order then keeps consecutive calls from touching them concurrently.
+    DeviceGuard guard;
+    if (int rc = acquire(o, &dev, &ctx, guard)) return rc;
+    // Calls from several host threads are serialised per device while they enqueue.  The slots (workspace + staging
+    // buffer) are shared between calls and may be used from different streams: see DeviceCtx::ev_slot.
     std::lock_guard<std::mutex> call_lock(ctx->call_mutex);
     const bool on_device = o && o->mem == MLKEM_B200_MEM_DEVICE;
-    static const int env_chunk = env_int("MLKEM_B200_CHUNK", 0), env_streams = env_int("MLKEM_B200_STREAMS", 0);  // tuning knobs
+    static const int env_chunk = env_int("MLKEM_B200_CHUNK", 0);  // tuning knobs
     static const int env_hchunk = env_int("MLKEM_B200_HOST_CHUNK", 0);
     static const int host_slots = std::min(kSlots, std::max(1, env_int("MLKEM_B200_HOST_SLOTS", kHostSlots)));
-    if (env_streams > 0) g_streams.store(env_streams > kSlots ? kSlots : env_streams);
     size_t chunk = (o && o->chunk_items > 0) ? (size_t)o->chunk_items
                    : (on_device ? (env_chunk > 0 ? (size_t)env_chunk : (size_t)1 << 18) : (env_hchunk > 0 ? (size_t)env_hchunk : (size_t)1 << 16));
     if (chunk > ((size_t)1 << 26)) chunk = (size_t)1 << 26;  // the kernels index rows (items x k) and list entries with int
@@ -451,45 +515,55 @@ int drive(const mlkem_b200_opts *o, size_t n, size_t ws_per_item, std::vector<Bu
         {
             std::lock_guard<std::mutex> lock(g_mutex);
             for (int k = 0; k < nstreams; k++)
-                if (int rc = ensure_buffer(&ctx->ws[k], &ctx->ws_bytes[k], chunk * ws_per_item + kWsSlack)) return rc;
+                if (int rc = ensure_buffer(&ctx->ws[k], &ctx->ws_bytes[k], chunk * ws_per_item + kWsSlack, ctx->ev_slot[k])) return rc;
         }
-        if (nstreams > 1) {
-            CU(cudaEventRecord(ctx->ev_fork, st));
-            for (int k = 0; k < nstreams; k++) CU(cudaStreamWaitEvent(ctx->stream[k], ctx->ev_fork, 0));
+        const bool fork = nstreams > 1;
+        if (fork) CU(cudaEventRecord(ctx->ev_fork, st));
+        for (int k = 0; k < nstreams; k++) {
+            cudaStream_t sk = fork ? ctx->stream[k] : st;
+            if (fork) CU(cudaStreamWaitEvent(sk, ctx->ev_fork, 0));
+            CU(cudaStreamWaitEvent(sk, ctx->ev_slot[k], 0));  // the previous user of slot k, whatever stream it was on
         }
-        for (size_t ci = 0; ci < nch; ci++) {
+        int rc = 0;
+        for (size_t ci = 0; ci < nch && !rc; ci++) {
             size_t i0 = ci * chunk, cn = (i0 + chunk <= n) ? chunk : n - i0;
             for (size_t b = 0; b < bufs.size(); b++) {
                 const uint8_t *base = static_cast<const uint8_t *>(bufs[b].in ? bufs[b].in : bufs[b].out);
                 ptrs[b] = const_cast<uint8_t *>(base) + i0 * bufs[b].item_bytes;
             }
-            const int k = nstreams > 1 ? (int)(ci % nstreams) : 0;
+            const int k = fork ? (int)(ci % nstreams) : 0;
             Arena arena(ctx->ws[k]);
-            if (int rc = run(nstreams > 1 ? ctx->stream[k] : st, arena, (int)cn, ptrs.data())) return rc;
+            rc = run(fork ? ctx->stream[k] : st, arena, (int)cn, ptrs.data(), i0);
         }
-        if (nstreams > 1) {
-            for (int k = 0; k < nstreams; k++) {
-                CU(cudaEventRecord(ctx->ev_join[k], ctx->stream[k]));
-                CU(cudaStreamWaitEvent(st, ctx->ev_join[k], 0));
+        // also on the error path: whatever was enqueued is joined back into the caller's stream and the slots are marked
+        for (int k = 0; k < nstreams; k++) {
+            cudaStream_t sk = fork ? ctx->stream[k] : st;
+            cudaError_t e = cudaEventRecord(ctx->ev_slot[k], sk);
+            if (fork && e == cudaSuccess) e = cudaEventRecord(ctx->ev_join[k], sk);
+            if (fork && e == cudaSuccess) e = cudaStreamWaitEvent(st, ctx->ev_join[k], 0);
+            if (e != cudaSuccess && !rc) {
+                snprintf(tl_error, sizeof tl_error, "stream join failed: %s", cudaGetErrorString(e));
+                rc = MLKEM_B200_ERR_CUDA;
             }
         }
-        return MLKEM_B200_OK;
+        return rc;
     }
 
     // host memory: stage each chunk through device buffers, rotating over the staging slots / streams so that the
     // copies of one chunk overlap the kernels of the other
     size_t io_per_item = 0;
     for (auto &b : bufs) io_per_item += (b.item_bytes + 15) & ~size_t(15);
+    const int nslots = nchunks > 1 ? (int)std::min<size_t>(host_slots, nchunks) : 1;
     {
         std::lock_guard<std::mutex> lock(g_mutex);
-        const int nslots = nchunks > 1 ? host_slots : 1;
         for (int s = 0; s < nslots; s++) {
-            if (int rc = ensure_buffer(&ctx->ws[s], &ctx->ws_bytes[s], chunk * ws_per_item + kWsSlack)) return rc;
-            if (int rc = ensure_buffer(&ctx->io[s], &ctx->io_bytes[s], chunk * io_per_item + 256 * bufs.size())) return rc;
+            if (int rc = ensure_buffer(&ctx->ws[s], &ctx->ws_bytes[s], chunk * ws_per_item + kWsSlack, ctx->ev_slot[s])) return rc;
+            if (int rc = ensure_buffer(&ctx->io[s], &ctx->io_bytes[s], chunk * io_per_item + 256 * bufs.size(), ctx->ev_slot[s])) return rc;
         }
     }
-    for (size_t ci = 0; ci < nchunks; ci++) {
-        const int s = (int)(ci % host_slots);
+    for (int s = 0; s < nslots; s++) CU(cudaStreamWaitEvent(ctx->stream[s], ctx->ev_slot[s], 0));
+    auto chunk_of = [&](size_t ci) -> int {
+        const int s = (int)(ci % nslots);
         cudaStream_t st = ctx->stream[s];
         size_t i0 = ci * chunk, cn = (i0 + chunk <= n) ? chunk : n - i0;
         Arena io(ctx->io[s]);
@@ -500,14 +574,25 @@ int drive(const mlkem_b200_opts *o, size_t n, size_t ws_per_item, std::vector<Bu
                                    cudaMemcpyHostToDevice, st));
         }
         Arena arena(ctx->ws[s]);
-        if (int rc = run(st, arena, (int)cn, ptrs.data())) return rc;
+        if (int rc = run(st, arena, (int)cn, ptrs.data(), i0)) return rc;
         for (size_t b = 0; b < bufs.size(); b++)
             if (bufs[b].out)
                 CU(cudaMemcpyAsync(static_cast<uint8_t *>(bufs[b].out) + i0 * bufs[b].item_bytes, ptrs[b], cn * bufs[b].item_bytes,
                                    cudaMemcpyDeviceToHost, st));
+        return 0;
+    };
+    int rc = 0;
+    for (size_t ci = 0; ci < nchunks && !rc; ci++) rc = chunk_of(ci);
+    // also on the error path: nothing may still be writing into the caller's buffers when the call returns
+    for (int s = 0; s < nslots; s++) {
+        cudaEventRecord(ctx->ev_slot[s], ctx->stream[s]);
+        cudaError_t e = cudaStreamSynchronize(ctx->stream[s]);
+        if (e != cudaSuccess && !rc) {
+            snprintf(tl_error, sizeof tl_error, "cudaStreamSynchronize failed: %s", cudaGetErrorString(e));
+            rc = MLKEM_B200_ERR_CUDA;
+        }
     }
-    for (int s = 0; s < host_slots; s++) CU(cudaStreamSynchronize(ctx->stream[s]));
-    return MLKEM_B200_OK;
+    return rc;
 }
 
 int group_limit_of(const mlkem_b200_opts *o) { return (o && o->sample_group_limit > 0) ? o->sample_group_limit : 278; }
@@ -543,7 +628,9 @@ int mlkem_b200_device_count(void) {
     return n;
 }
 int mlkem_b200_synchronize(int device, void *stream) {
-    if (device >= 0) CU(cudaSetDevice(device));
+    DeviceGuard guard;
+    if (device >= 0)
+        if (int rc = guard.enter(device)) return rc;
     if (stream) CU(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
     else CU(cudaDeviceSynchronize());
     return 0;
@@ -551,6 +638,11 @@ int mlkem_b200_synchronize(int device, void *stream) {
 void *mlkem_b200_host_alloc(size_t bytes) {
     void *p = nullptr;
     if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) return nullptr;
+    return p;
+}
+void *mlkem_b200_host_alloc_wc(size_t bytes) {
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable | cudaHostAllocWriteCombined) != cudaSuccess) return nullptr;
     return p;
 }
 void mlkem_b200_host_free(void *p) {
@@ -561,13 +653,25 @@ void mlkem_b200_release(int device) {
     std::lock_guard<std::mutex> lock(g_mutex);
     DeviceCtx &c = g_ctx[device];
     if (!c.ready) return;
-    cudaSetDevice(device);
+    DeviceGuard guard;
+    if (guard.enter(device)) return;
+    std::lock_guard<std::mutex> call_lock(c.call_mutex);
+    std::lock_guard<std::mutex> misc_lock(c.misc_mutex);
+    cudaDeviceSynchronize();
+    // the workspaces hold secret-dependent intermediates (sigma, s^ / e^, m', K' || r') and staged keys: wipe, then free
+    auto wipe_free = [](void *&p, size_t &bytes) {
+        if (p) {
+            cudaMemset(p, 0, bytes);
+            cudaFree(p);
+        }
+        p = nullptr;
+        bytes = 0;
+    };
     for (int s = 0; s < kSlots; s++) {
-        if (c.ws[s]) cudaFree(c.ws[s]);
-        if (c.io[s]) cudaFree(c.io[s]);
-        c.ws[s] = c.io[s] = nullptr;
-        c.ws_bytes[s] = c.io_bytes[s] = 0;
+        wipe_free(c.ws[s], c.ws_bytes[s]);
+        wipe_free(c.io[s], c.io_bytes[s]);
     }
+    wipe_free(c.misc, c.misc_bytes);
 }
 
 static unsigned k_of(int set) { return set == 512 ? 2 : set == 768 ? 3 : set == 1024 ? 4 : 0; }
@@ -587,7 +691,7 @@ int mlkem_b200_keygen_batch(int set, size_t n, const uint8_t *d, const uint8_t *
     const int gl = group_limit_of(o);
     const bool fips = fips_of(o);
     DISPATCH_SET(set, return drive(o, n, ws_bytes_per_item<P>(), {{d, nullptr, 32}, {z, nullptr, 32}, {nullptr, ek, P::EK}, {nullptr, dk, P::DK}},
-                                   [=](cudaStream_t st, Arena &ws, int cn, void **p) {
+                                   [=](cudaStream_t st, Arena &ws, int cn, void **p, size_t) {
                                        return enqueue_keygen<P>(st, ws, cn, (const uint8_t *)p[0], (const uint8_t *)p[1], (uint8_t *)p[2], (uint8_t *)p[3], gl, fips);
                                    }));
     return MLKEM_B200_ERR_PARAM;
@@ -597,7 +701,7 @@ int mlkem_b200_pke_keygen_batch(int set, size_t n, const uint8_t *d, uint8_t *ek
     const int gl = group_limit_of(o);
     const bool fips = fips_of(o);
     DISPATCH_SET(set, return drive(o, n, ws_bytes_per_item<P>(), {{d, nullptr, 32}, {nullptr, ek, P::EK}, {nullptr, dkpke, P::DKPKE}},
-                                   [=](cudaStream_t st, Arena &ws, int cn, void **p) {
+                                   [=](cudaStream_t st, Arena &ws, int cn, void **p, size_t) {
                                        return enqueue_keygen<P>(st, ws, cn, (const uint8_t *)p[0], nullptr, (uint8_t *)p[1], (uint8_t *)p[2], gl, fips);
                                    }));
     return MLKEM_B200_ERR_PARAM;
@@ -607,7 +711,7 @@ int mlkem_b200_encaps_batch(int set, size_t n, const uint8_t *ek, const uint8_t 
     const int gl = group_limit_of(o);
     const bool fips = fips_of(o);
     DISPATCH_SET(set, return drive(o, n, ws_bytes_per_item<P>(), {{ek, nullptr, P::EK}, {m, nullptr, 32}, {nullptr, c, P::C}, {nullptr, K, 32}},
-                                   [=](cudaStream_t st, Arena &ws, int cn, void **p) {
+                                   [=](cudaStream_t st, Arena &ws, int cn, void **p, size_t) {
                                        return enqueue_encaps<P>(st, ws, cn, (const uint8_t *)p[0], (const uint8_t *)p[1], (uint8_t *)p[2], (uint8_t *)p[3], gl, fips);
                                    }));
     return MLKEM_B200_ERR_PARAM;
@@ -617,14 +721,14 @@ int mlkem_b200_decaps_batch(int set, size_t n, const uint8_t *dk, const uint8_t 
     const int gl = group_limit_of(o);
     const bool fips = fips_of(o);
     DISPATCH_SET(set, return drive(o, n, ws_bytes_per_item<P>(), {{dk, nullptr, P::DK}, {c, nullptr, P::C}, {nullptr, K, 32}},
-                                   [=](cudaStream_t st, Arena &ws, int cn, void **p) {
-                                       return enqueue_decaps<P>(st, ws, cn, (const uint8_t *)p[0], (const uint8_t *)p[1], (uint8_t *)p[2], gl, fips);
+                                   [=](cudaStream_t st, Arena &ws, int cn, void **p, size_t) {
+                                       return enqueue_decaps<P>(st, ws, cn, (const uint8_t *)p[0], KeySel{}, (const uint8_t *)p[1], (uint8_t *)p[2], gl, fips);
                                    }));
     return MLKEM_B200_ERR_PARAM;
 }
 
 int mlkem_b200_check_dk_batch(int set, size_t n, const uint8_t *dk, int32_t *status, const mlkem_b200_opts *o) {
-    DISPATCH_SET(set, return drive(o, n, 0, {{dk, nullptr, P::DK}, {nullptr, status, 4}}, [=](cudaStream_t st, Arena &, int cn, void **p) {
+    DISPATCH_SET(set, return drive(o, n, 0, {{dk, nullptr, P::DK}, {nullptr, status, 4}}, [=](cudaStream_t st, Arena &, int cn, void **p, size_t) {
                      LAUNCH((k_check_dk_hash<P>), cdiv(cn, kHashTPB), kHashTPB, 0, st, cn, (const uint8_t *)p[0], (int *)p[1]);
                      return 0;
                  }));
@@ -645,22 +749,50 @@ static int host_entropy(uint8_t *out, size_t bytes) {
     return got == bytes ? 0 : -2;  // ml_errno -2: random bit generation failed (ml_kem.c:1243,1297)
 }
 
+// A lease on the device's pooled scratch buffer (entropy seeds, status words): no cudaMalloc / cudaFree per call.
+// Held until the user's stream has drained, then wiped.
+struct MiscLease {
+    DeviceCtx *ctx = nullptr;
+    std::unique_lock<std::mutex> lock;
+    uint8_t *ptr = nullptr;
+    size_t bytes = 0;
+    cudaStream_t st = nullptr;
+    int take(DeviceCtx *c, size_t need, cudaStream_t stream) {
+        ctx = c;
+        st = stream;
+        bytes = need;
+        lock = std::unique_lock<std::mutex>(c->misc_mutex);
+        if (int rc = ensure_buffer(&c->misc, &c->misc_bytes, need)) return rc;
+        ptr = static_cast<uint8_t *>(c->misc);
+        return 0;
+    }
+    ~MiscLease() {
+        if (!ptr) return;
+        cudaMemsetAsync(ptr, 0, bytes, st);  // seeds are secrets
+        cudaStreamSynchronize(st);
+    }
+};
+
 // Runs `call(seed_ptr)` with `bytes` of fresh entropy placed where opts says the buffers live.
 template <class F>
 static int with_entropy(const mlkem_b200_opts *o, size_t bytes, F call) {
-    std::vector<uint8_t> host(bytes);
-    if (int rc = host_entropy(host.data(), bytes)) return rc;
-    if (!(o && o->mem == MLKEM_B200_MEM_DEVICE)) return call(host.data());
+    struct Wiped {  // the host copy of the seeds is zeroed on every exit path
+        std::vector<uint8_t> v;
+        ~Wiped() { explicit_bzero(v.data(), v.size()); }
+    } host{std::vector<uint8_t>(bytes)};
+    if (int rc = host_entropy(host.v.data(), bytes)) return rc;
+    if (!(o && o->mem == MLKEM_B200_MEM_DEVICE)) return call(host.v.data());
     int dev;
     DeviceCtx *ctx;
-    if (int rc = acquire(o, &dev, &ctx)) return rc;
-    uint8_t *d = nullptr;
-    CU(cudaMalloc(&d, bytes));
-    cudaError_t e = cudaMemcpy(d, host.data(), bytes, cudaMemcpyHostToDevice);
-    int rc = e == cudaSuccess ? call(d) : MLKEM_B200_ERR_CUDA;
-    cudaStreamSynchronize(static_cast<cudaStream_t>(o->stream));  // the seeds must outlive the kernels reading them
-    cudaFree(d);
-    return rc;
+    DeviceGuard guard;
+    if (int rc = acquire(o, &dev, &ctx, guard)) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(o->stream);
+    MiscLease lease;
+    if (int rc = lease.take(ctx, bytes, st)) return rc;
+    // on the caller's stream: ordered before the kernels that read the seeds (pageable source: the call returns once the
+    // bytes are staged, and the lease drains the stream before the host copy and the device buffer are wiped)
+    CU(cudaMemcpyAsync(lease.ptr, host.v.data(), bytes, cudaMemcpyHostToDevice, st));
+    return call(lease.ptr);
 }
 
 extern "C" {
@@ -679,19 +811,23 @@ int mlkem_b200_kem_encaps_batch(int set, size_t n, const uint8_t *ek, size_t ek_
     // In FIPS mode it is a real check: any coefficient >= q in any key rejects the call with -4.
     if (n == 0) return MLKEM_B200_OK;
     if (fips_of(o)) {
-        std::vector<int32_t> st_host;
-        int32_t *status = nullptr;
+        std::vector<int32_t> st_host(n);
         const bool on_dev = o->mem == MLKEM_B200_MEM_DEVICE;
-        if (on_dev) CU(cudaMalloc(&status, 4 * n));
-        else {
-            st_host.resize(n);
-            status = st_host.data();
+        int dev;
+        DeviceCtx *ctx;
+        DeviceGuard guard;
+        MiscLease lease;
+        int32_t *status = st_host.data();
+        if (on_dev) {
+            if (int rc = acquire(o, &dev, &ctx, guard)) return rc;
+            if (int rc = lease.take(ctx, 4 * n, static_cast<cudaStream_t>(o->stream))) return rc;
+            status = reinterpret_cast<int32_t *>(lease.ptr);
         }
         int rc = MLKEM_B200_ERR_PARAM;
         switch (set) {
 #define MODCHK(PS, PT)                                                                                                              \
     case PS:                                                                                                                        \
-        rc = drive(o, n, 0, {{ek, nullptr, PT::EK}, {nullptr, status, 4}}, [=](cudaStream_t st, Arena &, int cn, void **p) {          \
+        rc = drive(o, n, 0, {{ek, nullptr, PT::EK}, {nullptr, status, 4}}, [=](cudaStream_t st, Arena &, int cn, void **p, size_t) { \
             LAUNCH((k_check_ek_modulus<PT>), cdiv(cn, kHashTPB), kHashTPB, 0, st, cn, (const uint8_t *)p[0], (int *)p[1]);            \
             return 0;                                                                                                               \
         });                                                                                                                         \
@@ -700,11 +836,11 @@ int mlkem_b200_kem_encaps_batch(int set, size_t n, const uint8_t *ek, size_t ek_
 #undef MODCHK
         }
         if (!rc && on_dev) {
-            st_host.resize(n);
-            cudaStreamSynchronize(static_cast<cudaStream_t>(o->stream));
-            if (cudaMemcpy(st_host.data(), status, 4 * n, cudaMemcpyDeviceToHost) != cudaSuccess) rc = MLKEM_B200_ERR_CUDA;
+            cudaStream_t st = static_cast<cudaStream_t>(o->stream);
+            if (cudaMemcpyAsync(st_host.data(), status, 4 * n, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+                cudaStreamSynchronize(st) != cudaSuccess)
+                rc = MLKEM_B200_ERR_CUDA;
         }
-        if (on_dev) cudaFree(status);
         if (rc) return rc;
         for (size_t i = 0; i < n; i++)
             if (st_host[i] != 0) return MLKEM_B200_ERR_MODULUS;
@@ -734,8 +870,8 @@ int mlkem_b200_pke_encrypt_batch(int set, size_t n, const uint8_t *ek, const uin
     const int gl = group_limit_of(o);
     const bool fips = fips_of(o);
     DISPATCH_SET(set, return drive(o, n, ws_bytes_per_item<P>(), {{ek, nullptr, P::EK}, {m, nullptr, 32}, {r, nullptr, 32}, {nullptr, c, P::C}},
-                                   [=](cudaStream_t st, Arena &ws, int cn, void **p) {
-                                       return enqueue_encrypt<P>(st, ws, cn, (const uint8_t *)p[0], P::EK, (const uint8_t *)p[1], (const uint8_t *)p[2], 32,
+                                   [=](cudaStream_t st, Arena &ws, int cn, void **p, size_t) {
+                                       return enqueue_encrypt<P>(st, ws, cn, (const uint8_t *)p[0], P::EK, KeySel{}, (const uint8_t *)p[1], (const uint8_t *)p[2], 32,
                                                                  (uint8_t *)p[3], nullptr, nullptr, gl, fips);
                                    }));
     return MLKEM_B200_ERR_PARAM;
@@ -748,8 +884,8 @@ int mlkem_b200_pke_decrypt_batch(int set, size_t n, const uint8_t *dk, size_t dk
     }
     DISPATCH_SET(set, {
         if (dk_stride < (size_t)P::DKPKE) return MLKEM_B200_ERR_LENGTH;
-        return drive(o, n, 0, {{dk, nullptr, dk_stride}, {c, nullptr, P::C}, {nullptr, m, 32}}, [=](cudaStream_t st, Arena &, int cn, void **p) {
-            LAUNCH((k_decrypt<P>), warp_grid(cn, kWarpTPB / 32), kWarpTPB, 0, st, cn, (const uint8_t *)p[0], dk_stride, (const uint8_t *)p[1], (uint8_t *)p[2]);
+        return drive(o, n, 0, {{dk, nullptr, dk_stride}, {c, nullptr, P::C}, {nullptr, m, 32}}, [=](cudaStream_t st, Arena &, int cn, void **p, size_t) {
+            LAUNCH((k_decrypt<P>), warp_grid(cn, kWarpTPB / 32), kWarpTPB, 0, st, cn, (const uint8_t *)p[0], dk_stride, KeySel{}, (const uint8_t *)p[1], (uint8_t *)p[2]);
             return 0;
         });
     });
@@ -757,19 +893,19 @@ int mlkem_b200_pke_decrypt_batch(int set, size_t n, const uint8_t *dk, size_t dk
 }
 
 int mlkem_b200_ntt_batch(size_t n, const uint16_t *f, uint16_t *fh, const mlkem_b200_opts *o) {
-    return drive(o, n, 0, {{f, nullptr, 512}, {nullptr, fh, 512}}, [=](cudaStream_t st, Arena &, int cn, void **p) {
+    return drive(o, n, 0, {{f, nullptr, 512}, {nullptr, fh, 512}}, [=](cudaStream_t st, Arena &, int cn, void **p, size_t) {
         LAUNCH(k_ntt_batch, prim_grid(cn), kPrimTPB, 0, st, cn, (const uint16_t *)p[0], (uint16_t *)p[1]);
         return 0;
     });
 }
 int mlkem_b200_intt_batch(size_t n, const uint16_t *fh, uint16_t *f, const mlkem_b200_opts *o) {
-    return drive(o, n, 0, {{fh, nullptr, 512}, {nullptr, f, 512}}, [=](cudaStream_t st, Arena &, int cn, void **p) {
+    return drive(o, n, 0, {{fh, nullptr, 512}, {nullptr, f, 512}}, [=](cudaStream_t st, Arena &, int cn, void **p, size_t) {
         LAUNCH(k_intt_batch, prim_grid(cn), kPrimTPB, 0, st, cn, (const uint16_t *)p[0], (uint16_t *)p[1]);
         return 0;
     });
 }
 int mlkem_b200_multiply_ntts_batch(size_t n, const uint16_t *f, const uint16_t *g, uint16_t *h, const mlkem_b200_opts *o) {
-    return drive(o, n, 0, {{f, nullptr, 512}, {g, nullptr, 512}, {nullptr, h, 512}}, [=](cudaStream_t st, Arena &, int cn, void **p) {
+    return drive(o, n, 0, {{f, nullptr, 512}, {g, nullptr, 512}, {nullptr, h, 512}}, [=](cudaStream_t st, Arena &, int cn, void **p, size_t) {
         LAUNCH(k_mulntt_batch, prim_grid(cn), kPrimTPB, 0, st, cn, (const uint16_t *)p[0], (const uint16_t *)p[1], (uint16_t *)p[2]);
         return 0;
     });
@@ -784,7 +920,7 @@ int mlkem_b200_sample_ntt_batch(size_t n, const uint8_t *seeds, uint16_t *a, uin
     mlkem_b200_opts oo = o ? *o : mlkem_b200_opts{-1, MLKEM_B200_MEM_HOST, nullptr, 0, 0, 0};
     if (oo.chunk_items <= 0) oo.chunk_items = 1 << 16;
     oo.chunk_items = (oo.chunk_items + 7) & ~7;
-    return drive(&oo, n, 0, bufs, [=](cudaStream_t st, Arena &, int cn, void **p) {
+    return drive(&oo, n, 0, bufs, [=](cudaStream_t st, Arena &, int cn, void **p, size_t) {
         LAUNCH(k_sample_ntt_batch, cdiv(cn, 128), 128, 128 * kSlotWords * 4, st, cn, (const uint8_t *)p[0], (uint16_t *)p[1],
                has_after ? (uint8_t *)p[2] : (uint8_t *)nullptr, gl);
         return 0;
@@ -793,7 +929,7 @@ int mlkem_b200_sample_ntt_batch(size_t n, const uint8_t *seeds, uint16_t *a, uin
 
 int mlkem_b200_cbd_batch(int eta, size_t n, const uint8_t *bytes, uint16_t *f, const mlkem_b200_opts *o) {
     if (eta != 2 && eta != 3) return MLKEM_B200_ERR_ARG;
-    return drive(o, n, 0, {{bytes, nullptr, (size_t)64 * eta}, {nullptr, f, 512}}, [=](cudaStream_t st, Arena &, int cn, void **p) {
+    return drive(o, n, 0, {{bytes, nullptr, (size_t)64 * eta}, {nullptr, f, 512}}, [=](cudaStream_t st, Arena &, int cn, void **p, size_t) {
         if (eta == 2) LAUNCH((k_cbd_batch<2>), prim_grid(cn), kPrimTPB, 0, st, cn, (const uint8_t *)p[0], (uint16_t *)p[1]);
         else LAUNCH((k_cbd_batch<3>), prim_grid(cn), kPrimTPB, 0, st, cn, (const uint8_t *)p[0], (uint16_t *)p[1]);
         return 0;
@@ -805,7 +941,7 @@ int mlkem_b200_prf_cbd_batch(int eta, size_t n, const uint8_t *seeds, const uint
     mlkem_b200_opts oo = o ? *o : mlkem_b200_opts{-1, MLKEM_B200_MEM_HOST, nullptr, 0, 0, 0};
     if (oo.chunk_items <= 0) oo.chunk_items = 1 << 16;
     oo.chunk_items = (oo.chunk_items + 15) & ~15;  // 1-byte nonces: keep chunk starts 16-byte aligned
-    return drive(&oo, n, 0, {{seeds, nullptr, 32}, {nonces, nullptr, 1}, {nullptr, f, 512}}, [=](cudaStream_t st, Arena &, int cn, void **p) {
+    return drive(&oo, n, 0, {{seeds, nullptr, 32}, {nonces, nullptr, 1}, {nullptr, f, 512}}, [=](cudaStream_t st, Arena &, int cn, void **p, size_t) {
         if (fips) {
             if (eta == 2) LAUNCH((k_prf_cbd_batch<2, kRateSha3_256>), cdiv(cn, kNoiseTPB), kNoiseTPB, 0, st, cn, (const uint8_t *)p[0], (const uint8_t *)p[1], (uint16_t *)p[2]);
             else LAUNCH((k_prf_cbd_batch<3, kRateSha3_256>), cdiv(cn, kNoiseTPB), kNoiseTPB, 0, st, cn, (const uint8_t *)p[0], (const uint8_t *)p[1], (uint16_t *)p[2]);
@@ -829,7 +965,7 @@ int mlkem_b200_prf_cbd_batch(int eta, size_t n, const uint8_t *seeds, const uint
     }
 
 static int encode_impl(int d, size_t n, const uint16_t *F, uint8_t *B, const mlkem_b200_opts *o, bool comp) {
-    return drive(o, n, 0, {{F, nullptr, 512}, {nullptr, B, (size_t)32 * d}}, [=](cudaStream_t st, Arena &, int cn, void **p) {
+    return drive(o, n, 0, {{F, nullptr, 512}, {nullptr, B, (size_t)32 * d}}, [=](cudaStream_t st, Arena &, int cn, void **p, size_t) {
         DISPATCH_D(d, {
             if (comp) LAUNCH((k_encode_batch<D, true>), prim_grid(cn), kPrimTPB, 0, st, cn, (const uint16_t *)p[0], (uint8_t *)p[1]);
             else LAUNCH((k_encode_batch<D, false>), prim_grid(cn), kPrimTPB, 0, st, cn, (const uint16_t *)p[0], (uint8_t *)p[1]);
@@ -838,7 +974,7 @@ static int encode_impl(int d, size_t n, const uint16_t *F, uint8_t *B, const mlk
     });
 }
 static int decode_impl(int d, size_t n, const uint8_t *B, uint16_t *F, const mlkem_b200_opts *o, bool decomp) {
-    return drive(o, n, 0, {{B, nullptr, (size_t)32 * d}, {nullptr, F, 512}}, [=](cudaStream_t st, Arena &, int cn, void **p) {
+    return drive(o, n, 0, {{B, nullptr, (size_t)32 * d}, {nullptr, F, 512}}, [=](cudaStream_t st, Arena &, int cn, void **p, size_t) {
         DISPATCH_D(d, {
             if (decomp) LAUNCH((k_decode_batch<D, true>), prim_grid(cn), kPrimTPB, 0, st, cn, (const uint8_t *)p[0], (uint16_t *)p[1]);
             else LAUNCH((k_decode_batch<D, false>), prim_grid(cn), kPrimTPB, 0, st, cn, (const uint8_t *)p[0], (uint16_t *)p[1]);
@@ -854,7 +990,7 @@ int mlkem_b200_decode_decompress_batch(int d, size_t n, const uint8_t *B, uint16
 static int compress_impl(int d, size_t ncoef, const uint16_t *x, uint16_t *y, const mlkem_b200_opts *o, bool decomp) {
     if (ncoef % 8 != 0) return MLKEM_B200_ERR_ARG;
     if (d < 1 || d > 12) return MLKEM_B200_ERR_ARG;
-    return drive(o, ncoef / 8, 0, {{x, nullptr, 16}, {nullptr, y, 16}}, [=](cudaStream_t st, Arena &, int cn, void **p) {
+    return drive(o, ncoef / 8, 0, {{x, nullptr, 16}, {nullptr, y, 16}}, [=](cudaStream_t st, Arena &, int cn, void **p, size_t) {
         unsigned grid = cdiv(cn, kPrimTPB);
         if (grid > 148 * 32) grid = 148 * 32;
 #define CASE_D(DD)                                                                                                                        \
@@ -881,7 +1017,7 @@ int mlkem_b200_hash_batch(int which, size_t n, size_t len, const uint8_t *in, ui
     if (oo.chunk_items <= 0) oo.chunk_items = 1 << 16;
     oo.chunk_items = (oo.chunk_items + 1) & ~1;
     const int nw = (int)(len / 8);
-    return drive(&oo, n, 0, {{in, nullptr, len ? len : 1}, {nullptr, out, which == 1 ? (size_t)64 : (size_t)32}}, [=](cudaStream_t st, Arena &, int cn, void **p) {
+    return drive(&oo, n, 0, {{in, nullptr, len ? len : 1}, {nullptr, out, which == 1 ? (size_t)64 : (size_t)32}}, [=](cudaStream_t st, Arena &, int cn, void **p, size_t) {
         if (which == 0) LAUNCH((k_hash_words<kRateSha3_256, 4>), cdiv(cn, kHashTPB), kHashTPB, 0, st, cn, (const uint8_t *)p[0], nw, kSfxHash, (uint8_t *)p[1]);
         else if (which == 1) LAUNCH((k_hash_words<kRateSha3_512, 8>), cdiv(cn, kHashTPB), kHashTPB, 0, st, cn, (const uint8_t *)p[0], nw, kSfxHash, (uint8_t *)p[1]);
         else if (which == 2) LAUNCH((k_hash_words<kRateShake128, 4>), cdiv(cn, kHashTPB), kHashTPB, 0, st, cn, (const uint8_t *)p[0], nw, kSfxXof, (uint8_t *)p[1]);
@@ -915,7 +1051,7 @@ int mlkem_b200_sha3_bits_batch(size_t n, const uint8_t *msgs, size_t nbits, cons
     }
     const int rl = (int)(r / 64), nb = (int)nblocks, ob = (int)out_bytes;
     int rc = drive(o, n, 0, {{padded.data(), nullptr, nblocks * blk_bytes}, {nullptr, res.data(), out_stride}},
-                   [=](cudaStream_t st, Arena &, int cn, void **p) {
+                   [=](cudaStream_t st, Arena &, int cn, void **p, size_t) {
                        LAUNCH(k_sponge_padded, cdiv(cn, kHashTPB), kHashTPB, 0, st, cn, (const uint8_t *)p[0], nb, rl, (uint8_t *)p[1], ob);
                        return 0;
                    });
@@ -927,10 +1063,227 @@ int mlkem_b200_sha3_bits_batch(size_t n, const uint8_t *msgs, size_t nbits, cons
     return MLKEM_B200_OK;
 }
 
+// ---- resident key tables (fewer bytes per operation on the host path) ----------------------------
+// A server decapsulates many ciphertexts under few keys, and a 2400-byte dk per item is 69 % of the bytes Decaps moves
+// over PCIe.  A key table lives in device memory; keyed calls ship only the ciphertext (or message) and a 4-byte index.
+}  // extern "C"
+
+struct mlkem_b200_keys {
+    int set = 0, device = 0;
+    size_t n = 0;
+    uint8_t *dk = nullptr;   // n x DK, or nullptr for a table of encapsulation keys only
+    uint8_t *ek = nullptr;   // row i at ek + i*ek_stride (inside dk when dk != nullptr)
+    size_t ek_stride = 0;
+    uint8_t *hek = nullptr;  // n x 32: H(ek_i), computed once at load time
+};
+
+namespace {
+
+void keys_destroy(mlkem_b200_keys *k) {
+    if (!k) return;
+    DeviceGuard guard;
+    if (guard.enter(k->device) == 0) {
+        cudaDeviceSynchronize();
+        if (k->dk) {
+            cudaMemset(k->dk, 0, k->n * mlkem_b200_dk_bytes(k->set));  // decapsulation keys are secrets
+            cudaFree(k->dk);
+        } else if (k->ek) {
+            cudaFree(k->ek);
+        }
+        if (k->hek) cudaFree(k->hek);
+    }
+    delete k;
+}
+
+// Allocates the table and fills it through `fill(ctx, stream, table)`, then hashes the ek rows.
+template <class Fill>
+int keys_create(int set, size_t n, bool with_dk, const mlkem_b200_opts *o, mlkem_b200_keys **out, Fill fill) {
+    if (!out) return MLKEM_B200_ERR_ARG;
+    *out = nullptr;
+    const unsigned dkb = mlkem_b200_dk_bytes(set), ekb = mlkem_b200_ek_bytes(set), kk = k_of(set);
+    if (!dkb) return MLKEM_B200_ERR_PARAM;
+    if (n == 0 || n > 0x7FFFFFFFull / 8) {
+        snprintf(tl_error, sizeof tl_error, "key table size out of range");
+        return MLKEM_B200_ERR_ARG;
+    }
+    int dev;
+    DeviceCtx *ctx;
+    DeviceGuard guard;
+    if (int rc = acquire(o, &dev, &ctx, guard)) return rc;
+    mlkem_b200_keys *k = new mlkem_b200_keys;
+    k->set = set;
+    k->device = dev;
+    k->n = n;
+    auto fail = [&](int rc) {
+        keys_destroy(k);
+        return rc;
+    };
+    if (with_dk) {
+        if (cudaMalloc(&k->dk, n * dkb) != cudaSuccess) return fail(MLKEM_B200_ERR_CUDA);
+        k->ek = k->dk + 384 * kk;
+        k->ek_stride = dkb;
+    } else {
+        if (cudaMalloc(&k->ek, n * ekb) != cudaSuccess) return fail(MLKEM_B200_ERR_CUDA);
+        k->ek_stride = ekb;
+    }
+    if (cudaMalloc(&k->hek, n * 32) != cudaSuccess) return fail(MLKEM_B200_ERR_CUDA);
+    cudaStream_t st = (o && o->mem == MLKEM_B200_MEM_DEVICE) ? static_cast<cudaStream_t>(o->stream) : ctx->stream[0];
+    if (int rc = fill(ctx, st, k)) return fail(rc);
+    auto hash = [&]() -> int {
+        switch (set) {
+        case 512: LAUNCH((k_hash_ek_table<P512>), cdiv(n, kHashTPB), kHashTPB, 0, st, (int)n, k->ek, k->ek_stride, k->hek); break;
+        case 768: LAUNCH((k_hash_ek_table<P768>), cdiv(n, kHashTPB), kHashTPB, 0, st, (int)n, k->ek, k->ek_stride, k->hek); break;
+        default: LAUNCH((k_hash_ek_table<P1024>), cdiv(n, kHashTPB), kHashTPB, 0, st, (int)n, k->ek, k->ek_stride, k->hek); break;
+        }
+        CU(cudaStreamSynchronize(st));  // loading is a set-up call: the table is complete when it returns
+        return 0;
+    };
+    if (int rc = hash()) return fail(rc);
+    *out = k;
+    return MLKEM_B200_OK;
+}
+
+// key_index of a keyed host-memory call is checked on the host; device-memory calls clamp in the kernel (key_row).
+int check_key_index(const mlkem_b200_keys *k, size_t n, const uint32_t *idx, const mlkem_b200_opts *o) {
+    if (!idx || (o && o->mem == MLKEM_B200_MEM_DEVICE)) return 0;
+    for (size_t i = 0; i < n; i++)
+        if (idx[i] >= k->n) {
+            snprintf(tl_error, sizeof tl_error, "key_index[%zu] = %u is outside the table of %zu keys", i, idx[i], k->n);
+            return MLKEM_B200_ERR_ARG;
+        }
+    return 0;
+}
+
+// The options of a keyed call: the table decides the device.
+int keyed_opts(const mlkem_b200_keys *k, const mlkem_b200_opts *o, mlkem_b200_opts *oo) {
+    if (!k) return MLKEM_B200_ERR_ARG;
+    *oo = o ? *o : mlkem_b200_opts{-1, MLKEM_B200_MEM_HOST, nullptr, 0, 0, 0};
+    if (oo->device >= 0 && oo->device != k->device) {
+        snprintf(tl_error, sizeof tl_error, "the key table lives on device %d, the call names device %d", k->device, oo->device);
+        return MLKEM_B200_ERR_ARG;
+    }
+    oo->device = k->device;
+    if (oo->chunk_items > 0) oo->chunk_items = (oo->chunk_items + 3) & ~3;  // 4-byte indices: chunk starts stay 16-byte aligned
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mlkem_b200_keys_load(int set, size_t n_keys, const uint8_t *dk, int32_t *status, const mlkem_b200_opts *o, mlkem_b200_keys **out) {
+    if (!dk) return MLKEM_B200_ERR_ARG;
+    const unsigned dkb = mlkem_b200_dk_bytes(set);
+    const bool src_dev = o && o->mem == MLKEM_B200_MEM_DEVICE;
+    int rc = keys_create(set, n_keys, true, o, out, [&](DeviceCtx *, cudaStream_t st, mlkem_b200_keys *k) -> int {
+        CU(cudaMemcpyAsync(k->dk, dk, n_keys * dkb, src_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+        return 0;
+    });
+    if (rc || !status) return rc;
+    // the hash check of KEM_Decaps (ml_kem.c:1336-1350), once per key instead of once per ciphertext; status is HOST memory
+    mlkem_b200_opts od{(*out)->device, MLKEM_B200_MEM_DEVICE, nullptr, 0, 0, 0};
+    int32_t *d_status = nullptr;
+    DeviceGuard guard;
+    if (int r = guard.enter((*out)->device)) return r;
+    CU(cudaMalloc(&d_status, 4 * n_keys));
+    rc = mlkem_b200_check_dk_batch(set, n_keys, (*out)->dk, d_status, &od);
+    if (!rc && cudaMemcpy(status, d_status, 4 * n_keys, cudaMemcpyDeviceToHost) != cudaSuccess) rc = MLKEM_B200_ERR_CUDA;
+    cudaFree(d_status);
+    return rc;
+}
+
+int mlkem_b200_keys_load_ek(int set, size_t n_keys, const uint8_t *ek, const mlkem_b200_opts *o, mlkem_b200_keys **out) {
+    if (!ek) return MLKEM_B200_ERR_ARG;
+    const unsigned ekb = mlkem_b200_ek_bytes(set);
+    const bool src_dev = o && o->mem == MLKEM_B200_MEM_DEVICE;
+    return keys_create(set, n_keys, false, o, out, [&](DeviceCtx *, cudaStream_t st, mlkem_b200_keys *k) -> int {
+        CU(cudaMemcpyAsync(k->ek, ek, n_keys * ekb, src_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+        return 0;
+    });
+}
+
+int mlkem_b200_keys_from_seeds(int set, size_t n_keys, const uint8_t *d, const uint8_t *z, const mlkem_b200_opts *o, mlkem_b200_keys **out) {
+    if (!d || !z) return MLKEM_B200_ERR_ARG;
+    const unsigned ekb = mlkem_b200_ek_bytes(set);
+    const bool src_dev = o && o->mem == MLKEM_B200_MEM_DEVICE;
+    // KeyGen_internal on the device (ml_kem.c:1034): 64 bytes per key cross PCIe instead of 2400, and KeyGen is faster than
+    // the copy it replaces.  A scratch ek array receives KeyGen's first output (dk embeds the same bytes).
+    return keys_create(set, n_keys, true, o, out, [&](DeviceCtx *, cudaStream_t st, mlkem_b200_keys *k) -> int {
+        uint8_t *tmp = nullptr;
+        CU(cudaMalloc(&tmp, n_keys * (ekb + 64)));
+        uint8_t *dd = tmp + n_keys * ekb, *dz = dd + 32 * n_keys;
+        const cudaMemcpyKind kind = src_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+        int rc = 0;
+        if (cudaMemcpyAsync(dd, d, 32 * n_keys, kind, st) != cudaSuccess || cudaMemcpyAsync(dz, z, 32 * n_keys, kind, st) != cudaSuccess)
+            rc = MLKEM_B200_ERR_CUDA;
+        mlkem_b200_opts od{k->device, MLKEM_B200_MEM_DEVICE, st, 0, o ? o->sample_group_limit : 0, o ? o->flags : 0};
+        if (!rc) rc = mlkem_b200_keygen_batch(set, n_keys, dd, dz, tmp, k->dk, &od);
+        cudaStreamSynchronize(st);
+        cudaMemset(tmp, 0, n_keys * (ekb + 64));
+        cudaFree(tmp);
+        return rc;
+    });
+}
+
+size_t mlkem_b200_keys_count(const mlkem_b200_keys *k) { return k ? k->n : 0; }
+void mlkem_b200_keys_free(mlkem_b200_keys *k) { keys_destroy(k); }
+
+int mlkem_b200_encaps_keyed_batch(const mlkem_b200_keys *k, size_t n, const uint32_t *key_index, const uint8_t *m, uint8_t *c, uint8_t *K,
+                                  const mlkem_b200_opts *o) {
+    mlkem_b200_opts oo;
+    if (int rc = keyed_opts(k, o, &oo)) return rc;
+    if (int rc = check_key_index(k, n, key_index, &oo)) return rc;
+    const int gl = group_limit_of(&oo);
+    const bool fips = fips_of(&oo), has_idx = key_index != nullptr;
+    const uint32_t nk = (uint32_t)k->n;
+    std::vector<Buf> bufs = {{m, nullptr, 32}, {nullptr, c, mlkem_b200_ct_bytes(k->set)}, {nullptr, K, 32}};
+    if (has_idx) bufs.push_back({key_index, nullptr, 4});
+    DISPATCH_SET(k->set, return drive(&oo, n, ws_bytes_per_item<P>(), bufs, [=](cudaStream_t st, Arena &ws, int cn, void **p, size_t first) {
+                     KeySel ks{has_idx ? (const uint32_t *)p[3] : nullptr, (uint32_t)(first % nk), nk};
+                     return enqueue_encaps_keyed<P>(st, ws, cn, k->ek, k->ek_stride, k->hek, ks, (const uint8_t *)p[0], (uint8_t *)p[1],
+                                                    (uint8_t *)p[2], gl, fips);
+                 }));
+    return MLKEM_B200_ERR_PARAM;
+}
+
+int mlkem_b200_decaps_keyed_batch(const mlkem_b200_keys *k, size_t n, const uint32_t *key_index, const uint8_t *c, uint8_t *K,
+                                  const mlkem_b200_opts *o) {
+    mlkem_b200_opts oo;
+    if (int rc = keyed_opts(k, o, &oo)) return rc;
+    if (!k->dk) {
+        snprintf(tl_error, sizeof tl_error, "the key table holds encapsulation keys only");
+        return MLKEM_B200_ERR_ARG;
+    }
+    if (int rc = check_key_index(k, n, key_index, &oo)) return rc;
+    const int gl = group_limit_of(&oo);
+    const bool fips = fips_of(&oo), has_idx = key_index != nullptr;
+    const uint32_t nk = (uint32_t)k->n;
+    std::vector<Buf> bufs = {{c, nullptr, mlkem_b200_ct_bytes(k->set)}, {nullptr, K, 32}};
+    if (has_idx) bufs.push_back({key_index, nullptr, 4});
+    DISPATCH_SET(k->set, return drive(&oo, n, ws_bytes_per_item<P>(), bufs, [=](cudaStream_t st, Arena &ws, int cn, void **p, size_t first) {
+                     KeySel ks{has_idx ? (const uint32_t *)p[2] : nullptr, (uint32_t)(first % nk), nk};
+                     return enqueue_decaps<P>(st, ws, cn, k->dk, ks, (const uint8_t *)p[0], (uint8_t *)p[1], gl, fips);
+                 }));
+    return MLKEM_B200_ERR_PARAM;
+}
+
+// The copy-only ceiling of a host-memory call: the same chunking, staging slots, streams and copy sizes as a real call
+// with these buffers, but no kernels in between (bench.py's e2e.copy_ceiling).
+int mlkem_b200_copy_probe(size_t n, int n_in, const void *const *in, const size_t *in_item_bytes, int n_out, void *const *out,
+                          const size_t *out_item_bytes, const mlkem_b200_opts *o) {
+    if (o && o->mem == MLKEM_B200_MEM_DEVICE) return MLKEM_B200_ERR_ARG;
+    std::vector<Buf> bufs;
+    for (int i = 0; i < n_in; i++) bufs.push_back({in[i], nullptr, in_item_bytes[i]});
+    for (int i = 0; i < n_out; i++) bufs.push_back({nullptr, out[i], out_item_bytes[i]});
+    if (bufs.empty()) return MLKEM_B200_ERR_ARG;
+    return drive(o, n, 0, bufs, [](cudaStream_t, Arena &, int, void **, size_t) { return 0; });
+}
+
 int mlkem_b200_tables(uint16_t zeta[128], uint16_t gamma[128]) {
     int dev;
     DeviceCtx *ctx;
-    if (int rc = acquire(nullptr, &dev, &ctx)) return rc;
+    DeviceGuard guard;
+    if (int rc = acquire(nullptr, &dev, &ctx, guard)) return rc;
     TwiddleTables t;
     CU(cudaMemcpyFromSymbol(&t, c_tw, sizeof t));
     for (int i = 0; i < 128; i++) {

@@ -7,8 +7,8 @@
 //   2. Keccak-f[1600] with one sponge per THREAD (25 lanes as 50 x 32-bit registers, funnel-shift
 //      rotates), plus absorb/squeeze helpers for SHA3-256 / SHA3-512 / SHAKE128,
 //   3. polynomial routines with one polynomial per WARP: NTT / inverse NTT (8 coefficients per lane,
-//      register butterflies + one shared-memory transpose + one shuffle layer), NTT-domain
-//      multiply-accumulate, Compress/Decompress and ByteEncode/ByteDecode.
+//      three register-local passes with two transposes through a swizzled shared-memory scratch, no
+//      shuffles), NTT-domain multiply-accumulate, Compress/Decompress and ByteEncode/ByteDecode.
 //
 // Bit-exactness contract: results equal the reference rsjahnige/CRYSTALS-Kyber `ml_kem.c`
 // (see SURVEY.md section 0 for where it differs from FIPS 203).  File:line citations below refer to
@@ -24,7 +24,7 @@ constexpr uint32_t kQ = 3329;
 constexpr uint32_t kFullMask = 0xFFFFFFFFu;
 
 // ------------------------------------------------------------------------------------------------
-// Constant tables (filled once per device by the host, see mlkem_tables.cu)
+// Constant tables (filled once per device by the host: build_tables() / acquire() in mlkem_b200.cu)
 // ------------------------------------------------------------------------------------------------
 // zeta_i = 17^BitRev7(i) mod q (ml_kem.c:300-307) as {w, floor(w * 2^16 / q)} for Shoup multiplication.
 // gamma_i = 17^(2 BitRev7(i) + 1) mod q (ml_kem.c:424-433), same packing.
@@ -366,7 +366,8 @@ __device__ __forceinline__ void ct_bfly(uint32_t &a, uint32_t &b, uint2 z) {
     a = a + t;
 }
 
-// ml_kem.c:287 NTT.  x in layout A with values < 4096 (values >= q are treated as residues).  Returns the
+// ml_kem.c:287 NTT.  x in layout A with values < 4096 (values >= q are treated as residues here; callers that can see
+// such values -- the stand-alone k_ntt_batch -- switch to ntt_warp_exact, which reproduces the reference).  Returns the
 // transform in layout C, canonical.  `scratch` = this warp's 512-byte scratch; tw from load_lane_twiddles<FMA>.
 template <bool FMA = false>
 __device__ __forceinline__ void ntt_warp(uint32_t x[8], uint16_t *scratch, int lane, const LaneTwiddles &tw) {
@@ -403,6 +404,50 @@ __device__ __forceinline__ void ntt_warp(uint32_t x[8], uint16_t *scratch, int l
         for (int r = 0; r < 2; r++) ct_bfly<FMA>(x[4 * h + r], x[4 * h + r + 2], tw.z2[h]);
 #pragma unroll
     for (int r = 0; r < 8; r++) x[r] = FMA ? canon_fma(x[r]) : canon16(x[r]);  // < 4096 + 14q < 2^16
+}
+
+// ml_kem.c:309-320 restated literally, for polynomials that contain coefficients in [q, 4096).  The reference's update
+//     t = zeta f[j+len] % q;   f[j+len] = f[j] >= t ? f[j] - t : q - (t - f[j]);   f[j] = (f[j] + t) % q
+// reduces the sum but not the difference: a 12-bit value >= q in the f[j] role survives as f[j] - t, so some outputs
+// are the canonical residue plus q.  Which ones depends on the whole chain of comparisons, hence this separate path,
+// taken (warp-uniformly) only when such an input is present -- never on the KEM path, whose NTT inputs are CBD samples
+// and Decompress outputs, all < q.
+__device__ __forceinline__ void ct_bfly_exact(uint32_t &a, uint32_t &b, uint2 z) {
+    const uint32_t t = csubq(mul_shoup(b, z)), lo = a;  // b < 4096
+    b = lo >= t ? lo - t : kQ - (t - lo);
+    a = canon16(lo + t);                                // lo + t < 4096 + q
+}
+__device__ __forceinline__ void ntt_warp_exact(uint32_t x[8], uint16_t *scratch, int lane) {
+    LaneTwiddles tw;
+    load_lane_twiddles<false>(tw, lane);
+#pragma unroll
+    for (int r = 0; r < 4; r++) ct_bfly_exact(x[r], x[r + 4], uniform_z<false>(1));
+#pragma unroll
+    for (int h = 0; h < 2; h++)
+#pragma unroll
+        for (int r = 0; r < 2; r++) ct_bfly_exact(x[4 * h + r], x[4 * h + r + 2], uniform_z<false>(2 + h));
+#pragma unroll
+    for (int h = 0; h < 4; h++) ct_bfly_exact(x[2 * h], x[2 * h + 1], uniform_z<false>(4 + h));
+    store_scratch_A(x, scratch, lane);
+    __syncwarp();
+    load_scratch_B(x, scratch, lane);
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < 4; r++) ct_bfly_exact(x[r], x[r + 4], tw.z16);
+#pragma unroll
+    for (int h = 0; h < 2; h++)
+#pragma unroll
+        for (int r = 0; r < 2; r++) ct_bfly_exact(x[4 * h + r], x[4 * h + r + 2], tw.z8[h]);
+#pragma unroll
+    for (int h = 0; h < 4; h++) ct_bfly_exact(x[2 * h], x[2 * h + 1], tw.z4[h]);
+    store_scratch_B(x, scratch, lane);
+    __syncwarp();
+    load_scratch_C(x, scratch, lane);
+    __syncwarp();
+#pragma unroll
+    for (int h = 0; h < 2; h++)
+#pragma unroll
+        for (int r = 0; r < 2; r++) ct_bfly_exact(x[4 * h + r], x[4 * h + r + 2], tw.z2[h]);
 }
 
 // Gentleman-Sande butterfly for the inverse transform (ml_kem.c:359-373): a' = a + b, b' = zeta (b - a).

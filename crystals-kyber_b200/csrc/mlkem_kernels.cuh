@@ -33,6 +33,19 @@ using P512 = ParamSet<2, 3, 2, 10, 4>;
 using P768 = ParamSet<3, 2, 2, 10, 4>;
 using P1024 = ParamSet<4, 2, 2, 11, 5>;
 
+// Which key an item uses.  Unkeyed calls: item i reads row i of the key array it was given.  Keyed calls (the resident
+// key tables of mlkem_b200_keys_*): row index[i], or row (base + i) % nkeys when the caller passed no index array
+// (keys reused cyclically, base = global index of the chunk's first item).
+struct KeySel {
+    const uint32_t *index;
+    uint32_t base, nkeys;
+};
+__device__ __forceinline__ size_t key_row(const KeySel &k, int item) {
+    if (k.index) return min(__ldg(k.index + item), k.nkeys - 1u);  // clamped: memory safety for device-memory callers
+    if (k.nkeys) return (k.base + (uint32_t)item) % k.nkeys;
+    return (size_t)item;
+}
+
 constexpr int kHashTPB = 128;   // threads per block of the thread-per-item hash kernels
 constexpr int kNoiseTPB = 128;  // threads (= sponges) per block of k_noise
 constexpr int kSlotWords = 129; // shared-memory words per sampled polynomial slot (odd: conflict-free per-thread writes)
@@ -121,6 +134,37 @@ __global__ void __launch_bounds__(kHashTPB) k_encaps_HG(int n, const uint8_t *__
     }
 }
 
+// Keyed Encaps front: h = H(ek) was computed once when the key table was loaded (k_hash_ek_table), so only
+// (K, r) = G(m || h) is left (ml_kem.c:1116-1124).
+__global__ void __launch_bounds__(kHashTPB) k_encaps_G_keyed(int n, const uint8_t *__restrict__ hek, KeySel keys, const uint8_t *__restrict__ m,
+                                                             uint8_t *__restrict__ Kout, uint8_t *__restrict__ r) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Lane h[4], mm[4], a[25];
+    const uint8_t *hp = hek + 32 * key_row(keys, i);
+#pragma unroll
+    for (int w = 0; w < 4; w++) {
+        mm[w] = load_lane(m + 32 * (size_t)i + 8 * w);
+        h[w] = load_lane(hp + 8 * w);
+    }
+    hash_G_64(a, mm, h);
+#pragma unroll
+    for (int w = 0; w < 4; w++) {
+        store_lane(Kout + 32 * (size_t)i + 8 * w, a[w]);
+        store_lane(r + 32 * (size_t)i + 8 * w, a[4 + w]);
+    }
+}
+// h[i] = H(ek_i) for the rows of a key table (ek_i at ek + i*ek_stride): run once per table.
+template <class P>
+__global__ void __launch_bounds__(kHashTPB) k_hash_ek_table(int n, const uint8_t *__restrict__ ek, size_t ek_stride, uint8_t *__restrict__ hek) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Lane h[4];
+    hash_H_ek<P>(ek + ek_stride * i, h);
+#pragma unroll
+    for (int w = 0; w < 4; w++) store_lane(hek + 32 * (size_t)i + 8 * w, h[w]);
+}
+
 // Plain H over ek (used by the public-wrapper hash check, ml_kem.c:1336-1350): status[i] = -5 on mismatch.
 template <class P>
 __global__ void __launch_bounds__(kHashTPB) k_check_dk_hash(int n, const uint8_t *__restrict__ dk, int *__restrict__ status) {
@@ -170,12 +214,12 @@ __global__ void __launch_bounds__(kHashTPB) k_mask_keys(int n, const int *__rest
 
 // Decaps (ml_kem.c:1181-1193): (K', r') = G(m' || h), h = dk[768k+32 .. +32).
 template <class P>
-__global__ void __launch_bounds__(kHashTPB) k_decaps_G(int n, const uint8_t *__restrict__ mprime, const uint8_t *__restrict__ dk,
+__global__ void __launch_bounds__(kHashTPB) k_decaps_G(int n, const uint8_t *__restrict__ mprime, const uint8_t *__restrict__ dk, KeySel keys,
                                                        uint8_t *__restrict__ Kr) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     Lane h[4], mm[4], a[25];
-    const uint8_t *hp = dk + (size_t)P::DK * i + 768 * P::K + 32;
+    const uint8_t *hp = dk + (size_t)P::DK * key_row(keys, i) + 768 * P::K + 32;
 #pragma unroll
     for (int w = 0; w < 4; w++) {
         mm[w] = load_lane(mprime + 32 * (size_t)i + 8 * w);
@@ -190,12 +234,12 @@ __global__ void __launch_bounds__(kHashTPB) k_decaps_G(int n, const uint8_t *__r
 // branch-free select between K' and Kbar on the re-encryption mismatch flag.  The reference's compare is
 // an early-exit loop; the selected key is the same.
 template <class P, int RATE = kRateShake128>
-__global__ void __launch_bounds__(kHashTPB) k_decaps_J_select(int n, const uint8_t *__restrict__ dk, const uint8_t *__restrict__ c,
+__global__ void __launch_bounds__(kHashTPB) k_decaps_J_select(int n, const uint8_t *__restrict__ dk, KeySel keys, const uint8_t *__restrict__ c,
                                                               const uint8_t *__restrict__ Kr, const uint32_t *__restrict__ flags,
                                                               uint8_t *__restrict__ Kout) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const uint8_t *z = dk + (size_t)P::DK * i + 768 * P::K + 64;
+    const uint8_t *z = dk + (size_t)P::DK * key_row(keys, i) + 768 * P::K + 64;
     const uint8_t *ci = c + (size_t)P::C * i;
     Lane a[25];
     // RATE 21 = SHAKE128 (the reference's J, D2); RATE 17 = SHAKE256 (FIPS 203)
@@ -583,8 +627,9 @@ enum MatvecMode { kModeKeyGen = 0, kModeEncrypt = 1, kModeEncryptCompare = 2 };
 struct MatvecArgs {
     int n;
     int group_limit;
-    const uint8_t *rho;      // 32-byte matrix seed of item i at rho + i*rho_stride
+    const uint8_t *rho;      // 32-byte matrix seed of item i at rho + key_row(keys, i)*rho_stride
     size_t rho_stride;
+    KeySel keys;
     const uint16_t *vec;     // s^ (KeyGen) or y^ (Encrypt): item i, polynomial j at vec + i*vec_stride + 256 j
     size_t vec_stride;
     const uint16_t *add16;   // KeyGen: e^ as uint16, same addressing as vec (polynomial index = row)
@@ -600,7 +645,7 @@ struct MatvecArgs {
     int *defer_list;         // rows (item * K + row) left to the clean-up pass; nullptr for the list kernel = all rows
     int *defer_count;        // number of entries in defer_list (zeroed by the host before the fused kernel)
 #ifdef MLKEM_B200_EXPERIMENT
-    int experiment;          // build/libmlkem_b200_exp.so only (make exp): 1 = skip phase 2, 2 = skip parsing, 4 = phase 2 twice
+    int experiment;          // build/libmlkem_b200_exp.so only (make exp): 1 = skip phase 2, 2 = skip parsing, 4 = phase 2 twice, 8 = skip phase 1
 #endif
 };
 
@@ -808,13 +853,15 @@ __global__ void __launch_bounds__(32 * P::K) k_sample_matvec(MatvecArgs g) {
         const bool active = item < g.n;
         Lane rho[4];
 #pragma unroll
-        for (int w = 0; w < 4; w++) rho[w] = active ? load_lane(g.rho + g.rho_stride * item + 8 * w) : Lane{0u, 0u};
+        for (int w = 0; w < 4; w++) rho[w] = active ? load_lane(g.rho + g.rho_stride * key_row(g.keys, item) + 8 * w) : Lane{0u, 0u};
         // KeyGen: A[row][col] = SampleNTT(rho || col || row)      (ml_kem.c:686-693)
         // Encrypt: At[row][col] = SampleNTT(rho || row || col)    (ml_kem.c:817-823, stored transposed)
         const uint32_t b32 = MODE == kModeKeyGen ? col : row, b33 = MODE == kModeKeyGen ? row : col;
         // threads beyond the batch sample a dummy sponge into their own slot (the straight-line sampler has no idle mode)
 #ifdef MLKEM_B200_EXPERIMENT
-        const bool complete = sample_ntt_three_blocks(rho, b32, b33, reinterpret_cast<uint16_t *>(s_slots + kSlotWords * tid), g.experiment);
+        // bit 8: phase 2 alone, on whatever the slots hold (what does the polynomial arithmetic cost when no Keccak runs next to it?)
+        const bool complete = (g.experiment & 8) ? true
+                                                 : sample_ntt_three_blocks(rho, b32, b33, reinterpret_cast<uint16_t *>(s_slots + kSlotWords * tid), g.experiment);
 #else
         const bool complete = sample_ntt_three_blocks(rho, b32, b33, reinterpret_cast<uint16_t *>(s_slots + kSlotWords * tid));
 #endif
@@ -874,7 +921,7 @@ __global__ void __launch_bounds__(32 * P::K) k_sample_matvec_list(MatvecArgs g) 
             if (col == 0) s_gg[grp] = gg;
             Lane rho[4];
 #pragma unroll
-            for (int w = 0; w < 4; w++) rho[w] = active ? load_lane(g.rho + g.rho_stride * item + 8 * w) : Lane{0u, 0u};
+            for (int w = 0; w < 4; w++) rho[w] = active ? load_lane(g.rho + g.rho_stride * key_row(g.keys, item) + 8 * w) : Lane{0u, 0u};
             uint32_t b32 = MODE == kModeKeyGen ? col : row, b33 = MODE == kModeKeyGen ? row : col;
             sample_ntt_thread(rho, b32, b33, reinterpret_cast<uint16_t *>(s_slots + kSlotWords * tid), active, g.group_limit);
         }
@@ -900,8 +947,9 @@ constexpr bool kPrimPipe = MLKEM_B200_PRIM_PIPE;
 
 struct EncVArgs {
     int n;
-    const uint8_t *ek;      // item i at ek + i*ek_stride: ByteEncode12(t^) (384 K bytes) || rho
+    const uint8_t *ek;      // item i at ek + key_row(keys, i)*ek_stride: ByteEncode12(t^) (384 K bytes) || rho
     size_t ek_stride;
+    KeySel keys;
     const uint16_t *yhat;   // y^ polynomials, item stride in uint16
     size_t yhat_stride;
     const uint32_t *addc;   // noise codes, e2 is row K
@@ -920,55 +968,86 @@ __device__ __forceinline__ void stage_row(uint8_t *dst, const uint8_t *src, int 
     for (int i = lane; i < bytes / 16; i += 32) d4[i] = __ldg(s4 + i);
 }
 
-// Asynchronous global -> shared copies (cp.async, LDGSTS): the persistent warps of k_encrypt_v / k_decrypt fetch the
-// inputs of their NEXT item while they work on the current one (two buffers per warp), so the global-load latency is
-// off the critical path without spending registers on the prefetch.
-__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
-    uint32_t s = (uint32_t)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem_src) : "memory");
+// Bulk asynchronous global -> shared copies (cp.async.bulk, the 1-D form of the TMA engine, completion signalled on an
+// mbarrier): the persistent warps of k_encrypt_v / k_decrypt fetch the inputs of their NEXT item while they work on the
+// current one (two buffers and two mbarriers per warp).  ONE lane issues one instruction per contiguous row -- 1 to 2 KB
+// each -- where round 1 had every lane issue 16-byte cp.async copies (140 per item in k_decrypt), and the copy engine,
+// not the LSU pipe, moves the data.  Sources and destinations are 16-byte aligned and sizes are multiples of 16 (every
+// per-item size on this path is).
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void stage_row_async(uint8_t *dst, const uint8_t *src, int bytes, int lane) {
-    for (int i = lane; i < bytes / 16; i += 32) cp_async16(dst + 16 * i, src + 16 * i);
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
 }
 
 // v = InverseNTT(t^ . y^) + e2 + Decompress_1(m)  (ml_kem.c:867-880); c2 = ByteEncode_dv(Compress_dv(v)) (:899-904).
 // One item per warp; every lane owns 8 consecutive coefficients (= 12 bytes of each ByteEncode12 row).
 // COMPARE: OR the mismatch against the received ciphertext into flags instead of storing.
+// (Blocks per SM: 8 would cap the kernel at 64 registers, which it no longer fits without spilling 8 of them; 7 = 72 registers.)
+#ifndef MLKEM_B200_ENCV_BLOCKS
+#define MLKEM_B200_ENCV_BLOCKS 7
+#endif
 template <class P, bool COMPARE>
-__global__ void __launch_bounds__(kWarpTPB, 8) k_encrypt_v(EncVArgs g) {
+__global__ void __launch_bounds__(kWarpTPB, MLKEM_B200_ENCV_BLOCKS) k_encrypt_v(EncVArgs g) {
     constexpr int K = P::K, NW = kWarpTPB / 32;
     constexpr int kRowsBytes = 384 * K, kVecBytes = 512 * K, kBufBytes = kRowsBytes + kVecBytes + 16;  // t^ rows | y^ | slack
     __shared__ __align__(16) uint16_t s_scratch[NW * kScratchU16];
     __shared__ __align__(16) uint8_t s_in[NW * 2 * kBufBytes];
     __shared__ __align__(16) uint8_t s_stage[NW * 32 * P::DV];
+    __shared__ __align__(8) uint64_t s_bar[NW * 2];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint16_t *scratch = s_scratch + warp * kScratchU16;
     uint8_t *inbuf = s_in + warp * 2 * kBufBytes;
     uint8_t *stage = s_stage + warp * 32 * P::DV;
+    uint64_t *bar = s_bar + 2 * warp;
+    if (lane == 0) {
+        mbar_init(bar, 1);
+        mbar_init(bar + 1, 1);
+        mbar_fence_init();
+    }
+    __syncwarp();
     uint2 gam[4];
 #pragma unroll
     for (int i = 0; i < 4; i++) gam[i] = lane_gamma(4 * lane + i);
     LaneTwiddles tw;
     load_lane_twiddles_inv<kFmaPipe>(tw, lane);
     const uint32_t pw = nibble_weight(lane & 7);
-    auto fetch = [&](int item, uint8_t *buf) {
-        stage_row_async(buf, g.ek + g.ek_stride * item, kRowsBytes, lane);
-        stage_row_async(buf + kRowsBytes, reinterpret_cast<const uint8_t *>(g.yhat + g.yhat_stride * item), kVecBytes, lane);
+    auto fetch = [&](int item, int b) {  // lane 0 only: the t^ rows of the key and the y^ polynomials of the item
+        uint8_t *buf = inbuf + b * kBufBytes;
+        mbar_expect_tx(bar + b, kRowsBytes + kVecBytes);
+        bulk_g2s(buf, g.ek + g.ek_stride * key_row(g.keys, item), kRowsBytes, bar + b);
+        bulk_g2s(buf + kRowsBytes, g.yhat + g.yhat_stride * item, kVecBytes, bar + b);
     };
     const int stride = gridDim.x * NW;
     int item = blockIdx.x * NW + warp, cur = 0;
-    if (item < g.n) fetch(item, inbuf);
-    cp_async_commit();
+    uint32_t phase = 0;  // bit b = parity the next wait on buffer b expects
+    if (item < g.n && lane == 0) fetch(item, 0);
     for (; item < g.n; item += stride, cur ^= 1) {  // persistent warps
-        if (item + stride < g.n) fetch(item + stride, inbuf + (cur ^ 1) * kBufBytes);
-        cp_async_commit();
-        cp_async_wait<1>();  // all but the newest group have landed: this item's buffer is complete
-        __syncwarp();
+        // the other buffer was last read in the previous iteration, which ended with __syncwarp()
+        if (item + stride < g.n && lane == 0) fetch(item + stride, cur ^ 1);
+        mbar_wait(bar + cur, (phase >> cur) & 1u);  // this item's rows have landed
+        phase ^= 1u << cur;
         const uint8_t *rows = inbuf + cur * kBufBytes;
         const uint16_t *yv = reinterpret_cast<const uint16_t *>(rows + kRowsBytes);
         // e2 codes and the message bits are needed after the inverse transform: issue their loads now
@@ -1020,40 +1099,48 @@ __global__ void __launch_bounds__(kWarpTPB, 8) k_encrypt_v(EncVArgs g) {
         }
         __syncwarp();
     }
-    cp_async_wait<0>();
 }
 
 // ml_kem.c:942 PKE_Decrypt: m' = ByteEncode_1(Compress_1(v - InverseNTT(s^ . NTT(u)))).  One item per warp; the
 // ciphertext and the ByteEncode12 rows of s^ are staged in shared memory with 128-bit loads.
 template <class P>
-__global__ void __launch_bounds__(kWarpTPB) k_decrypt(int n, const uint8_t *__restrict__ dk, size_t dk_stride,
+__global__ void __launch_bounds__(kWarpTPB) k_decrypt(int n, const uint8_t *__restrict__ dk, size_t dk_stride, KeySel keys,
                                                       const uint8_t *__restrict__ c, uint8_t *__restrict__ mout) {
     constexpr int K = P::K, NW = kWarpTPB / 32;
     constexpr int kSkBytes = 384 * K, kBufBytes = P::C + kSkBytes + 32;  // ciphertext | s^ rows | slack
     __shared__ __align__(16) uint16_t s_scratch[NW * kScratchU16];
     __shared__ __align__(16) uint8_t s_in[NW * 2 * kBufBytes];
+    __shared__ __align__(8) uint64_t s_bar[NW * 2];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint16_t *scratch = s_scratch + warp * kScratchU16;
     uint8_t *inbuf = s_in + warp * 2 * kBufBytes;
+    uint64_t *bar = s_bar + 2 * warp;
+    if (lane == 0) {
+        mbar_init(bar, 1);
+        mbar_init(bar + 1, 1);
+        mbar_fence_init();
+    }
+    __syncwarp();
     uint2 gam[4];
 #pragma unroll
     for (int i = 0; i < 4; i++) gam[i] = lane_gamma(4 * lane + i);
     LaneTwiddles tw, twi;
     load_lane_twiddles<kPrimPipe>(tw, lane);
     load_lane_twiddles_inv<kPrimPipe>(twi, lane);
-    auto fetch = [&](int item, uint8_t *buf) {
-        stage_row_async(buf, c + (size_t)P::C * item, P::C, lane);
-        stage_row_async(buf + P::C, dk + dk_stride * item, kSkBytes, lane);
+    auto fetch = [&](int item, int b) {  // lane 0 only: the ciphertext of the item and the s^ rows of its key
+        uint8_t *buf = inbuf + b * kBufBytes;
+        mbar_expect_tx(bar + b, P::C + kSkBytes);
+        bulk_g2s(buf, c + (size_t)P::C * item, P::C, bar + b);
+        bulk_g2s(buf + P::C, dk + dk_stride * key_row(keys, item), kSkBytes, bar + b);
     };
     const int stride = gridDim.x * NW;
     int item = blockIdx.x * NW + warp, cur = 0;
-    if (item < n) fetch(item, inbuf);
-    cp_async_commit();
+    uint32_t phase = 0;  // bit b = parity the next wait on buffer b expects
+    if (item < n && lane == 0) fetch(item, 0);
     for (; item < n; item += stride, cur ^= 1) {  // persistent warps
-        if (item + stride < n) fetch(item + stride, inbuf + (cur ^ 1) * kBufBytes);
-        cp_async_commit();
-        cp_async_wait<1>();
-        __syncwarp();
+        if (item + stride < n && lane == 0) fetch(item + stride, cur ^ 1);
+        mbar_wait(bar + cur, (phase >> cur) & 1u);
+        phase ^= 1u << cur;
         const uint8_t *ct = inbuf + cur * kBufBytes, *sk = ct + P::C;
         uint32_t acc[8];
 #pragma unroll
@@ -1089,7 +1176,6 @@ __global__ void __launch_bounds__(kWarpTPB) k_decrypt(int n, const uint8_t *__re
         if (lane < 8) reinterpret_cast<uint32_t *>(mout + 32 * (size_t)item)[lane] = myword;
         __syncwarp();
     }
-    cp_async_wait<0>();
 }
 
 // =================================================================================================
@@ -1121,7 +1207,11 @@ __global__ void __launch_bounds__(kPrimTPB) k_ntt_batch(int n, const uint16_t *_
 #pragma unroll
             for (int r = 0; r < 8; r++) nxt[r] = __ldg(in + 256 * (p + stride) + idxA(lane, r));
         }
-        ntt_warp<kPrimPipe>(x, scratch, lane, tw);
+        bool big = false;
+#pragma unroll
+        for (int r = 0; r < 8; r++) big |= x[r] >= kQ;
+        if (__any_sync(kFullMask, big)) ntt_warp_exact(x, scratch, lane);  // a coefficient in [q, 4096): ml_kem.c:317-318 literally
+        else ntt_warp<kPrimPipe>(x, scratch, lane, tw);
         store_layoutC_global(x, lane, out + 256 * p);
     }
 }

@@ -29,7 +29,10 @@ SIGNATURES = {
     "mlkem_b200_device_count": (C.c_int, []),
     "mlkem_b200_synchronize": (C.c_int, [C.c_int, C.c_void_p]),
     "mlkem_b200_host_alloc": (C.c_void_p, [C.c_size_t]),
+    "mlkem_b200_host_alloc_wc": (C.c_void_p, [C.c_size_t]),
     "mlkem_b200_host_free": (None, [C.c_void_p]),
+    "mlkem_b200_copy_probe": (C.c_int, [C.c_size_t, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.c_int, C.POINTER(C.c_void_p),
+                                        C.POINTER(C.c_size_t), _PO]),
     "mlkem_b200_release": (None, [C.c_int]),
     "mlkem_b200_ek_bytes": (C.c_uint, [C.c_int]),
     "mlkem_b200_dk_bytes": (C.c_uint, [C.c_int]),
@@ -39,6 +42,13 @@ SIGNATURES = {
     "mlkem_b200_encaps_batch": (C.c_int, [C.c_int, C.c_size_t, _P8, _P8, _P8, _P8, _PO]),
     "mlkem_b200_decaps_batch": (C.c_int, [C.c_int, C.c_size_t, _P8, _P8, _P8, _PO]),
     "mlkem_b200_check_dk_batch": (C.c_int, [C.c_int, C.c_size_t, _P8, C.c_void_p, _PO]),
+    "mlkem_b200_keys_load": (C.c_int, [C.c_int, C.c_size_t, _P8, C.c_void_p, _PO, C.POINTER(C.c_void_p)]),
+    "mlkem_b200_keys_load_ek": (C.c_int, [C.c_int, C.c_size_t, _P8, _PO, C.POINTER(C.c_void_p)]),
+    "mlkem_b200_keys_from_seeds": (C.c_int, [C.c_int, C.c_size_t, _P8, _P8, _PO, C.POINTER(C.c_void_p)]),
+    "mlkem_b200_keys_count": (C.c_size_t, [C.c_void_p]),
+    "mlkem_b200_keys_free": (None, [C.c_void_p]),
+    "mlkem_b200_encaps_keyed_batch": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, _P8, _P8, _P8, _PO]),
+    "mlkem_b200_decaps_keyed_batch": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, _P8, _P8, _PO]),
     "mlkem_b200_kem_keygen_batch": (C.c_int, [C.c_int, C.c_size_t, _P8, _P8, _PO]),
     "mlkem_b200_kem_encaps_batch": (C.c_int, [C.c_int, C.c_size_t, _P8, C.c_size_t, _P8, _P8, _PO]),
     "mlkem_b200_kem_decaps_batch": (C.c_int, [C.c_int, C.c_size_t, _P8, C.c_size_t, _P8, C.c_size_t, _P8, C.c_void_p, _PO]),

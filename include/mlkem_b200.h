@@ -28,6 +28,11 @@
  *   MLKEM_B200_MEM_DEVICE  pointers are device memory on opts.device, 16-byte aligned.  The call enqueues
  *                          its kernels on opts.stream (NULL = the CUDA default stream) and returns
  *                          without synchronising; the caller orders its own work through that stream.
+ *
+ * Threads, streams and devices.  Calls may come from several host threads and name different streams or devices: the
+ * per-device workspaces are shared, each use is fenced by an event, so calls on different streams never touch each
+ * other's intermediates (they serialise on the workspace instead).  A call switches the calling thread's current
+ * CUDA device to opts.device only for its own duration.
  */
 #ifndef MLKEM_B200_H
 #define MLKEM_B200_H
@@ -65,7 +70,8 @@ typedef struct mlkem_b200_opts {
  *
  * Tuning knobs read from the environment (defaults in brackets; measured on B200 in profiles/experiments_r01.txt):
  *   MLKEM_B200_CHUNK       items per chunk of a device-memory call [262144]; workspace is about 4.3 KB per item and stream
- *   MLKEM_B200_STREAMS     internal streams the chunks of a device-memory call take turns on [4]
+ *   MLKEM_B200_STREAMS     internal streams the chunks of a device-memory call take turns on [4]; read once at load time,
+ *                          mlkem_b200_set_streams() overrides it
  *   MLKEM_B200_HOST_CHUNK  items per staged chunk of a host-memory call [65536]
  *   MLKEM_B200_HOST_SLOTS  staging slots (H2D / kernels / D2H overlap) of a host-memory call [3] */
 
@@ -82,6 +88,7 @@ unsigned long long mlkem_b200_launch_count(void); /* kernels launched by this li
 int mlkem_b200_device_count(void);
 int mlkem_b200_synchronize(int device, void *stream);
 void *mlkem_b200_host_alloc(size_t bytes);        /* pinned host memory (cudaHostAlloc) */
+void *mlkem_b200_host_alloc_wc(size_t bytes);     /* the same, write-combined: for INPUT buffers the CPU only ever fills sequentially */
 void mlkem_b200_host_free(void *p);
 void mlkem_b200_release(int device);              /* drop the cached workspace of a device */
 
@@ -105,6 +112,38 @@ int mlkem_b200_decaps_batch(int param_set, size_t n, const uint8_t *dk, const ui
                             const mlkem_b200_opts *opts);
 /* The dk hash check of KEM_Decaps, ml_kem.c:1336-1350: status[i] = 0 or -5.  status: n x int32. */
 int mlkem_b200_check_dk_batch(int param_set, size_t n, const uint8_t *dk, int32_t *status, const mlkem_b200_opts *opts);
+
+/* ---- resident key tables: keyed Encaps / Decaps (fewer bytes per operation) ---------------- */
+
+/* A decapsulation key is 768k+96 bytes and a server uses the same few keys for every ciphertext it receives, so on
+ * the host path mlkem_b200_decaps_batch spends 69 % of its PCIe bytes re-sending keys.  A key table is loaded into the
+ * memory of opts->device once; the keyed calls then take only the ciphertexts (or messages) and a 4-byte key index
+ * per item.  Results are bit-identical to the unkeyed calls with dk[i] = table[key_index[i]] (Decaps_internal,
+ * ml_kem.c:1136; Encaps_internal, ml_kem.c:1093).  Loading is a set-up call: it returns when the table is complete. */
+typedef struct mlkem_b200_keys mlkem_b200_keys;
+
+/* n_keys decapsulation keys (n_keys x (768k+96) bytes, host or device memory per opts->mem).  status (HOST memory, may
+ * be NULL): the dk hash check of KEM_Decaps (ml_kem.c:1336-1350) once per key, status[i] = 0 or -5; failing keys are
+ * loaded all the same (Decaps_internal does not validate either). */
+int mlkem_b200_keys_load(int param_set, size_t n_keys, const uint8_t *dk, int32_t *status, const mlkem_b200_opts *opts,
+                         mlkem_b200_keys **out);
+/* n_keys encapsulation keys only (n_keys x (384k+32) bytes): a table for mlkem_b200_encaps_keyed_batch. */
+int mlkem_b200_keys_load_ek(int param_set, size_t n_keys, const uint8_t *ek, const mlkem_b200_opts *opts,
+                            mlkem_b200_keys **out);
+/* The same table as mlkem_b200_keys_load(KeyGen_internal(d, z)) built on the device from the 64-byte seeds
+ * (ml_kem.c:1034): 64 instead of 2400 bytes per key cross PCIe.  d, z: n_keys x 32. */
+int mlkem_b200_keys_from_seeds(int param_set, size_t n_keys, const uint8_t *d, const uint8_t *z,
+                               const mlkem_b200_opts *opts, mlkem_b200_keys **out);
+size_t mlkem_b200_keys_count(const mlkem_b200_keys *keys);
+void mlkem_b200_keys_free(mlkem_b200_keys *keys); /* wipes the decapsulation keys, then frees the table */
+
+/* Encaps_internal / Decaps_internal for n items, item i under key key_index[i] of the table.  key_index: n x uint32 in
+ * the same memory space as the other buffers, or NULL = key (i mod n_keys).  Host-memory calls reject an index >=
+ * n_keys (MLKEM_B200_ERR_ARG); device-memory calls clamp it to n_keys-1.  opts->device must be -1 or the table's. */
+int mlkem_b200_encaps_keyed_batch(const mlkem_b200_keys *keys, size_t n, const uint32_t *key_index, const uint8_t *m,
+                                  uint8_t *c, uint8_t *K, const mlkem_b200_opts *opts);
+int mlkem_b200_decaps_keyed_batch(const mlkem_b200_keys *keys, size_t n, const uint32_t *key_index, const uint8_t *c,
+                                  uint8_t *K, const mlkem_b200_opts *opts);
 
 /* ---- batched forms of the public wrappers: entropy + input checks around the internal algorithms --------- */
 
@@ -135,10 +174,14 @@ int mlkem_b200_pke_decrypt_batch(int param_set, size_t n, const uint8_t *dk_pke,
 
 /* ---- ring arithmetic ------------------------------------------------------------------------------- */
 
-/* NTT, ml_kem.c:287.  Coefficients must be < q (any 12-bit value is reduced mod q first; the reference's
- * behaviour for values in [q, 4096) differs and is not reproduced -- it never occurs on the KEM path). */
+/* NTT, ml_kem.c:287, for any 12-bit coefficients.  For inputs in [q, 4096) the reference's butterfly leaves the
+ * difference f[j] - t unreduced (ml_kem.c:317-318), so some outputs are the residue plus q: reproduced bit for bit
+ * (a polynomial that contains such a coefficient takes a literal restatement of the reference's update). */
 int mlkem_b200_ntt_batch(size_t n, const uint16_t *f, uint16_t *f_hat, const mlkem_b200_opts *opts);
-/* InverseNTT, ml_kem.c:336 (includes the multiplication by 3303). */
+/* InverseNTT, ml_kem.c:336 (includes the multiplication by 3303).  Coefficients are taken as residues mod q and the
+ * output is canonical, which is the reference's result whenever its arithmetic is defined: for a pair with
+ * f[j] - f[j+len] > q (needs f[j] >= q) the reference's `Q - (t - f[j+len])` wraps in a 24-bit field and the
+ * following product overflows a signed int (ml_kem.c:366-368) -- undefined behaviour, not reproduced. */
 int mlkem_b200_intt_batch(size_t n, const uint16_t *f_hat, uint16_t *f, const mlkem_b200_opts *opts);
 /* MultiplyNTTs, ml_kem.c:415 (128 BaseCaseMultiply, ml_kem.c:395).  Operands may be any 12-bit value. */
 int mlkem_b200_multiply_ntts_batch(size_t n, const uint16_t *f_hat, const uint16_t *g_hat, uint16_t *h_hat,
@@ -198,6 +241,12 @@ void mlkem_b200_profile(int enable);
  * the default. */
 void mlkem_b200_set_streams(int n);
 int mlkem_b200_profile_report(char *buf, int cap);
+
+/* Copy-only ceiling of a host-memory call: moves the same bytes through the same chunking, staging slots and streams as
+ * a real call with n items and these buffers (n_in inputs copied to the device, n_out outputs copied back), with no
+ * kernels in between.  bench.py times it next to the real calls (e2e.copy_ceiling). */
+int mlkem_b200_copy_probe(size_t n, int n_in, const void *const *in, const size_t *in_item_bytes, int n_out,
+                          void *const *out, const size_t *out_item_bytes, const mlkem_b200_opts *opts);
 
 /* INT32 roofline denominators of the current device, measured now: sustained thread-operations per second
  * of out[0] LOP3, out[1] SHF (alu pipe), out[2] IMAD (fma pipe), out[3] LOP3+IMAD interleaved (both pipes),

@@ -41,6 +41,11 @@ def ref_vectors():
 
 
 @pytest.fixture(scope="session")
+def ref_vectors_r02():
+    return json.load(open(os.path.join(GOLDEN, "ref_vectors_r02.json")))
+
+
+@pytest.fixture(scope="session")
 def archive_stdout():
     return json.load(open(os.path.join(GOLDEN, "archive_stdout.json")))
 
