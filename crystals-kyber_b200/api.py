@@ -78,7 +78,7 @@ class MLKEM:
             import torch
 
             dev = next(a for a, _ in ins if _is_torch(a)).device
-            tdt = {np.uint8: torch.uint8, np.uint16: torch.uint16, np.int32: torch.int32}
+            tdt = {np.uint8: torch.uint8, np.uint16: torch.uint16, np.int32: torch.int32, np.uint32: torch.uint32}
             iarr = []
             for a, dt in ins:
                 if a is None:
@@ -126,6 +126,30 @@ class MLKEM:
     def check_dk(self, ps, dk):
         n = self._count(dk, sizes(ps)["dk"])
         return self._call("mlkem_b200_check_dk_batch", (ps, n), [(dk, np.uint8)], [((n,), np.int32)])
+
+    # ------------------------------------------------------------------ the reference's cell layout (one byte per uint32 cell)
+    def keygen_cells(self, ps, d, z):
+        sz, n = sizes(ps), self._count(d, 32)
+        return self._call("mlkem_b200_keygen_cells_batch", (ps, n), [(d, np.uint32), (z, np.uint32)],
+                          [((n, sz["ek"]), np.uint32), ((n, sz["dk"]), np.uint32)])
+
+    def encaps_cells(self, ps, ek, m):
+        sz, n = sizes(ps), self._count(m, 32)
+        return self._call("mlkem_b200_encaps_cells_batch", (ps, n), [(ek, np.uint32), (m, np.uint32)],
+                          [((n, sz["c"]), np.uint32), ((n, 32), np.uint32)])
+
+    def decaps_cells(self, ps, dk, c):
+        sz = sizes(ps)
+        n = self._count(c, sz["c"])
+        return self._call("mlkem_b200_decaps_cells_batch", (ps, n), [(dk, np.uint32), (c, np.uint32)], [((n, 32), np.uint32)])
+
+    def cells_from_bytes(self, b):
+        n = self._count(b, 1)
+        return self._call("mlkem_b200_cells_from_bytes", (n,), [(b, np.uint8)], [(tuple(b.shape), np.uint32)])
+
+    def cells_to_bytes(self, c):
+        n = self._count(c, 1)
+        return self._call("mlkem_b200_cells_to_bytes", (n,), [(c, np.uint32)], [(tuple(c.shape), np.uint8)])
 
     # ------------------------------------------------------------------ resident key tables (keyed Encaps / Decaps)
     def _src_opts(self, *arrays, device=None):

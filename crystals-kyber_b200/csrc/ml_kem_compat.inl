@@ -1,9 +1,10 @@
 // ml_kem_compat.inl -- the reference-signature API (include/ml_kem.h) on top of the batched C ABI.
 //
-// Every function converts between the reference's stride-4 union arrays (one value per 4-byte cell,
-// ml_kem.h:35-38 / ml_kem.c:20-23 in /root/reference) and the dense buffers of mlkem_b200.h, then runs a
-// batch of ONE on the GPU.  Only layout conversion, length checks, the random-byte source and the error
-// reporting live on the host; every arithmetic result comes from a CUDA kernel.
+// Every function runs a batch of ONE on the GPU.  KeyGen_internal / Encaps_internal / Decaps_internal (and through them
+// KEM_KeyGen / KEM_Encaps / KEM_Decaps) hand the reference's stride-4 union arrays (one value per 4-byte cell,
+// ml_kem.h:35-38 / ml_kem.c:20-23 in /root/reference) to the batched cell-layout entry points, which convert on the
+// device; the primitives convert on the host.  Only layout conversion, length checks, the random-byte source and the
+// error reporting live on the host; every arithmetic result comes from a CUDA kernel.
 //
 // Included at the end of mlkem_b200.cu (single translation unit).
 #include "../../include/ml_kem.h"
@@ -29,6 +30,11 @@ void cuda_failure(const char *where, int rc) {
     fprintf(stderr, "ERROR: mlkem_b200 - %s: rc=%d %s\n", where, rc, mlkem_b200_last_error());
     ml_errno = rc == MLKEM_B200_ERR_CUDA ? -10 : rc;
 }
+
+// `union byte` is one 4-byte cell (include/ml_kem.h, D5): the batched cell-layout entry points take it as uint32_t.
+static_assert(sizeof(union byte) == 4, "cell size");
+const uint32_t *cells_of(const union byte *b) { return reinterpret_cast<const uint32_t *>(b); }
+uint32_t *cells_of(union byte *b) { return reinterpret_cast<uint32_t *>(b); }
 
 std::vector<uint8_t> dense_bytes(const union byte *b, size_t n) {
     std::vector<uint8_t> v(n);
@@ -107,22 +113,29 @@ struct PKE keygen_common(const struct PARAMS *params, const union byte *d, const
         cuda_failure("unsupported PARAMS", MLKEM_B200_ERR_PARAM);
         return out;
     }
-    std::vector<uint8_t> dd = dense_bytes(d, 32), zz;
     unsigned ekl = mlkem_b200_ek_bytes(set), dkl = z ? mlkem_b200_dk_bytes(set) : mlkem_b200_dkpke_bytes(set);
-    std::vector<uint8_t> ek(ekl), dk(dkl);
-    int rc;
     if (z) {
-        zz = dense_bytes(z, 32);
-        rc = mlkem_b200_keygen_batch(set, 1, dd.data(), zz.data(), ek.data(), dk.data(), nullptr);
+        // the caller's cell arrays go to the device as they are; the layout conversion is a kernel (mlkem_b200_*_cells_batch)
+        union byte *ekc = (union byte *)calloc(ekl, sizeof(union byte)), *dkc = (union byte *)calloc(dkl, sizeof(union byte));
+        int rc = mlkem_b200_keygen_cells_batch(set, 1, cells_of(d), cells_of(z), cells_of(ekc), cells_of(dkc), nullptr);
+        if (rc) {
+            free(ekc);
+            free(dkc);
+            cuda_failure("keygen", rc);
+            return out;
+        }
+        out.ek = ekc;
+        out.dk = dkc;
     } else {
-        rc = mlkem_b200_pke_keygen_batch(set, 1, dd.data(), ek.data(), dk.data(), nullptr);
+        std::vector<uint8_t> dd = dense_bytes(d, 32), ek(ekl), dk(dkl);
+        int rc = mlkem_b200_pke_keygen_batch(set, 1, dd.data(), ek.data(), dk.data(), nullptr);
+        if (rc) {
+            cuda_failure("keygen", rc);
+            return out;
+        }
+        out.ek = wide_bytes(ek.data(), ekl);
+        out.dk = wide_bytes(dk.data(), dkl);
     }
-    if (rc) {
-        cuda_failure("keygen", rc);
-        return out;
-    }
-    out.ek = wide_bytes(ek.data(), ekl);
-    out.dk = wide_bytes(dk.data(), dkl);
     out.ek_len = ekl;
     out.dk_len = dkl;
     return out;
@@ -313,15 +326,15 @@ struct KEM Encaps_internal(const struct PARAMS *params, const union byte *ek, co
         cuda_failure("unsupported PARAMS", MLKEM_B200_ERR_PARAM);
         return out;
     }
-    unsigned ekl = mlkem_b200_ek_bytes(set), cl = mlkem_b200_ct_bytes(set);
-    std::vector<uint8_t> e = dense_bytes(ek, ekl), mm = dense_bytes(m, 32), c(cl), K(32);
-    int rc = mlkem_b200_encaps_batch(set, 1, e.data(), mm.data(), c.data(), K.data(), nullptr);
+    unsigned cl = mlkem_b200_ct_bytes(set);
+    union byte *cc = (union byte *)calloc(cl, sizeof(union byte));
+    int rc = mlkem_b200_encaps_cells_batch(set, 1, cells_of(ek), cells_of(m), cells_of(cc), cells_of(out.K), nullptr);
     if (rc) {
+        free(cc);
         cuda_failure("Encaps_internal", rc);
         return out;
     }
-    for (int i = 0; i < 32; i++) out.K[i].e = K[i];
-    out.c = wide_bytes(c.data(), cl);
+    out.c = cc;
     out.c_len = cl;
     return out;
 }
@@ -331,14 +344,14 @@ union byte *Decaps_internal(const struct PARAMS *params, const union byte *dk, c
         cuda_failure("unsupported PARAMS", MLKEM_B200_ERR_PARAM);
         return NULL;
     }
-    unsigned dl = mlkem_b200_dk_bytes(set), cl = mlkem_b200_ct_bytes(set);
-    std::vector<uint8_t> d = dense_bytes(dk, dl), cc = dense_bytes(c, cl), K(32);
-    int rc = mlkem_b200_decaps_batch(set, 1, d.data(), cc.data(), K.data(), nullptr);
+    union byte *K = (union byte *)calloc(32, sizeof(union byte));
+    int rc = mlkem_b200_decaps_cells_batch(set, 1, cells_of(dk), cells_of(c), cells_of(K), nullptr);
     if (rc) {
+        free(K);
         cuda_failure("Decaps_internal", rc);
         return NULL;
     }
-    return wide_bytes(K.data(), 32);
+    return K;
 }
 
 // ---- L6 public wrappers --------------------------------------------------------------------------------

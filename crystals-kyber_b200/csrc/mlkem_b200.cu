@@ -455,7 +455,20 @@ struct Buf {
     const void *in;   // non-null for inputs
     void *out;        // non-null for outputs
     size_t item_bytes;
+    bool cells = false;  // the caller's array is in the reference's cell layout: one byte per 4-byte `union byte` (ml_kem.h:35-38)
 };
+
+// Cell layout <-> dense bytes, on the device (the stride-4 conversion off the host's critical path).
+int launch_narrow(cudaStream_t st, const void *cells, void *dense, size_t bytes) {
+    const size_t nw = bytes / 4;
+    if (nw) LAUNCH(k_cells_to_bytes, cdiv(nw, 256), 256, 0, st, nw, (const uint4 *)cells, (uint32_t *)dense);
+    return 0;
+}
+int launch_widen(cudaStream_t st, const void *dense, void *cells, size_t bytes) {
+    const size_t nw = bytes / 4;
+    if (nw) LAUNCH(k_bytes_to_cells, cdiv(nw, 256), 256, 0, st, nw, (const uint32_t *)dense, (uint4 *)cells);
+    return 0;
+}
 
 bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
@@ -479,7 +492,7 @@ int drive(const mlkem_b200_opts *o, size_t n, size_t ws_per_item, std::vector<Bu
     if (int rc = acquire(o, &dev, &ctx, guard)) return rc;
     // Calls from several host threads are serialised per device while they enqueue.  The slots (workspace + staging
     // buffer) are shared between calls and may be used from different streams: see DeviceCtx::ev_slot.
-    std::lock_guard<std::mutex> call_lock(ctx->call_mutex);
+    std::unique_lock<std::mutex> call_lock(ctx->call_mutex);
     const bool on_device = o && o->mem == MLKEM_B200_MEM_DEVICE;
     static const int env_chunk = env_int("MLKEM_B200_CHUNK", 0);  // tuning knobs
     static const int env_hchunk = env_int("MLKEM_B200_HOST_CHUNK", 0);
@@ -490,6 +503,9 @@ int drive(const mlkem_b200_opts *o, size_t n, size_t ws_per_item, std::vector<Bu
     if (chunk > n) chunk = n;
     const size_t nchunks = (n + chunk - 1) / chunk;
     std::vector<void *> ptrs(bufs.size());
+    size_t cell_dense_per_item = 0;  // dense images of cell-layout buffers live in the workspace (device path) / staging buffer (host path)
+    for (auto &b : bufs)
+        if (b.cells) cell_dense_per_item += (b.item_bytes + 15) & ~size_t(15);
 
     if (on_device) {
         for (auto &b : bufs)
@@ -515,7 +531,9 @@ int drive(const mlkem_b200_opts *o, size_t n, size_t ws_per_item, std::vector<Bu
         {
             std::lock_guard<std::mutex> lock(g_mutex);
             for (int k = 0; k < nstreams; k++)
-                if (int rc = ensure_buffer(&ctx->ws[k], &ctx->ws_bytes[k], chunk * ws_per_item + kWsSlack, ctx->ev_slot[k])) return rc;
+                if (int rc = ensure_buffer(&ctx->ws[k], &ctx->ws_bytes[k], chunk * (ws_per_item + cell_dense_per_item) + kWsSlack + 256 * bufs.size(),
+                                           ctx->ev_slot[k]))
+                    return rc;
         }
         const bool fork = nstreams > 1;
         if (fork) CU(cudaEventRecord(ctx->ev_fork, st));
@@ -527,13 +545,22 @@ int drive(const mlkem_b200_opts *o, size_t n, size_t ws_per_item, std::vector<Bu
         int rc = 0;
         for (size_t ci = 0; ci < nch && !rc; ci++) {
             size_t i0 = ci * chunk, cn = (i0 + chunk <= n) ? chunk : n - i0;
-            for (size_t b = 0; b < bufs.size(); b++) {
-                const uint8_t *base = static_cast<const uint8_t *>(bufs[b].in ? bufs[b].in : bufs[b].out);
-                ptrs[b] = const_cast<uint8_t *>(base) + i0 * bufs[b].item_bytes;
-            }
             const int k = fork ? (int)(ci % nstreams) : 0;
+            cudaStream_t sk = fork ? ctx->stream[k] : st;
             Arena arena(ctx->ws[k]);
-            rc = run(fork ? ctx->stream[k] : st, arena, (int)cn, ptrs.data(), i0);
+            for (size_t b = 0; b < bufs.size() && !rc; b++) {
+                const uint8_t *base = static_cast<const uint8_t *>(bufs[b].in ? bufs[b].in : bufs[b].out);
+                if (!bufs[b].cells) {
+                    ptrs[b] = const_cast<uint8_t *>(base) + i0 * bufs[b].item_bytes;
+                } else {  // dense image in the workspace; inputs are narrowed now, outputs widened after the pipeline
+                    ptrs[b] = arena.take<uint8_t>(cn * bufs[b].item_bytes);
+                    if (bufs[b].in) rc = launch_narrow(sk, base + 4 * i0 * bufs[b].item_bytes, ptrs[b], cn * bufs[b].item_bytes);
+                }
+            }
+            if (!rc) rc = run(sk, arena, (int)cn, ptrs.data(), i0);
+            for (size_t b = 0; b < bufs.size() && !rc; b++)
+                if (bufs[b].cells && bufs[b].out)
+                    rc = launch_widen(sk, ptrs[b], static_cast<uint8_t *>(bufs[b].out) + 4 * i0 * bufs[b].item_bytes, cn * bufs[b].item_bytes);
         }
         // also on the error path: whatever was enqueued is joined back into the caller's stream and the slots are marked
         for (int k = 0; k < nstreams; k++) {
@@ -552,7 +579,7 @@ int drive(const mlkem_b200_opts *o, size_t n, size_t ws_per_item, std::vector<Bu
     // host memory: stage each chunk through device buffers, rotating over the staging slots / streams so that the
     // copies of one chunk overlap the kernels of the other
     size_t io_per_item = 0;
-    for (auto &b : bufs) io_per_item += (b.item_bytes + 15) & ~size_t(15);
+    for (auto &b : bufs) io_per_item += ((b.item_bytes + 15) & ~size_t(15)) * (b.cells ? 5 : 1);  // cells: 4x image + dense image
     const int nslots = nchunks > 1 ? (int)std::min<size_t>(host_slots, nchunks) : 1;
     {
         std::lock_guard<std::mutex> lock(g_mutex);
@@ -567,25 +594,42 @@ int drive(const mlkem_b200_opts *o, size_t n, size_t ws_per_item, std::vector<Bu
         cudaStream_t st = ctx->stream[s];
         size_t i0 = ci * chunk, cn = (i0 + chunk <= n) ? chunk : n - i0;
         Arena io(ctx->io[s]);
+        std::vector<uint8_t *> wide(bufs.size(), nullptr);  // device image of a cell-layout buffer (4 bytes per byte)
         for (size_t b = 0; b < bufs.size(); b++) {
-            ptrs[b] = io.take<uint8_t>(chunk * bufs[b].item_bytes);
-            if (bufs[b].in)
-                CU(cudaMemcpyAsync(ptrs[b], static_cast<const uint8_t *>(bufs[b].in) + i0 * bufs[b].item_bytes, cn * bufs[b].item_bytes,
-                                   cudaMemcpyHostToDevice, st));
+            const size_t ib = bufs[b].item_bytes, scale = bufs[b].cells ? 4 : 1;
+            ptrs[b] = io.take<uint8_t>(chunk * ib);
+            uint8_t *land = (uint8_t *)ptrs[b];
+            if (bufs[b].cells) land = wide[b] = io.take<uint8_t>(4 * chunk * ib);
+            if (bufs[b].in) {
+                CU(cudaMemcpyAsync(land, static_cast<const uint8_t *>(bufs[b].in) + scale * i0 * ib, scale * cn * ib, cudaMemcpyHostToDevice, st));
+                if (bufs[b].cells)
+                    if (int rc = launch_narrow(st, land, ptrs[b], cn * ib)) return rc;
+            }
         }
         Arena arena(ctx->ws[s]);
         if (int rc = run(st, arena, (int)cn, ptrs.data(), i0)) return rc;
         for (size_t b = 0; b < bufs.size(); b++)
-            if (bufs[b].out)
-                CU(cudaMemcpyAsync(static_cast<uint8_t *>(bufs[b].out) + i0 * bufs[b].item_bytes, ptrs[b], cn * bufs[b].item_bytes,
-                                   cudaMemcpyDeviceToHost, st));
+            if (bufs[b].out) {
+                const size_t ib = bufs[b].item_bytes, scale = bufs[b].cells ? 4 : 1;
+                const uint8_t *src = (const uint8_t *)ptrs[b];
+                if (bufs[b].cells) {
+                    if (int rc = launch_widen(st, ptrs[b], wide[b], cn * ib)) return rc;
+                    src = wide[b];
+                }
+                CU(cudaMemcpyAsync(static_cast<uint8_t *>(bufs[b].out) + scale * i0 * ib, src, scale * cn * ib, cudaMemcpyDeviceToHost, st));
+            }
         return 0;
     };
     int rc = 0;
     for (size_t ci = 0; ci < nchunks && !rc; ci++) rc = chunk_of(ci);
+    for (int s = 0; s < nslots; s++) cudaEventRecord(ctx->ev_slot[s], ctx->stream[s]);
+    // Enqueueing is over: the next call may start filling the slots behind this one (it waits on ev_slot), so that the
+    // D2H tail of this call overlaps the H2D head of the next.
+    call_lock.unlock();
+    // MLKEM_B200_FLAG_ASYNC: return now; the caller keeps its (pinned) buffers untouched until mlkem_b200_synchronize().
+    if (!rc && o && (o->flags & MLKEM_B200_FLAG_ASYNC)) return MLKEM_B200_OK;
     // also on the error path: nothing may still be writing into the caller's buffers when the call returns
     for (int s = 0; s < nslots; s++) {
-        cudaEventRecord(ctx->ev_slot[s], ctx->stream[s]);
         cudaError_t e = cudaStreamSynchronize(ctx->stream[s]);
         if (e != cudaSuccess && !rc) {
             snprintf(tl_error, sizeof tl_error, "cudaStreamSynchronize failed: %s", cudaGetErrorString(e));
@@ -1061,6 +1105,54 @@ int mlkem_b200_sha3_bits_batch(size_t n, const uint8_t *msgs, size_t nbits, cons
         if (d % 8) out[i * out_bytes + out_bytes - 1] &= (uint8_t)((1u << (d % 8)) - 1);
     }
     return MLKEM_B200_OK;
+}
+
+// ---- the same algorithms on arrays in the reference's cell layout (ml_kem.h:35-38), converted on the device -----------
+int mlkem_b200_keygen_cells_batch(int set, size_t n, const uint32_t *d, const uint32_t *z, uint32_t *ek, uint32_t *dk, const mlkem_b200_opts *o) {
+    const int gl = group_limit_of(o);
+    const bool fips = fips_of(o);
+    DISPATCH_SET(set, return drive(o, n, ws_bytes_per_item<P>(), {{d, nullptr, 32, true}, {z, nullptr, 32, true}, {nullptr, ek, P::EK, true}, {nullptr, dk, P::DK, true}},
+                                   [=](cudaStream_t st, Arena &ws, int cn, void **p, size_t) {
+                                       return enqueue_keygen<P>(st, ws, cn, (const uint8_t *)p[0], (const uint8_t *)p[1], (uint8_t *)p[2], (uint8_t *)p[3], gl, fips);
+                                   }));
+    return MLKEM_B200_ERR_PARAM;
+}
+int mlkem_b200_encaps_cells_batch(int set, size_t n, const uint32_t *ek, const uint32_t *m, uint32_t *c, uint32_t *K, const mlkem_b200_opts *o) {
+    const int gl = group_limit_of(o);
+    const bool fips = fips_of(o);
+    DISPATCH_SET(set, return drive(o, n, ws_bytes_per_item<P>(), {{ek, nullptr, P::EK, true}, {m, nullptr, 32, true}, {nullptr, c, P::C, true}, {nullptr, K, 32, true}},
+                                   [=](cudaStream_t st, Arena &ws, int cn, void **p, size_t) {
+                                       return enqueue_encaps<P>(st, ws, cn, (const uint8_t *)p[0], (const uint8_t *)p[1], (uint8_t *)p[2], (uint8_t *)p[3], gl, fips);
+                                   }));
+    return MLKEM_B200_ERR_PARAM;
+}
+int mlkem_b200_decaps_cells_batch(int set, size_t n, const uint32_t *dk, const uint32_t *c, uint32_t *K, const mlkem_b200_opts *o) {
+    const int gl = group_limit_of(o);
+    const bool fips = fips_of(o);
+    DISPATCH_SET(set, return drive(o, n, ws_bytes_per_item<P>(), {{dk, nullptr, P::DK, true}, {c, nullptr, P::C, true}, {nullptr, K, 32, true}},
+                                   [=](cudaStream_t st, Arena &ws, int cn, void **p, size_t) {
+                                       return enqueue_decaps<P>(st, ws, cn, (const uint8_t *)p[0], KeySel{}, (const uint8_t *)p[1], (uint8_t *)p[2], gl, fips);
+                                   }));
+    return MLKEM_B200_ERR_PARAM;
+}
+// Layout conversion alone (n_bytes a multiple of 4): dense bytes <-> cells, host or device memory.
+int mlkem_b200_cells_from_bytes(size_t n_bytes, const uint8_t *bytes, uint32_t *cells, const mlkem_b200_opts *o) {
+    if (n_bytes % 4) return MLKEM_B200_ERR_ARG;
+    mlkem_b200_opts oo = o ? *o : mlkem_b200_opts{-1, MLKEM_B200_MEM_HOST, nullptr, 0, 0, 0};
+    if (oo.chunk_items <= 0) oo.chunk_items = 1 << 22;  // items are single words here
+    return drive(&oo, n_bytes / 4, 0, {{bytes, nullptr, 4}, {nullptr, cells, 4, true}}, [=](cudaStream_t st, Arena &, int cn, void **p, size_t) {
+        CU(cudaMemcpyAsync(p[1], p[0], (size_t)cn * 4, cudaMemcpyDeviceToDevice, st));
+        return 0;
+    });
+}
+int mlkem_b200_cells_to_bytes(size_t n_bytes, const uint32_t *cells, uint8_t *bytes, const mlkem_b200_opts *o) {
+    if (n_bytes % 4) return MLKEM_B200_ERR_ARG;
+    mlkem_b200_opts oo = o ? *o : mlkem_b200_opts{-1, MLKEM_B200_MEM_HOST, nullptr, 0, 0, 0};
+    if (oo.chunk_items <= 0) oo.chunk_items = 1 << 22;
+    return drive(&oo, n_bytes / 4, 0, {{cells, nullptr, 4, true}, {nullptr, bytes, 4}}, [=](cudaStream_t st, Arena &, int cn, void **p, size_t) {
+        CU(cudaMemcpyAsync(p[1], p[0], (size_t)cn * 4, cudaMemcpyDeviceToDevice, st));
+        return 0;
+    });
 }
 
 // ---- resident key tables (fewer bytes per operation on the host path) ----------------------------

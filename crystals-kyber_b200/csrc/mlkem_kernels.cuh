@@ -51,6 +51,25 @@ constexpr int kNoiseTPB = 128;  // threads (= sponges) per block of k_noise
 constexpr int kSlotWords = 129; // shared-memory words per sampled polynomial slot (odd: conflict-free per-thread writes)
 
 // =================================================================================================
+// Reference cell layout <-> dense bytes
+// =================================================================================================
+// The reference keeps one byte per 4-byte `union byte` cell (ml_kem.h:35-38; value in the low 8 bits, upper bits ignored on
+// input -- D5).  Thread = four cells = one dense 32-bit word: a 128-bit access on the cell side, a 32-bit one on the
+// dense side, both coalesced.  HBM-bound (20 bytes moved per 4 payload bytes).
+__global__ void __launch_bounds__(256) k_cells_to_bytes(size_t nwords, const uint4 *__restrict__ cells, uint32_t *__restrict__ dense) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nwords) return;
+    const uint4 c = __ldg(cells + i);
+    dense[i] = (c.x & 0xFFu) | ((c.y & 0xFFu) << 8) | ((c.z & 0xFFu) << 16) | (c.w << 24);
+}
+__global__ void __launch_bounds__(256) k_bytes_to_cells(size_t nwords, const uint32_t *__restrict__ dense, uint4 *__restrict__ cells) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nwords) return;
+    const uint32_t w = __ldg(dense + i);
+    cells[i] = make_uint4(w & 0xFFu, (w >> 8) & 0xFFu, (w >> 16) & 0xFFu, w >> 24);
+}
+
+// =================================================================================================
 // Hash kernels: one item per thread
 // =================================================================================================
 

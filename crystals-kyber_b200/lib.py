@@ -42,6 +42,11 @@ SIGNATURES = {
     "mlkem_b200_encaps_batch": (C.c_int, [C.c_int, C.c_size_t, _P8, _P8, _P8, _P8, _PO]),
     "mlkem_b200_decaps_batch": (C.c_int, [C.c_int, C.c_size_t, _P8, _P8, _P8, _PO]),
     "mlkem_b200_check_dk_batch": (C.c_int, [C.c_int, C.c_size_t, _P8, C.c_void_p, _PO]),
+    "mlkem_b200_keygen_cells_batch": (C.c_int, [C.c_int, C.c_size_t, _P8, _P8, _P8, _P8, _PO]),
+    "mlkem_b200_encaps_cells_batch": (C.c_int, [C.c_int, C.c_size_t, _P8, _P8, _P8, _P8, _PO]),
+    "mlkem_b200_decaps_cells_batch": (C.c_int, [C.c_int, C.c_size_t, _P8, _P8, _P8, _PO]),
+    "mlkem_b200_cells_from_bytes": (C.c_int, [C.c_size_t, _P8, C.c_void_p, _PO]),
+    "mlkem_b200_cells_to_bytes": (C.c_int, [C.c_size_t, C.c_void_p, _P8, _PO]),
     "mlkem_b200_keys_load": (C.c_int, [C.c_int, C.c_size_t, _P8, C.c_void_p, _PO, C.POINTER(C.c_void_p)]),
     "mlkem_b200_keys_load_ek": (C.c_int, [C.c_int, C.c_size_t, _P8, _PO, C.POINTER(C.c_void_p)]),
     "mlkem_b200_keys_from_seeds": (C.c_int, [C.c_int, C.c_size_t, _P8, _P8, _PO, C.POINTER(C.c_void_p)]),

@@ -81,6 +81,11 @@ typedef struct mlkem_b200_opts {
  * ML-KEM (pinned in tests against an independent FIPS 203 implementation), NOT those of the reference. */
 #define MLKEM_B200_FLAG_FIPS203 1
 #define MLKEM_B200_ERR_MODULUS (-4)   /* FIPS mode only: an encapsulation key has a coefficient >= q (ml_errno -4) */
+/* Host-memory calls only: return as soon as the copies and kernels are enqueued on the library's streams instead of
+ * waiting for the results.  The buffers must be pinned (mlkem_b200_host_alloc) and stay untouched until
+ * mlkem_b200_synchronize(device, NULL) returns.  Consecutive asynchronous calls pipeline through the staging slots:
+ * the device-to-host tail of one overlaps the host-to-device head of the next. */
+#define MLKEM_B200_FLAG_ASYNC 2
 
 const char *mlkem_b200_version(void);
 const char *mlkem_b200_last_error(void);          /* text of the last CUDA error seen by this thread */
@@ -144,6 +149,23 @@ int mlkem_b200_encaps_keyed_batch(const mlkem_b200_keys *keys, size_t n, const u
                                   uint8_t *c, uint8_t *K, const mlkem_b200_opts *opts);
 int mlkem_b200_decaps_keyed_batch(const mlkem_b200_keys *keys, size_t n, const uint32_t *key_index, const uint8_t *c,
                                   uint8_t *K, const mlkem_b200_opts *opts);
+
+/* ---- the reference's cell layout, batched ------------------------------------------------------ */
+
+/* KeyGen_internal / Encaps_internal / Decaps_internal on arrays in the layout the reference itself uses: one byte per
+ * 4-byte `union byte` cell (ml_kem.h:35-38; uint32_t here, layout-compatible), item-major, value in the low 8 bits,
+ * upper bits ignored on input and zero on output.  Same sizes in CELLS as the dense calls have in bytes.  The
+ * conversion to and from dense bytes runs on the device inside the chunk pipeline (host-memory calls ship the cells as
+ * they are: four PCIe bytes per payload byte -- the price of not touching every byte on the host). */
+int mlkem_b200_keygen_cells_batch(int param_set, size_t n, const uint32_t *d, const uint32_t *z, uint32_t *ek, uint32_t *dk,
+                                  const mlkem_b200_opts *opts);
+int mlkem_b200_encaps_cells_batch(int param_set, size_t n, const uint32_t *ek, const uint32_t *m, uint32_t *c, uint32_t *K,
+                                  const mlkem_b200_opts *opts);
+int mlkem_b200_decaps_cells_batch(int param_set, size_t n, const uint32_t *dk, const uint32_t *c, uint32_t *K,
+                                  const mlkem_b200_opts *opts);
+/* The conversion alone, n_bytes (a multiple of 4) payload bytes: for callers that keep dense copies around. */
+int mlkem_b200_cells_from_bytes(size_t n_bytes, const uint8_t *bytes, uint32_t *cells, const mlkem_b200_opts *opts);
+int mlkem_b200_cells_to_bytes(size_t n_bytes, const uint32_t *cells, uint8_t *bytes, const mlkem_b200_opts *opts);
 
 /* ---- batched forms of the public wrappers: entropy + input checks around the internal algorithms --------- */
 

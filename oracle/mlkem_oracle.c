@@ -74,17 +74,20 @@ ORC_API void orc_keccak_f1600(uint64_t a[25]) {
     static const unsigned rho[25] = {0,  1,  62, 28, 27, 36, 44, 6,  55, 20, 3,  10, 43,
                                      25, 39, 41, 45, 15, 21, 8,  18, 2,  61, 56, 14};
     if (!orc_rc_ready) orc_rc_init();
+    /* pi as a table: lane x + 5y moves to y + 5((2x + 3y) mod 5) (sha3.c:88); the index arithmetic is hoisted out of
+     * the rounds so that the whole-batch parity tests (2^20 keys on the GPU box's host cores) finish in seconds */
+    static const unsigned char pi[25] = {0, 10, 20, 5, 15, 16, 1, 11, 21, 6, 7, 17, 2, 12, 22, 23, 8, 18, 3, 13, 14, 24, 9, 19, 4};
+    static const unsigned char n1[5] = {1, 2, 3, 4, 0}, n2[5] = {2, 3, 4, 0, 1}, p1[5] = {4, 0, 1, 2, 3};
     for (int round = 0; round < 24; round++) {
         uint64_t c[5], b[25];
         for (int x = 0; x < 5; x++) c[x] = a[x] ^ a[x + 5] ^ a[x + 10] ^ a[x + 15] ^ a[x + 20];
         for (int x = 0; x < 5; x++) { /* theta, sha3.c:15 */
-            uint64_t d = c[(x + 4) % 5] ^ orc_rotl(c[(x + 1) % 5], 1);
+            uint64_t d = c[p1[x]] ^ orc_rotl(c[n1[x]], 1);
             for (int y = 0; y < 25; y += 5) a[y + x] ^= d;
         }
-        for (int x = 0; x < 5; x++) /* rho + pi, sha3.c:53,88 */
-            for (int y = 0; y < 5; y++) b[y + 5 * ((2 * x + 3 * y) % 5)] = orc_rotl(a[x + 5 * y], rho[x + 5 * y]);
+        for (int i = 0; i < 25; i++) b[pi[i]] = orc_rotl(a[i], rho[i]); /* rho + pi, sha3.c:53,88 */
         for (int y = 0; y < 25; y += 5) /* chi, sha3.c:116 */
-            for (int x = 0; x < 5; x++) a[y + x] = b[y + x] ^ (~b[y + (x + 1) % 5] & b[y + (x + 2) % 5]);
+            for (int x = 0; x < 5; x++) a[y + x] = b[y + x] ^ (~b[y + n1[x]] & b[y + n2[x]]);
         a[0] ^= orc_rc_table[round]; /* iota, sha3.c:182 */
     }
 }
@@ -326,11 +329,25 @@ static unsigned orc_pow17(unsigned e) {
 }
 
 /* zeta_i = 17^BitRev7(i) (ml_kem.c:300-307), gamma_i = 17^(2 BitRev7(i)+1) (ml_kem.c:424-433) */
+/* The reference recomputes every power inside its loops; the values are what matters.  Computed once (racing threads
+ * write identical values; the flag is published with release / acquire order). */
+static uint16_t orc_zeta_cache[128], orc_gamma_cache[128];
+static int orc_tables_ready = 0;
+static void orc_tables_init(void) {
+    if (__atomic_load_n(&orc_tables_ready, __ATOMIC_ACQUIRE)) return;
+    for (unsigned i = 0; i < 128; i++) {
+        orc_zeta_cache[i] = (uint16_t)orc_pow17(orc_bitrev7((uint8_t)i));
+        orc_gamma_cache[i] = (uint16_t)orc_pow17(2 * orc_bitrev7((uint8_t)i) + 1);
+    }
+    __atomic_store_n(&orc_tables_ready, 1, __ATOMIC_RELEASE);
+}
 ORC_API void orc_zeta_table(uint16_t z[128]) {
-    for (unsigned i = 0; i < 128; i++) z[i] = (uint16_t)orc_pow17(orc_bitrev7((uint8_t)i));
+    orc_tables_init();
+    memcpy(z, orc_zeta_cache, sizeof orc_zeta_cache);
 }
 ORC_API void orc_gamma_table(uint16_t g[128]) {
-    for (unsigned i = 0; i < 128; i++) g[i] = (uint16_t)orc_pow17(2 * orc_bitrev7((uint8_t)i) + 1);
+    orc_tables_init();
+    memcpy(g, orc_gamma_cache, sizeof orc_gamma_cache);
 }
 
 /*

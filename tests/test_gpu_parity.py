@@ -923,3 +923,69 @@ def test_current_device_is_restored(mlkem):
     assert mlkem.lib.mlkem_b200_ntt_batch(4, C.c_void_p(buf.ctypes.data), C.c_void_p(out.ctypes.data), C.byref(o)) == 0
     assert torch.cuda.current_device() == 0
     assert torch.zeros(1, device="cuda").device.index == 0
+
+
+def test_cell_layout_batches(mlkem, oracle):
+    """mlkem_b200_*_cells_batch: the KEM on arrays in the reference's own layout (one byte per 4-byte `union byte`,
+    ml_kem.h:35-38), converted on the device.  Upper bits of the input cells are garbage on purpose (D5: ignored)."""
+    import torch
+
+    rng = np.random.default_rng(3538)
+    n = 3000
+    d, z, m = (rng.integers(0, 256, (n, 32), dtype=np.uint8) for _ in range(3))
+    junk = lambda b: b.astype(np.uint32) | (rng.integers(0, 1 << 24, b.shape, dtype=np.uint32) << 8)
+    for ps in SETS:
+        oek, odk = oracle.keygen(ps, d, z)
+        oc, oK = oracle.encaps(ps, oek, m)
+        bad, _ = tamper(oc)
+        oKd = oracle.decaps(ps, odk, bad)
+        for dev in (False, True):
+            up = (lambda a: torch.from_numpy(a).cuda()) if dev else (lambda a: a)
+            down = (lambda t: t.cpu().numpy()) if dev else (lambda a: a)
+            ek, dk = mlkem.keygen_cells(ps, up(junk(d)), up(junk(z)))
+            assert (down(ek) == oek).all() and (down(dk) == odk).all()  # output cells: the byte, upper bits zero
+            c, K = mlkem.encaps_cells(ps, up(junk(oek)), up(junk(m)))
+            assert (down(c) == oc).all() and (down(K) == oK).all()
+            Kd = mlkem.decaps_cells(ps, up(junk(odk)), up(junk(bad)))
+            assert (down(Kd) == oKd).all()
+    small = __import__("crystals_kyber_b200").MLKEM(chunk_items=96)  # several chunks through the staging slots
+    c, K = small.encaps_cells(768, junk(oracle.keygen(768, d, z)[0]), junk(m))
+    assert (c == oracle.encaps(768, oracle.keygen(768, d, z)[0], m)[0]).all()
+    b = rng.integers(0, 256, (777, 1088), dtype=np.uint8)
+    cells = mlkem.cells_from_bytes(b)
+    assert cells.dtype == np.uint32 and (cells == b).all()
+    assert (mlkem.cells_to_bytes(junk(b)) == b).all()
+    tb = torch.from_numpy(b).cuda()
+    assert (mlkem.cells_to_bytes(mlkem.cells_from_bytes(tb)).cpu().numpy() == b).all()
+
+
+def test_asynchronous_host_calls(mlkem, oracle):
+    """MLKEM_B200_FLAG_ASYNC: host-memory calls that return once enqueued; several in flight, one synchronise at the end."""
+    import ctypes as C
+
+    import torch
+
+    from crystals_kyber_b200.lib import MEM_HOST, Opts
+
+    rng = np.random.default_rng(2)
+    n = 200_000  # four chunks of 2^16: the calls overlap in the staging slots
+    d, z, m = (rng.integers(0, 256, (n, 32), dtype=np.uint8) for _ in range(3))
+    ek, dk = mlkem.keygen(768, d, z)
+    pin = lambda a: torch.from_numpy(a).pin_memory()
+    hek, hdk, hm = pin(ek), pin(dk), pin(m)
+    hc = torch.empty((n, 1088), dtype=torch.uint8, pin_memory=True)
+    hK = torch.empty((n, 32), dtype=torch.uint8, pin_memory=True)
+    hKd = torch.empty((n, 32), dtype=torch.uint8, pin_memory=True)
+    P = lambda t: C.c_void_p(t.data_ptr())
+    o = Opts(0, MEM_HOST, None, 0, 0, 2)
+    lib = mlkem.lib
+    c_ref, K_ref = mlkem.encaps(768, ek, m)
+    hct = pin(c_ref)
+    for rep in range(2):
+        hK.zero_(); hKd.zero_()
+        assert lib.mlkem_b200_encaps_batch(768, n, P(hek), P(hm), P(hc), P(hK), C.byref(o)) == 0
+        assert lib.mlkem_b200_decaps_batch(768, n, P(hdk), P(hct), P(hKd), C.byref(o)) == 0
+        assert lib.mlkem_b200_synchronize(0, None) == 0
+        assert (hc.numpy() == c_ref).all() and (hK.numpy() == K_ref).all() and (hKd.numpy() == K_ref).all()
+    sl = slice(1000, 1300)
+    assert (K_ref[sl] == oracle.encaps(768, ek[sl], m[sl])[1]).all()
