@@ -162,9 +162,10 @@ class MLKEM:
             return self._opts(True, t.device.index, torch.cuda.current_stream(t.device).cuda_stream), True
         return self._opts(False, -1 if device is None else device), False
 
-    def keys_load(self, ps, dk=None, ek=None, seeds=None, device=None, return_status=False):
+    def keys_load(self, ps, dk=None, ek=None, seeds=None, device=None, return_status=False, expand=False):
         """A resident key table on the GPU from decapsulation keys `dk`, from encapsulation keys `ek` (Encaps only) or
-        from the 64-byte seeds `(d, z)` (KeyGen_internal on the device)."""
+        from the 64-byte seeds `(d, z)` (KeyGen_internal on the device).  expand=True also keeps every key's matrix A^
+        (MLKEM_B200_FLAG_EXPAND_KEYS): keyed calls then skip the matrix expansion."""
         sz = sizes(ps)
         handle = C.c_void_p()
         prep = lambda a: a.contiguous() if _is_torch(a) else np.ascontiguousarray(a, np.uint8)
@@ -174,15 +175,18 @@ class MLKEM:
             dk = prep(dk)
             n = self._count(dk, sz["dk"])
             o, _ = self._src_opts(dk, device=device)
+            o.flags |= 4 if expand else 0
             status = np.empty(n, np.int32)
             rc = self.lib.mlkem_b200_keys_load(ps, n, ptr(dk), C.c_void_p(status.ctypes.data), C.byref(o), C.byref(handle))
         elif ek is not None:
             ek = prep(ek)
             o, _ = self._src_opts(ek, device=device)
+            o.flags |= 4 if expand else 0
             rc = self.lib.mlkem_b200_keys_load_ek(ps, self._count(ek, sz["ek"]), ptr(ek), C.byref(o), C.byref(handle))
         else:
             d, z = (prep(a) for a in seeds)
             o, _ = self._src_opts(d, z, device=device)
+            o.flags |= 4 if expand else 0
             rc = self.lib.mlkem_b200_keys_from_seeds(ps, self._count(d, 32), ptr(d), ptr(z), C.byref(o), C.byref(handle))
         self._check(rc, "mlkem_b200_keys_load")
         table = KeyTable(self, handle, ps)

@@ -28,14 +28,15 @@ int env_int(const char *name, int dflt) {
     const char *v = getenv(name);
     return v && *v ? atoi(v) : dflt;
 }
-constexpr int kSlots = 4;      // streams / workspaces per device (host-memory calls use the first kHostSlots)
+constexpr int kSlots = 6;      // streams / workspaces per device: two groups of kHostSlots for host-memory calls, the first kDevSlots for device-memory calls
+constexpr int kDevSlots = 4;
 constexpr int kHostSlots = 3;  // measured: 3 slots keep the H2D copy engine at ~50.7 GB/s (2 slots: 48 GB/s)
 constexpr int kMaxDevices = 64;
 // Streams that device-memory calls interleave their chunks on (1 = serial; measured 31.3 / 32.4 / 32.5 / 32.5 M pairs/s with
 // 1 / 2 / 3 / 4).  MLKEM_B200_STREAMS sets the start value ONCE; mlkem_b200_set_streams() overrides it afterwards.
 int initial_streams() {
     int v = env_int("MLKEM_B200_STREAMS", 0);
-    return v < 1 ? kSlots : (v > kSlots ? kSlots : v);
+    return v < 1 ? kDevSlots : (v > kDevSlots ? kDevSlots : v);
 }
 std::atomic<int> g_streams{initial_streams()};
 
@@ -152,6 +153,8 @@ struct DeviceCtx {
     cudaEvent_t ev_fork = nullptr, ev_join[kSlots] = {}, ev_slot[kSlots] = {};
     void *misc = nullptr;  // small pooled device buffer: entropy seeds / status words of the public-wrapper batches
     size_t misc_bytes = 0;
+    int host_group = 0;     // consecutive host-memory calls alternate between slots 0..2 and 3..5: with MLKEM_B200_FLAG_ASYNC the
+                            // chunks of two calls in flight run side by side (one call's D2H under the other's H2D)
     std::mutex call_mutex;  // one call at a time enqueues on this device's streams / workspaces
     std::mutex misc_mutex;  // one user of `misc` at a time (held until its stream has drained)
 };
@@ -324,7 +327,8 @@ int launch_matvec(cudaStream_t st, Arena &ws, MatvecArgs a) {
 // Stores c, or (cmp != nullptr) ORs the mismatch of the re-encryption against cmp into flags.
 template <class P>
 int enqueue_encrypt(cudaStream_t st, Arena &ws, int n, const uint8_t *ek, size_t ek_stride, KeySel keys, const uint8_t *m,
-                    const uint8_t *seed, size_t seed_stride, uint8_t *c, const uint8_t *cmp, uint32_t *flags, int group_limit, bool fips) {
+                    const uint8_t *seed, size_t seed_stride, uint8_t *c, const uint8_t *cmp, uint32_t *flags, int group_limit, bool fips,
+                    const uint16_t *matrix = nullptr) {
     constexpr int K = P::K;
     uint16_t *yhat = ws.take<uint16_t>((size_t)n * K * 256);
     uint32_t *codes = ws.take<uint32_t>((size_t)n * (K + 1) * 32);
@@ -370,11 +374,15 @@ int enqueue_encrypt(cudaStream_t st, Arena &ws, int n, const uint8_t *ek, size_t
     v.c_stride = P::C;
     v.cmp = cmp;
     v.flags = flags;
+    // the u rows: from the expanded key table when there is one, else matrix expansion fused with the product
+    const unsigned tgrid = warp_grid((size_t)n * K, kMatTableTPB / 32);
     if (cmp) {
-        if (int rc = launch_matvec<P, kModeEncryptCompare>(st, ws, a)) return rc;
+        if (matrix) LAUNCH((k_matvec_table<P, kModeEncryptCompare>), tgrid, kMatTableTPB, 0, st, a, matrix);
+        else if (int rc = launch_matvec<P, kModeEncryptCompare>(st, ws, a)) return rc;
         LAUNCH((k_encrypt_v<P, true>), warp_grid(n, kWarpTPB / 32), kWarpTPB, 0, st, v);
     } else {
-        if (int rc = launch_matvec<P, kModeEncrypt>(st, ws, a)) return rc;
+        if (matrix) LAUNCH((k_matvec_table<P, kModeEncrypt>), tgrid, kMatTableTPB, 0, st, a, matrix);
+        else if (int rc = launch_matvec<P, kModeEncrypt>(st, ws, a)) return rc;
         LAUNCH((k_encrypt_v<P, false>), warp_grid(n, kWarpTPB / 32), kWarpTPB, 0, st, v);
     }
     return 0;
@@ -426,14 +434,15 @@ int enqueue_encaps(cudaStream_t st, Arena &ws, int n, const uint8_t *ek, const u
 // Encaps_internal against a resident key table: ek rows at ek + key*ek_stride, their hashes H(ek) at hek + 32 key.
 template <class P>
 int enqueue_encaps_keyed(cudaStream_t st, Arena &ws, int n, const uint8_t *ek, size_t ek_stride, const uint8_t *hek, KeySel keys,
-                         const uint8_t *m, uint8_t *c, uint8_t *Kout, int group_limit, bool fips) {
+                         const uint8_t *m, uint8_t *c, uint8_t *Kout, int group_limit, bool fips, const uint16_t *matrix) {
     uint8_t *r = ws.take<uint8_t>((size_t)n * 32);
     LAUNCH(k_encaps_G_keyed, cdiv(n, kHashTPB), kHashTPB, 0, st, n, hek, keys, m, Kout, r);
-    return enqueue_encrypt<P>(st, ws, n, ek, ek_stride, keys, m, r, 32, c, nullptr, nullptr, group_limit, fips);
+    return enqueue_encrypt<P>(st, ws, n, ek, ek_stride, keys, m, r, 32, c, nullptr, nullptr, group_limit, fips, matrix);
 }
 
 template <class P>
-int enqueue_decaps(cudaStream_t st, Arena &ws, int n, const uint8_t *dk, KeySel keys, const uint8_t *c, uint8_t *Kout, int group_limit, bool fips) {
+int enqueue_decaps(cudaStream_t st, Arena &ws, int n, const uint8_t *dk, KeySel keys, const uint8_t *c, uint8_t *Kout, int group_limit, bool fips,
+                   const uint16_t *matrix = nullptr) {
     constexpr int K = P::K;
     uint8_t *mp = ws.take<uint8_t>((size_t)n * 32);
     uint8_t *Kr = ws.take<uint8_t>((size_t)n * 64);
@@ -442,7 +451,7 @@ int enqueue_decaps(cudaStream_t st, Arena &ws, int n, const uint8_t *dk, KeySel 
     LAUNCH((k_decrypt<P>), warp_grid(n, kWarpTPB / 32), kWarpTPB, 0, st, n, dk, (size_t)P::DK, keys, c, mp);
     LAUNCH((k_decaps_G<P>), cdiv(n, kHashTPB), kHashTPB, 0, st, n, mp, dk, keys, Kr);
     // c' = K-PKE.Encrypt(ek_pke, m', r') compared on the fly (ml_kem.c:1206-1215)
-    if (int rc = enqueue_encrypt<P>(st, ws, n, dk + 384 * K, P::DK, keys, mp, Kr + 32, 64, nullptr, c, flags, group_limit, fips)) return rc;
+    if (int rc = enqueue_encrypt<P>(st, ws, n, dk + 384 * K, P::DK, keys, mp, Kr + 32, 64, nullptr, c, flags, group_limit, fips, matrix)) return rc;
     if (!fips) LAUNCH((k_decaps_J_select<P>), cdiv(n, kHashTPB), kHashTPB, 0, st, n, dk, keys, c, Kr, flags, Kout);
     else LAUNCH((k_decaps_J_select<P, kRateSha3_256>), cdiv(n, kHashTPB), kHashTPB, 0, st, n, dk, keys, c, Kr, flags, Kout);
     return 0;
@@ -496,7 +505,7 @@ int drive(const mlkem_b200_opts *o, size_t n, size_t ws_per_item, std::vector<Bu
     const bool on_device = o && o->mem == MLKEM_B200_MEM_DEVICE;
     static const int env_chunk = env_int("MLKEM_B200_CHUNK", 0);  // tuning knobs
     static const int env_hchunk = env_int("MLKEM_B200_HOST_CHUNK", 0);
-    static const int host_slots = std::min(kSlots, std::max(1, env_int("MLKEM_B200_HOST_SLOTS", kHostSlots)));
+    static const int host_slots = std::min(kHostSlots, std::max(1, env_int("MLKEM_B200_HOST_SLOTS", kHostSlots)));
     size_t chunk = (o && o->chunk_items > 0) ? (size_t)o->chunk_items
                    : (on_device ? (env_chunk > 0 ? (size_t)env_chunk : (size_t)1 << 18) : (env_hchunk > 0 ? (size_t)env_hchunk : (size_t)1 << 16));
     if (chunk > ((size_t)1 << 26)) chunk = (size_t)1 << 26;  // the kernels index rows (items x k) and list entries with int
@@ -525,7 +534,7 @@ int drive(const mlkem_b200_opts *o, size_t n, size_t ws_per_item, std::vector<Bu
         }
         const size_t nch = (n + chunk - 1) / chunk;
         int nstreams = g_streams.load();
-        if (nstreams > kSlots) nstreams = kSlots;
+        if (nstreams > kDevSlots) nstreams = kDevSlots;
         if ((size_t)nstreams > nch) nstreams = (int)nch;
         if (nstreams < 1) nstreams = 1;
         {
@@ -581,16 +590,18 @@ int drive(const mlkem_b200_opts *o, size_t n, size_t ws_per_item, std::vector<Bu
     size_t io_per_item = 0;
     for (auto &b : bufs) io_per_item += ((b.item_bytes + 15) & ~size_t(15)) * (b.cells ? 5 : 1);  // cells: 4x image + dense image
     const int nslots = nchunks > 1 ? (int)std::min<size_t>(host_slots, nchunks) : 1;
+    const int s0 = ctx->host_group * kHostSlots;  // this call's slot group
+    ctx->host_group ^= 1;
     {
         std::lock_guard<std::mutex> lock(g_mutex);
-        for (int s = 0; s < nslots; s++) {
+        for (int s = s0; s < s0 + nslots; s++) {
             if (int rc = ensure_buffer(&ctx->ws[s], &ctx->ws_bytes[s], chunk * ws_per_item + kWsSlack, ctx->ev_slot[s])) return rc;
             if (int rc = ensure_buffer(&ctx->io[s], &ctx->io_bytes[s], chunk * io_per_item + 256 * bufs.size(), ctx->ev_slot[s])) return rc;
         }
     }
-    for (int s = 0; s < nslots; s++) CU(cudaStreamWaitEvent(ctx->stream[s], ctx->ev_slot[s], 0));
+    for (int s = s0; s < s0 + nslots; s++) CU(cudaStreamWaitEvent(ctx->stream[s], ctx->ev_slot[s], 0));
     auto chunk_of = [&](size_t ci) -> int {
-        const int s = (int)(ci % nslots);
+        const int s = s0 + (int)(ci % nslots);
         cudaStream_t st = ctx->stream[s];
         size_t i0 = ci * chunk, cn = (i0 + chunk <= n) ? chunk : n - i0;
         Arena io(ctx->io[s]);
@@ -622,14 +633,14 @@ int drive(const mlkem_b200_opts *o, size_t n, size_t ws_per_item, std::vector<Bu
     };
     int rc = 0;
     for (size_t ci = 0; ci < nchunks && !rc; ci++) rc = chunk_of(ci);
-    for (int s = 0; s < nslots; s++) cudaEventRecord(ctx->ev_slot[s], ctx->stream[s]);
+    for (int s = s0; s < s0 + nslots; s++) cudaEventRecord(ctx->ev_slot[s], ctx->stream[s]);
     // Enqueueing is over: the next call may start filling the slots behind this one (it waits on ev_slot), so that the
     // D2H tail of this call overlaps the H2D head of the next.
     call_lock.unlock();
     // MLKEM_B200_FLAG_ASYNC: return now; the caller keeps its (pinned) buffers untouched until mlkem_b200_synchronize().
     if (!rc && o && (o->flags & MLKEM_B200_FLAG_ASYNC)) return MLKEM_B200_OK;
     // also on the error path: nothing may still be writing into the caller's buffers when the call returns
-    for (int s = 0; s < nslots; s++) {
+    for (int s = s0; s < s0 + nslots; s++) {
         cudaError_t e = cudaStreamSynchronize(ctx->stream[s]);
         if (e != cudaSuccess && !rc) {
             snprintf(tl_error, sizeof tl_error, "cudaStreamSynchronize failed: %s", cudaGetErrorString(e));
@@ -1167,6 +1178,8 @@ struct mlkem_b200_keys {
     uint8_t *ek = nullptr;   // row i at ek + i*ek_stride (inside dk when dk != nullptr)
     size_t ek_stride = 0;
     uint8_t *hek = nullptr;  // n x 32: H(ek_i), computed once at load time
+    uint16_t *matrix = nullptr;  // MLKEM_B200_FLAG_EXPAND_KEYS: n x K x K polynomials, At[row][col] = SampleNTT(rho || row || col)
+    int group_limit = 278;       // the SampleNTT group limit the matrix was sampled with
 };
 
 namespace {
@@ -1183,6 +1196,7 @@ void keys_destroy(mlkem_b200_keys *k) {
             cudaFree(k->ek);
         }
         if (k->hek) cudaFree(k->hek);
+        if (k->matrix) cudaFree(k->matrix);
     }
     delete k;
 }
@@ -1227,10 +1241,34 @@ int keys_create(int set, size_t n, bool with_dk, const mlkem_b200_opts *o, mlkem
         case 768: LAUNCH((k_hash_ek_table<P768>), cdiv(n, kHashTPB), kHashTPB, 0, st, (int)n, k->ek, k->ek_stride, k->hek); break;
         default: LAUNCH((k_hash_ek_table<P1024>), cdiv(n, kHashTPB), kHashTPB, 0, st, (int)n, k->ek, k->ek_stride, k->hek); break;
         }
-        CU(cudaStreamSynchronize(st));  // loading is a set-up call: the table is complete when it returns
         return 0;
     };
     if (int rc = hash()) return fail(rc);
+    auto expand = [&]() -> int {  // the matrix of every key, once (mlkem_kernels.cuh: expanded key tables)
+        const size_t entries = n * kk * kk;
+        uint8_t *seeds = nullptr;
+        CU(cudaMalloc(&k->matrix, entries * 512));
+        CU(cudaMalloc(&seeds, entries * 34 + 16));
+        k->group_limit = group_limit_of(o);
+        int rc = 0;
+        auto seed_kernel = [&]() -> int {
+            switch (set) {
+            case 512: LAUNCH((k_matrix_seeds<P512>), cdiv(entries, 256), 256, 0, st, (int)n, k->ek, k->ek_stride, seeds); break;
+            case 768: LAUNCH((k_matrix_seeds<P768>), cdiv(entries, 256), 256, 0, st, (int)n, k->ek, k->ek_stride, seeds); break;
+            default: LAUNCH((k_matrix_seeds<P1024>), cdiv(entries, 256), 256, 0, st, (int)n, k->ek, k->ek_stride, seeds); break;
+            }
+            return 0;
+        };
+        rc = seed_kernel();
+        mlkem_b200_opts od{k->device, MLKEM_B200_MEM_DEVICE, st, 0, o ? o->sample_group_limit : 0, 0};
+        if (!rc) rc = mlkem_b200_sample_ntt_batch(entries, seeds, k->matrix, nullptr, &od);
+        cudaStreamSynchronize(st);
+        cudaFree(seeds);
+        return rc;
+    };
+    if (o && (o->flags & MLKEM_B200_FLAG_EXPAND_KEYS))
+        if (int rc = expand()) return fail(rc);
+    if (cudaStreamSynchronize(st) != cudaSuccess) return fail(MLKEM_B200_ERR_CUDA);  // loading is a set-up call: the table is complete when it returns
     *out = k;
     return MLKEM_B200_OK;
 }
@@ -1333,7 +1371,7 @@ int mlkem_b200_encaps_keyed_batch(const mlkem_b200_keys *k, size_t n, const uint
     DISPATCH_SET(k->set, return drive(&oo, n, ws_bytes_per_item<P>(), bufs, [=](cudaStream_t st, Arena &ws, int cn, void **p, size_t first) {
                      KeySel ks{has_idx ? (const uint32_t *)p[3] : nullptr, (uint32_t)(first % nk), nk};
                      return enqueue_encaps_keyed<P>(st, ws, cn, k->ek, k->ek_stride, k->hek, ks, (const uint8_t *)p[0], (uint8_t *)p[1],
-                                                    (uint8_t *)p[2], gl, fips);
+                                                    (uint8_t *)p[2], gl, fips, k->matrix);
                  }));
     return MLKEM_B200_ERR_PARAM;
 }
@@ -1354,7 +1392,7 @@ int mlkem_b200_decaps_keyed_batch(const mlkem_b200_keys *k, size_t n, const uint
     if (has_idx) bufs.push_back({key_index, nullptr, 4});
     DISPATCH_SET(k->set, return drive(&oo, n, ws_bytes_per_item<P>(), bufs, [=](cudaStream_t st, Arena &ws, int cn, void **p, size_t first) {
                      KeySel ks{has_idx ? (const uint32_t *)p[2] : nullptr, (uint32_t)(first % nk), nk};
-                     return enqueue_decaps<P>(st, ws, cn, k->dk, ks, (const uint8_t *)p[0], (uint8_t *)p[1], gl, fips);
+                     return enqueue_decaps<P>(st, ws, cn, k->dk, ks, (const uint8_t *)p[0], (uint8_t *)p[1], gl, fips, k->matrix);
                  }));
     return MLKEM_B200_ERR_PARAM;
 }

@@ -49,6 +49,7 @@ __device__ __forceinline__ size_t key_row(const KeySel &k, int item) {
 constexpr int kHashTPB = 128;   // threads per block of the thread-per-item hash kernels
 constexpr int kNoiseTPB = 128;  // threads (= sponges) per block of k_noise
 constexpr int kSlotWords = 129; // shared-memory words per sampled polynomial slot (odd: conflict-free per-thread writes)
+constexpr int kMatTableTPB = 128; // threads per block of k_matvec_table (4 rows in flight per block)
 
 // =================================================================================================
 // Reference cell layout <-> dense bytes
@@ -739,6 +740,72 @@ __device__ __forceinline__ void matvec_prefetch(MatvecOperands<P> &o, const Matv
     }
 }
 
+// The rest of a row once its K base-case products are accumulated: (KeyGen) + e^ and ByteEncode12, or (Encrypt) inverse
+// transform, + e1, Compress_du, ByteEncode_du; then store the row or compare it with the received ciphertext.
+template <class P, int MODE>
+__device__ __forceinline__ void matvec_row_tail(const MatvecArgs &g, int item, int row, uint32_t acc[8], const uint32_t cw8[8],
+                                                const uint32_t *cmpw, const uint32_t ev4[4], uint16_t *scratch, uint8_t *stage, int lane,
+                                                const LaneTwiddles &tw, uint32_t pw) {
+    constexpr int kCmpWords = MatvecOperands<P>::kCmpWords;
+    int nwords;
+    if (MODE == kModeKeyGen) {
+        // t^[row] = A[row] . s^ + e^[row]   (ml_kem.c:723-727), then ByteEncode12 (:736-742)
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            int t = lane + 32 * r;
+            uint32_t e = ev4[r];
+            uint32_t c0 = csubq(canon32(acc[2 * r]) + (e & 0xFFFFu)), c1 = csubq(canon32(acc[2 * r + 1]) + (e >> 16));
+            uint32_t v = c0 | (c1 << 12);
+            stage[3 * t] = (uint8_t)v;
+            stage[3 * t + 1] = (uint8_t)(v >> 8);
+            stage[3 * t + 2] = (uint8_t)(v >> 16);
+        }
+        nwords = 96;
+    } else {
+        // u[row] = InverseNTT(At[row] . y^) + e1[row]  (ml_kem.c:854-864); Compress_du + ByteEncode_du (:886-896)
+        uint32_t *sw = reinterpret_cast<uint32_t *>(scratch);
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            int t = lane + 32 * r;
+            sw[sidx(2 * t) >> 1] = barrett32(acc[2 * r]) + barrett32(acc[2 * r + 1]) * 65536u;  // < 2q each
+        }
+        __syncwarp();
+        uint32_t x[8];
+        load_scratch_C(x, scratch, lane);
+        __syncwarp();
+        intt_warp<kFmaPipe, false>(x, scratch, lane, tw);  // [0, 2q)
+#pragma unroll
+        for (int r = 0; r < 8; r++) {  // (x + e1) mod q, exact, then Compress_du: everything but the final mask on the fma pipe
+            uint32_t y = x[r] + nibble_fma(cw8[r], pw) + (kQ - 3);  // < 3q + 4
+            x[r] = compress_canon<P::DU>(canon_fma(y));
+        }
+        store_scratch_A(x, scratch, lane);
+        __syncwarp();
+        load_scratch_C(x, scratch, lane);
+        pack8<P::DU>(x, stage + P::DU * lane);
+        nwords = 8 * P::DU;
+    }
+    __syncwarp();
+    const uint32_t *stw = reinterpret_cast<const uint32_t *>(stage);
+    const size_t row_off = (MODE == kModeKeyGen ? 384 : P::C1ROW) * (size_t)row;
+    if (MODE == kModeEncryptCompare) {
+        uint32_t d = 0;
+#pragma unroll
+        for (int i = 0; i < kCmpWords; i++)
+            if (lane + 32 * i < nwords) d |= stw[lane + 32 * i] ^ cmpw[i];
+        d = __any_sync(kFullMask, d != 0) ? 1u : 0u;
+        if (lane == 0) atomicOr(g.flags + item, d);  // unconditional: no data-dependent control flow
+    } else {
+        uint32_t *ow = reinterpret_cast<uint32_t *>(g.out + g.out_stride * item + row_off);
+        for (int w = lane; w < nwords; w += 32) ow[w] = stw[w];
+        if (MODE == kModeKeyGen && g.out2) {
+            uint32_t *ow2 = reinterpret_cast<uint32_t *>(g.out2 + g.out2_stride * item + row_off);
+            for (int w = lane; w < nwords; w += 32) ow2[w] = stw[w];
+        }
+    }
+    __syncwarp();
+}
+
 template <class P, int MODE>
 __device__ __forceinline__ void matvec_finish_rows(const MatvecArgs &g, uint32_t *s_slots, const int *s_gg, int lane, int warp,
                                                    const MatvecLaneConsts &lc, MatvecOperands<P> &nx) {
@@ -790,63 +857,7 @@ __device__ __forceinline__ void matvec_finish_rows(const MatvecArgs &g, uint32_t
                 basemul_acc(acc[2 * r], acc[2 * r + 1], a0, a1, v[8 * j + 2 * r], v[8 * j + 2 * r + 1], gam[r]);
             }
         }
-        int nwords;
-        if (MODE == kModeKeyGen) {
-            // t^[row] = A[row] . s^ + e^[row]   (ml_kem.c:723-727), then ByteEncode12 (:736-742)
-#pragma unroll
-            for (int r = 0; r < 4; r++) {
-                int t = lane + 32 * r;
-                uint32_t e = ev4[r];
-                uint32_t c0 = csubq(canon32(acc[2 * r]) + (e & 0xFFFFu)), c1 = csubq(canon32(acc[2 * r + 1]) + (e >> 16));
-                uint32_t v = c0 | (c1 << 12);
-                stage[3 * t] = (uint8_t)v;
-                stage[3 * t + 1] = (uint8_t)(v >> 8);
-                stage[3 * t + 2] = (uint8_t)(v >> 16);
-            }
-            nwords = 96;
-        } else {
-            // u[row] = InverseNTT(At[row] . y^) + e1[row]  (ml_kem.c:854-864); Compress_du + ByteEncode_du (:886-896)
-            uint32_t *sw = reinterpret_cast<uint32_t *>(scratch);
-#pragma unroll
-            for (int r = 0; r < 4; r++) {
-                int t = lane + 32 * r;
-                sw[sidx(2 * t) >> 1] = barrett32(acc[2 * r]) + barrett32(acc[2 * r + 1]) * 65536u;  // < 2q each
-            }
-            __syncwarp();
-            uint32_t x[8];
-            load_scratch_C(x, scratch, lane);
-            __syncwarp();
-            intt_warp<kFmaPipe, false>(x, scratch, lane, tw);  // [0, 2q)
-#pragma unroll
-            for (int r = 0; r < 8; r++) {  // (x + e1) mod q, exact, then Compress_du: everything but the final mask on the fma pipe
-                uint32_t y = x[r] + nibble_fma(cw8[r], pw) + (kQ - 3);  // < 3q + 4
-                x[r] = compress_canon<P::DU>(canon_fma(y));
-            }
-            store_scratch_A(x, scratch, lane);
-            __syncwarp();
-            load_scratch_C(x, scratch, lane);
-            pack8<P::DU>(x, stage + P::DU * lane);
-            nwords = 8 * P::DU;
-        }
-        __syncwarp();
-        const uint32_t *stw = reinterpret_cast<const uint32_t *>(stage);
-        const size_t row_off = (MODE == kModeKeyGen ? 384 : P::C1ROW) * (size_t)row;
-        if (MODE == kModeEncryptCompare) {
-            uint32_t d = 0;
-#pragma unroll
-            for (int i = 0; i < kCmpWords; i++)
-                if (lane + 32 * i < nwords) d |= stw[lane + 32 * i] ^ cmpw[i];
-            d = __any_sync(kFullMask, d != 0) ? 1u : 0u;
-            if (lane == 0) atomicOr(g.flags + item, d);  // unconditional: no data-dependent control flow
-        } else {
-            uint32_t *ow = reinterpret_cast<uint32_t *>(g.out + g.out_stride * item + row_off);
-            for (int w = lane; w < nwords; w += 32) ow[w] = stw[w];
-            if (MODE == kModeKeyGen && g.out2) {
-                uint32_t *ow2 = reinterpret_cast<uint32_t *>(g.out2 + g.out2_stride * item + row_off);
-                for (int w = lane; w < nwords; w += 32) ow2[w] = stw[w];
-            }
-        }
-        __syncwarp();
+        matvec_row_tail<P, MODE>(g, item, row, acc, cw8, cmpw, ev4, scratch, stage, lane, tw, pw);
     }
 }
 
@@ -949,6 +960,77 @@ __global__ void __launch_bounds__(32 * P::K) k_sample_matvec_list(MatvecArgs g) 
         matvec_prefetch<P, MODE>(nx, g, s_gg[warp], lane);
         matvec_finish_rows<P, MODE>(g, s_slots, s_gg, lane, warp, lc, nx);
         __syncthreads();  // the slots are reused by the next batch of rows
+    }
+}
+
+// =================================================================================================
+// Expanded key tables: the matrix of a resident key is sampled once, not once per ciphertext
+// =================================================================================================
+// A^ depends only on rho, i.e. on the key.  A resident key table (mlkem_b200_keys_*, MLKEM_B200_FLAG_EXPAND_KEYS) keeps
+// At[row][col] = SampleNTT(rho || row || col) (ml_kem.c:817-823, the order K-PKE.Encrypt consumes it in) as uint16
+// polynomials, K*K*512 bytes per key, so that keyed Encaps / Decaps run 8 / 15 Keccak permutations per item instead of
+// 44 / 42 at ML-KEM-768: what is left of the matrix-vector product is HBM-fed polynomial arithmetic.
+
+// Seeds of the matrix entries of n keys: seeds[(key*K + row)*K + col] = rho_key || row || col (34 bytes each).
+template <class P>
+__global__ void __launch_bounds__(256) k_matrix_seeds(int n, const uint8_t *__restrict__ ek, size_t ek_stride, uint8_t *__restrict__ seeds) {
+    constexpr int K = P::K;
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n * K * K) return;
+    const int key = e / (K * K), rc = e - key * K * K, row = rc / K, col = rc - row * K;
+    const uint8_t *rho = ek + ek_stride * key + 384 * K;
+    uint8_t *out = seeds + 34 * (size_t)e;
+    for (int b = 0; b < 32; b++) out[b] = rho[b];
+    out[32] = (uint8_t)row;
+    out[33] = (uint8_t)col;
+}
+
+// u rows of K-PKE.Encrypt from the table (ml_kem.c:854-896): persistent warps, warp = one (item, row); the K matrix
+// polynomials of the row come from HBM / L2 with coalesced 32-bit loads (a coefficient pair per lane and load), the
+// vector, noise codes and ciphertext row are fetched one row ahead like in the fused kernel.
+template <class P, int MODE>
+__global__ void __launch_bounds__(kMatTableTPB) k_matvec_table(MatvecArgs g, const uint16_t *__restrict__ table) {
+    static_assert(MODE != kModeKeyGen, "the table is kept in Encrypt order");
+    constexpr int K = P::K, NW = kMatTableTPB / 32;
+    __shared__ __align__(16) uint8_t s_warp[NW * kMatvecWarpBytes];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint16_t *scratch = reinterpret_cast<uint16_t *>(s_warp + warp * kMatvecWarpBytes);
+    uint8_t *stage = s_warp + warp * kMatvecWarpBytes + 512;
+    MatvecLaneConsts lc;
+    matvec_load_consts<MODE>(lc, lane);
+    const int rows = g.n * K, stride = gridDim.x * NW;
+    int gg = blockIdx.x * NW + warp;
+    MatvecOperands<P> nx;
+    matvec_prefetch<P, MODE>(nx, g, gg < rows ? gg : -1, lane);
+    constexpr int kCmpWords = MatvecOperands<P>::kCmpWords;
+#pragma unroll 1
+    for (; gg < rows; gg += stride) {
+        const int item = gg / K, row = gg - item * K;
+        const uint32_t *arow = reinterpret_cast<const uint32_t *>(table + ((size_t)key_row(g.keys, item) * K + row) * K * 256);
+        uint32_t aw[4 * K];
+#pragma unroll
+        for (int j = 0; j < K; j++)
+#pragma unroll
+            for (int r = 0; r < 4; r++) aw[4 * j + r] = __ldg(arow + 128 * j + lane + 32 * r);
+        uint32_t v[8 * K], cw8[8], cmpw[kCmpWords], ev4[4];
+#pragma unroll
+        for (int i = 0; i < 8 * K; i++) v[i] = nx.v[i];
+#pragma unroll
+        for (int i = 0; i < 8; i++) cw8[i] = nx.cw[i];
+#pragma unroll
+        for (int i = 0; i < kCmpWords; i++) cmpw[i] = nx.cmp[i];
+#pragma unroll
+        for (int i = 0; i < 4; i++) ev4[i] = 0;
+        matvec_prefetch<P, MODE>(nx, g, gg + stride < rows ? gg + stride : -1, lane);
+        uint32_t acc[8];
+#pragma unroll
+        for (int r = 0; r < 8; r++) acc[r] = 0;
+#pragma unroll
+        for (int j = 0; j < K; j++)
+#pragma unroll
+            for (int r = 0; r < 4; r++)
+                basemul_acc(acc[2 * r], acc[2 * r + 1], aw[4 * j + r] & 0xFFFFu, aw[4 * j + r] >> 16, v[8 * j + 2 * r], v[8 * j + 2 * r + 1], lc.gam[r]);
+        matvec_row_tail<P, MODE>(g, item, row, acc, cw8, cmpw, ev4, scratch, stage, lane, lc.tw, lc.pw);
     }
 }
 

@@ -62,7 +62,7 @@ int measure_rate(uint32_t *d_out, int sms, double *ops_per_s) {
 extern "C" {
 
 void mlkem_b200_profile(int enable) { g_profile.store(enable ? 1 : 0); }
-void mlkem_b200_set_streams(int n) { g_streams.store(n < 1 ? initial_streams() : (n > kSlots ? kSlots : n)); }  // n < 1: the default
+void mlkem_b200_set_streams(int n) { g_streams.store(n < 1 ? initial_streams() : (n > kDevSlots ? kDevSlots : n)); }  // n < 1: the default
 
 int mlkem_b200_profile_report(char *buf, int cap) {
     std::vector<ProfEntry> entries;

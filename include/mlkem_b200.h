@@ -86,6 +86,11 @@ typedef struct mlkem_b200_opts {
  * mlkem_b200_synchronize(device, NULL) returns.  Consecutive asynchronous calls pipeline through the staging slots:
  * the device-to-host tail of one overlaps the host-to-device head of the next. */
 #define MLKEM_B200_FLAG_ASYNC 2
+/* mlkem_b200_keys_load / _load_ek / _from_seeds only: also keep the expanded matrix A^ of every key in the table
+ * (At[row][col] = SampleNTT(rho || row || col), ml_kem.c:817-823; k*k*512 bytes per key, 4.6 KB at ML-KEM-768).  The matrix
+ * depends on the key alone, so keyed Encaps / Decaps then skip the 27 of their 44 / 42 Keccak permutations that
+ * re-sample it for every item.  Results are unchanged.  (sample_group_limit, the test hook, is fixed at load time.) */
+#define MLKEM_B200_FLAG_EXPAND_KEYS 4
 
 const char *mlkem_b200_version(void);
 const char *mlkem_b200_last_error(void);          /* text of the last CUDA error seen by this thread */

@@ -841,19 +841,21 @@ def test_keyed_calls_equal_unkeyed(mlkem, oracle):
         t_seeds = mlkem.keys_load(ps, seeds=(d, z))
         t_dev = mlkem.keys_load(ps, seeds=(torch.from_numpy(d).cuda(), torch.from_numpy(z).cuda()))
         t_ek = mlkem.keys_load(ps, ek=ek)
-        assert len(t_bytes) == len(t_seeds) == len(t_ek) == nk
+        t_exp = mlkem.keys_load(ps, seeds=(d, z), expand=True)  # with the matrix A^ of every key kept in the table
+        t_ek_exp = mlkem.keys_load(ps, ek=ek, expand=True)
+        assert len(t_bytes) == len(t_seeds) == len(t_ek) == len(t_exp) == nk
         idx = rng.integers(0, nk, n, dtype=np.uint32)
         m = rng.integers(0, 256, (n, 32), dtype=np.uint8)
         c, K = mlkem.encaps(ps, ek[idx], m)
         oc, oK = oracle.encaps(ps, ek[idx], m)
         assert first_mismatch(c, oc) == -1 and first_mismatch(K, oK) == -1
-        for t in (t_bytes, t_seeds, t_dev, t_ek):
+        for t in (t_bytes, t_seeds, t_dev, t_ek, t_exp, t_ek_exp):
             ck_, Kk = mlkem.encaps_keyed(t, idx, m)
             assert first_mismatch(ck_, c) == -1 and first_mismatch(Kk, K) == -1
         ct, _ = tamper(c)
         Kd = mlkem.decaps(ps, dk[idx], ct)
         assert first_mismatch(Kd, oracle.decaps(ps, dk[idx], ct)) == -1
-        for t in (t_bytes, t_seeds, t_dev):
+        for t in (t_bytes, t_seeds, t_dev, t_exp):
             assert first_mismatch(mlkem.decaps_keyed(t, idx, ct), Kd) == -1
             got = mlkem.decaps_keyed(t, torch.from_numpy(idx.astype(np.int32)).cuda(), torch.from_numpy(ct).cuda())
             assert first_mismatch(got.cpu().numpy(), Kd) == -1
@@ -869,8 +871,25 @@ def test_keyed_calls_equal_unkeyed(mlkem, oracle):
             mlkem.decaps_keyed(t_ek, idx, ct)  # a table of encapsulation keys cannot decapsulate
         with pytest.raises(ck.MlKemB200Error):
             mlkem.decaps_keyed(t_bytes, np.full(n, nk, np.uint32), ct)  # index out of range (host memory: rejected)
-        for t in (t_bytes, t_seeds, t_dev, t_ek):
+        assert first_mismatch(small.decaps_keyed(t_exp, None, cc), Kc) == -1
+        ce, Ke = small.encaps_keyed(t_ek_exp, None, m)
+        assert first_mismatch(ce, occ) == -1 and first_mismatch(Ke, oKc) == -1
+        for t in (t_bytes, t_seeds, t_dev, t_ek, t_exp, t_ek_exp):
             t.free()
+    # the expanded table with the lowered SampleNTT group limit (restart path, ml_kem.c:221-242) fixed at load time
+    lim = ck.MLKEM(sample_group_limit=158)
+    oracle.set_sample_group_limit(158)
+    try:
+        d, z, m = (rng.integers(0, 256, (400, 32), dtype=np.uint8) for _ in range(3))
+        oek, odk = oracle.keygen(768, d, z)
+        oc, oK = oracle.encaps(768, oek, m)
+        t = lim.keys_load(768, dk=odk, expand=True)
+        c, K = lim.encaps_keyed(t, None, m)
+        assert first_mismatch(c, oc) == -1 and first_mismatch(K, oK) == -1
+        assert first_mismatch(lim.decaps_keyed(t, None, tamper(oc)[0]), oracle.decaps(768, odk, tamper(oc)[0])) == -1
+        t.free()
+    finally:
+        oracle.set_sample_group_limit(0)
 
 
 def test_calls_on_different_streams_share_the_workspace_safely(mlkem, oracle):
