@@ -186,6 +186,7 @@ def main():
     ap.add_argument("--e2e-log2-items", type=int, default=None, help="items per GPU for the host-buffer leg (default: same)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--no-wc-inputs", action="store_true", help="e2e input buffers in ordinary pinned memory instead of write-combined")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -310,8 +311,22 @@ def main():
     ne = 1 << (args.e2e_log2_items if args.e2e_log2_items is not None else args.log2_items)
     ne = min(ne, n)
 
+    wc_allocs = []
+
     def pinned_copy(t):
-        h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        """Host copy of a device tensor in an INPUT buffer of the e2e legs: pinned and, unless --no-wc-inputs, write-combined
+        (mlkem_b200_host_alloc_wc).  The CPU only ever fills these buffers; write-combined pages are not snooped when the GPU
+        reads them, which is worth nothing on one GPU and 7 % (H2D alone) to 44 % (both directions busy) of the box's aggregate
+        copy rate with eight (tools/pcie_bw.py, profiles/pcie_bw_r02_8gpu.json)."""
+        if args.no_wc_inputs:
+            h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        else:
+            nbytes = t.numel() * t.element_size()
+            ptr = lib.mlkem_b200_host_alloc_wc(nbytes)
+            if not ptr:
+                raise MemoryError("mlkem_b200_host_alloc_wc failed")
+            wc_allocs.append(ptr)
+            h = torch.frombuffer((C.c_ubyte * nbytes).from_address(ptr), dtype=torch.uint8).view(t.dtype).view(t.shape)
         h.copy_(t)
         return h
 
@@ -379,6 +394,7 @@ def main():
     ceil_s = timed_host(lambda: probe_pair([hek, hm], hscratch[:2], [hdk, hct], hscratch[2:]))
     e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "items_per_gpu": ne,
            "ms_per_step": 1e3 * e2e_s / steps, "h2d_GBps_per_gpu": h2d * steps / e2e_s / 1e9,
+           "input_buffers": "pinned" if args.no_wc_inputs else "pinned, write-combined (mlkem_b200_host_alloc_wc)",
            "path": "mlkem_b200_encaps_batch + mlkem_b200_decaps_batch with MLKEM_B200_MEM_HOST (pinned buffers), distinct keys per item; the two "
                    "calls of a step are issued with MLKEM_B200_FLAG_ASYNC and followed by one mlkem_b200_synchronize",
            "blocking_calls": {"value": world * ne * steps / e2e_sync_s, "unit": UNIT, "ms_per_step": 1e3 * e2e_sync_s / steps,
@@ -403,9 +419,9 @@ def main():
             raise RuntimeError(lib.mlkem_b200_last_error().decode())
 
     step_keyed_encaps()
-    hctk = hct  # the ciphertexts Decaps receives: those of the keyed Encaps, 10 % tampered
+    hctk = hct  # the ciphertexts Decaps receives: those of the keyed Encaps, 10 % tampered (tampered in cached memory, then copied)
+    wl.tamper_inplace(hck.numpy(), begin)
     hctk.copy_(hck)
-    wl.tamper_inplace(hctk.numpy(), begin)
 
     def step_keyed(o=o_host):
         rc = lib.mlkem_b200_encaps_keyed_batch(table.handle, ne, None, P(hm), P(hck), P(hKk), C.byref(o))
@@ -479,7 +495,9 @@ def main():
     e2e_keyed["decaps_keyed_only"] = {"value": world * ne * steps / kd_s, "unit": UNIT, "h2d_bytes_per_step": ne * (sz["ek"] + 32 + sz["c"]),
                                       "d2h_bytes_per_step": d2h_k, "ms_per_step": 1e3 * kd_s / steps, "vs_unkeyed_e2e": e2e_s / kd_s}
     table.free()
-    del hek, hck, hct, hctk, hc, hscratch, ek16, dk16, cv, Kv, Kdv
+    del hek, hm, hck, hct, hctk, hc, hscratch, ek16, dk16, cv, Kv, Kdv
+    for ptr in wc_allocs:
+        lib.mlkem_b200_host_free(ptr)
     os.sched_setaffinity(0, all_cpus)  # the CPU baseline below uses every host core again
     sampler.stop()
 
@@ -564,10 +582,7 @@ def cross_n_digest(kem, wl, torch, dist, dev, rank, world):
     wl.tamper_inplace(ct, lo)
     Kd = kem.decaps(PS, dk, ct)
     torch.cuda.synchronize()
-    mine = {}
-    for name, t in (("c", c), ("K", K), ("Kd", Kd)):
-        h = t.cpu().numpy()
-        mine[name] = b"".join(hashlib.sha256(h[b : b + blk].tobytes()).digest() for b in range(0, hi - lo, blk))
+    mine = {name: wl.block_hashes(t.cpu().numpy(), blk) for name, t in (("c", c), ("K", K), ("Kd", Kd))}
     per_rank = {k: hashlib.sha256(v).hexdigest() for k, v in mine.items()}
     if dist is not None:
         parts = [None] * world
@@ -576,7 +591,7 @@ def cross_n_digest(kem, wl, torch, dist, dev, rank, world):
         parts = [mine]
     if rank != 0:
         return None
-    got = {k: hashlib.sha256(b"".join(p[k] for p in parts)).hexdigest() for k in ("c", "K", "Kd")}
+    got = {k: wl.combine_block_hashes([p[k] for p in parts]) for k in ("c", "K", "Kd")}
     ok = got == fixture["digest"]
     assert ok, f"cross-N digest mismatch at {world} ranks: {got} != {fixture['digest']}"
     return {"items_total": total, "ranks": world, "block_items": blk, "sha256_of_block_sha256s": got, "rank0_shard_sha256": per_rank,

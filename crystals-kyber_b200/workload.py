@@ -67,6 +67,26 @@ def tamper_inplace(c, begin: int):
     return sel
 
 
+# Checksum of checksums (SURVEY.md 8(e) "concatenated outputs at G = 1, 2, 4, 8 are byte-identical"): an output array is cut into
+# blocks of `block` consecutive items, each block hashed, and the digest is the hash of the concatenated block hashes.  A rank
+# whose shard starts and ends on block boundaries computes its part alone; concatenating the parts in rank order gives the digest
+# of the whole range whatever the number of ranks.
+def block_hashes(array, block: int) -> bytes:
+    """sha256 of every `block`-item slice of a host array (numpy, item-major), concatenated."""
+    import hashlib
+
+    a = np.ascontiguousarray(array)
+    assert a.shape[0] % block == 0, "a shard must be a whole number of blocks"
+    return b"".join(hashlib.sha256(a[b : b + block].tobytes()).digest() for b in range(0, a.shape[0], block))
+
+
+def combine_block_hashes(parts) -> str:
+    """parts: the block_hashes() of the shards in rank order.  Returns the hex digest of the whole range."""
+    import hashlib
+
+    return hashlib.sha256(b"".join(parts)).hexdigest()
+
+
 # Algorithmic work model (SURVEY.md 8(d)), in 32-bit integer-pipe operations.
 OPS_KECCAK_F = 24 * 180            # 4 320
 OPS_NTT = 896 * 5                  # 4 480

@@ -1008,3 +1008,47 @@ def test_asynchronous_host_calls(mlkem, oracle):
         assert (hc.numpy() == c_ref).all() and (hK.numpy() == K_ref).all() and (hKd.numpy() == K_ref).all()
     sl = slice(1000, 1300)
     assert (K_ref[sl] == oracle.encaps(768, ek[sl], m[sl])[1]).all()
+
+
+def test_concurrent_host_threads(mlkem, oracle):
+    """Several host threads in the library at once (ctypes releases the GIL): blocking host-memory calls alternate between the
+    two staging-slot groups, device-memory calls share the workspaces through the slot events.  Every result must be exact."""
+    import threading
+
+    import torch
+
+    rng = np.random.default_rng(77)
+    n = 70_000  # two chunks per host call
+    d, z = (rng.integers(0, 256, (n, 32), dtype=np.uint8) for _ in range(2))
+    ek, dk = oracle.keygen(768, d, z)
+    ms = [rng.integers(0, 256, (n, 32), dtype=np.uint8) for _ in range(4)]
+    want = [oracle.encaps(768, ek, m) for m in ms]
+    results, errors = {}, []
+
+    def host_worker(i):
+        try:
+            c, K = mlkem.encaps(768, ek, ms[i])
+            results[i] = (c, K, mlkem.decaps(768, dk, c))
+        except Exception as e:  # pragma: no cover
+            errors.append(e)
+
+    def device_worker(i):
+        try:
+            torch.cuda.set_device(0)
+            with torch.cuda.stream(torch.cuda.Stream()):
+                c, K = mlkem.encaps(768, torch.from_numpy(ek).cuda(), torch.from_numpy(ms[i]).cuda())
+                Kd = mlkem.decaps(768, torch.from_numpy(dk).cuda(), c)
+                torch.cuda.current_stream().synchronize()
+            results[i] = (c.cpu().numpy(), K.cpu().numpy(), Kd.cpu().numpy())
+        except Exception as e:  # pragma: no cover
+            errors.append(e)
+
+    threads = [threading.Thread(target=host_worker if i % 2 == 0 else device_worker, args=(i,)) for i in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    for i in range(4):
+        c, K, Kd = results[i]
+        assert first_mismatch(c, want[i][0]) == -1 and first_mismatch(K, want[i][1]) == -1 and first_mismatch(Kd, want[i][1]) == -1

@@ -106,3 +106,57 @@ def test_two_rank_sharded_run_matches_single_rank(oracle):
     for b, e, digest, n_equal in gathered:
         assert hashlib.sha256(ek[b:e].tobytes() + c[b:e].tobytes() + Kd[b:e].tobytes()).digest() == digest
         assert n_equal == (e - b) - len([i for i in range(b, e) if i % 10 == 3])
+
+
+def _digest_worker(rank, world, port, total, blk, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle.oracle import Oracle
+
+    orc = Oracle()
+    b, e = shard_range(total, rank, world)
+    d, z, m = wl.derive_inputs(lambda msg, ln: orc.hash_batch(1, msg, ln), b, e)
+    ek, dk = orc.keygen(768, d, z)
+    c, K = orc.encaps(768, ek, m)
+    ct = c.copy()
+    wl.tamper_inplace(ct, b)
+    Kd = orc.decaps(768, dk, ct)
+    mine = {name: wl.block_hashes(a, blk) for name, a in (("c", c), ("K", K), ("Kd", Kd))}
+    parts = [None] * world
+    dist.all_gather_object(parts, mine)
+    if rank == 0:
+        q.put({k: wl.combine_block_hashes([p[k] for p in parts]) for k in ("c", "K", "Kd")})
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_checksum_of_checksums_is_independent_of_the_rank_count(oracle):
+    """The cross-N digest of bench.py (crystals-kyber_b200/workload.py block_hashes / combine_block_hashes): two gloo ranks
+    over global items [0, 256) in blocks of 64 give the digest of a single-process run -- and the committed fixture
+    tests/golden/config4_digest.json is this very construction over 2^20 items in blocks of 2^14 (its first block is
+    recomputed here)."""
+    import json
+
+    total, blk = 256, 64
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_digest_worker, args=(r, 2, port, total, blk, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    d, z, m = wl.derive_inputs(lambda msg, ln: oracle.hash_batch(1, msg, ln), 0, total)
+    ek, dk = oracle.keygen(768, d, z)
+    c, K = oracle.encaps(768, ek, m)
+    ct = c.copy()
+    wl.tamper_inplace(ct, 0)
+    Kd = oracle.decaps(768, dk, ct)
+    want = {name: wl.combine_block_hashes([wl.block_hashes(a, blk)]) for name, a in (("c", c), ("K", K), ("Kd", Kd))}
+    assert got == want
+    fixture = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "config4_digest.json")))
+    assert fixture["log2_items"] == 20 and fixture["log2_block"] == 14 and set(fixture["digest"]) == {"c", "K", "Kd"}
+    with pytest.raises(AssertionError):
+        wl.block_hashes(c[:100], blk)  # a shard must be a whole number of blocks
