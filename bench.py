@@ -311,22 +311,22 @@ def main():
     ne = 1 << (args.e2e_log2_items if args.e2e_log2_items is not None else args.log2_items)
     ne = min(ne, n)
 
-    wc_allocs = []
+    wc_allocs, wc_bytes = [], [0, 0]  # write-combined / ordinary pinned bytes of the e2e input buffers
 
     def pinned_copy(t):
         """Host copy of a device tensor in an INPUT buffer of the e2e legs: pinned and, unless --no-wc-inputs, write-combined
         (mlkem_b200_host_alloc_wc).  The CPU only ever fills these buffers; write-combined pages are not snooped when the GPU
         reads them, which is worth nothing on one GPU and 7 % (H2D alone) to 44 % (both directions busy) of the box's aggregate
         copy rate with eight (tools/pcie_bw.py, profiles/pcie_bw_r02_8gpu.json)."""
-        if args.no_wc_inputs:
-            h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
-        else:
-            nbytes = t.numel() * t.element_size()
-            ptr = lib.mlkem_b200_host_alloc_wc(nbytes)
-            if not ptr:
-                raise MemoryError("mlkem_b200_host_alloc_wc failed")
+        nbytes = t.numel() * t.element_size()
+        ptr = None if args.no_wc_inputs else lib.mlkem_b200_host_alloc_wc(nbytes)
+        if ptr:
             wc_allocs.append(ptr)
+            wc_bytes[0] += nbytes
             h = torch.frombuffer((C.c_ubyte * nbytes).from_address(ptr), dtype=torch.uint8).view(t.dtype).view(t.shape)
+        else:  # write-combined mappings are a limited resource (8 ranks x 20 GB did not fit on the 8-GPU box): ordinary pinned memory
+            wc_bytes[1] += nbytes
+            h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
         h.copy_(t)
         return h
 
@@ -394,7 +394,8 @@ def main():
     ceil_s = timed_host(lambda: probe_pair([hek, hm], hscratch[:2], [hdk, hct], hscratch[2:]))
     e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "items_per_gpu": ne,
            "ms_per_step": 1e3 * e2e_s / steps, "h2d_GBps_per_gpu": h2d * steps / e2e_s / 1e9,
-           "input_buffers": "pinned" if args.no_wc_inputs else "pinned, write-combined (mlkem_b200_host_alloc_wc)",
+           "input_buffers": {"write_combined_bytes": wc_bytes[0], "pinned_bytes": wc_bytes[1],
+                             "note": "input buffers are write-combined (mlkem_b200_host_alloc_wc) where the box grants it, else ordinary pinned memory"},
            "path": "mlkem_b200_encaps_batch + mlkem_b200_decaps_batch with MLKEM_B200_MEM_HOST (pinned buffers), distinct keys per item; the two "
                    "calls of a step are issued with MLKEM_B200_FLAG_ASYNC and followed by one mlkem_b200_synchronize",
            "blocking_calls": {"value": world * ne * steps / e2e_sync_s, "unit": UNIT, "ms_per_step": 1e3 * e2e_sync_s / steps,
@@ -526,10 +527,13 @@ def main():
         "peak_source": "measured live: mlkem_b200_int32_peak (LOP3/SHF issue rate, alu pipe); MEASURED_PEAKS.json has no integer figure",
         "algorithmic_ops_per_item": ops["matvec_encrypt"], "items_per_launch": items_per_launch,
         "avg_launch_ms": mv_ms / max(mv_launches, 1), "share_of_step_kernel_time": mv_ms / total_kernel_ms if total_kernel_ms else None,
-        # dram__bytes_read.sum + dram__bytes_write.sum from the committed ncu --set full capture
-        # (profiles/ncu_kem_kernels_r01_final_summary.csv, one 65 536-item launch: fused kernel 133.7 + 40.6 MB, clean-up pass
-        # 8.5 MB = 2 790 B/item), scaled to this run's launch
-        "traffic": 2790.0 * items_per_launch, "traffic_bytes_per_item": 2790, "algorithmic_bytes_per_item": 32 + 1536 + 384 + 960,
+        # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed ncu --set full capture of this round
+        # (profiles/ncu_kem_kernels_r02_summary.csv, 65 536-item launches of tools/prof_kem.py: Encaps' store-mode launch
+        # 133.7 + 42.1 MB and its clean-up pass 8.7 MB = 2 815 B/item; Decaps' compare-mode launch 199.7 + 4.2 MB and its clean-up
+        # pass 10.8 MB = 3 276 B/item), scaled to this run's launch size -- a figure derived from that capture, not re-measured here
+        "traffic": 0.5 * (2815.0 + 3276.0) * items_per_launch, "traffic_bytes_per_item": {"encrypt_store": 2815, "encrypt_compare": 3276},
+        "traffic_source": "profiles/ncu_kem_kernels_r02_summary.csv (ncu --set full, tools/prof_kem.py), scaled by items_per_launch",
+        "algorithmic_bytes_per_item": 32 + 1536 + 384 + 960,
         "whole_step": {"algorithmic_ops_per_pair": ops["encaps"] + ops["decaps"],
                        "achieved": (ops["encaps"] + ops["decaps"]) * value / world / 1e12, "frac": (ops["encaps"] + ops["decaps"]) * value / world / peak},
         "peaks_tera_ops": {k: v / 1e12 for k, v in peaks.items()},

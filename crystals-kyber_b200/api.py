@@ -295,6 +295,18 @@ class MLKEM:
         n = self._count(f, 256)
         return self._call("mlkem_b200_multiply_ntts_batch", (n,), [(f, np.uint16), (g, np.uint16)], [((n, 256), np.uint16)])
 
+    def poly_add(self, u, v):
+        n = self._count(u, 256)
+        return self._call("mlkem_b200_poly_add_batch", (n,), [(u, np.uint16), (v, np.uint16)], [((n, 256), np.uint16)])
+
+    def poly_sub(self, u, v):
+        n = self._count(u, 256)
+        return self._call("mlkem_b200_poly_sub_batch", (n,), [(u, np.uint16), (v, np.uint16)], [((n, 256), np.uint16)])
+
+    def vector_multiply(self, u, v, k):
+        n = self._count(u, 256 * k)
+        return self._call("mlkem_b200_vector_multiply_batch", (k, n), [(u, np.uint16), (v, np.uint16)], [((n, 256), np.uint16)])
+
     # ------------------------------------------------------------------ samplers
     def sample_ntt(self, seeds34, return_seeds=False):
         n = self._count(seeds34, 34)

@@ -966,6 +966,25 @@ int mlkem_b200_multiply_ntts_batch(size_t n, const uint16_t *f, const uint16_t *
     });
 }
 
+static int addsub_impl(size_t n, const uint16_t *u, const uint16_t *v, uint16_t *z, const mlkem_b200_opts *o, bool sub) {
+    return drive(o, n * 32, 0, {{u, nullptr, 16}, {v, nullptr, 16}, {nullptr, z, 16}}, [=](cudaStream_t st, Arena &, int cn, void **p, size_t) {
+        unsigned grid = cdiv(cn, kPrimTPB);
+        if (grid > 148 * 32) grid = 148 * 32;
+        if (sub) LAUNCH((k_poly_addsub<true>), grid, kPrimTPB, 0, st, (long long)cn, (const uint4 *)p[0], (const uint4 *)p[1], (uint4 *)p[2]);
+        else LAUNCH((k_poly_addsub<false>), grid, kPrimTPB, 0, st, (long long)cn, (const uint4 *)p[0], (const uint4 *)p[1], (uint4 *)p[2]);
+        return 0;
+    });
+}
+int mlkem_b200_poly_add_batch(size_t n, const uint16_t *u, const uint16_t *v, uint16_t *z, const mlkem_b200_opts *o) { return addsub_impl(n, u, v, z, o, false); }
+int mlkem_b200_poly_sub_batch(size_t n, const uint16_t *u, const uint16_t *v, uint16_t *z, const mlkem_b200_opts *o) { return addsub_impl(n, u, v, z, o, true); }
+int mlkem_b200_vector_multiply_batch(int k, size_t n, const uint16_t *u, const uint16_t *v, uint16_t *w, const mlkem_b200_opts *o) {
+    if (k < 1 || k > 16) return MLKEM_B200_ERR_ARG;
+    return drive(o, n, 0, {{u, nullptr, (size_t)512 * k}, {v, nullptr, (size_t)512 * k}, {nullptr, w, 512}}, [=](cudaStream_t st, Arena &, int cn, void **p, size_t) {
+        LAUNCH(k_vecmul_batch, prim_grid(cn), kPrimTPB, 0, st, cn, k, (const uint16_t *)p[0], (const uint16_t *)p[1], (uint16_t *)p[2]);
+        return 0;
+    });
+}
+
 int mlkem_b200_sample_ntt_batch(size_t n, const uint8_t *seeds, uint16_t *a, uint8_t *seeds_after, const mlkem_b200_opts *o) {
     const int gl = group_limit_of(o);
     std::vector<Buf> bufs = {{seeds, nullptr, 34}, {nullptr, a, 512}};

@@ -274,8 +274,8 @@ __global__ void __launch_bounds__(kHashTPB) k_decaps_J_select(int n, const uint8
     }
 }
 
-// Generic batched hash (H / G / J) over equal-length messages, length a multiple of 8 bytes.
-// which: 0 = H (SHA3-256, 32 B out), 1 = G (SHA3-512, 64 B out), 2 = J (SHAKE128, 32 B out).
+// Generic batched hash over equal-length messages, length a multiple of 8 bytes.  RATE (lanes) and the suffix select the
+// function, OUTW the output lanes: H = <17, 4> + 0x06, G = <9, 8> + 0x06, J = <21, 4> + 0x1F (the host maps `which` to these).
 template <int RATE, int OUTW>
 __global__ void __launch_bounds__(kHashTPB) k_hash_words(int n, const uint8_t *__restrict__ in, int nwords, uint32_t sfx,
                                                          uint8_t *__restrict__ out) {
@@ -1356,6 +1356,58 @@ __global__ void __launch_bounds__(kPrimTPB) k_mulntt_batch(int n, const uint16_t
             basemul_acc(c0, c1, a & 0xFFFu, (a >> 16) & 0xFFFu, b & 0xFFFu, (b >> 16) & 0xFFFu, gam[r]);
             hw[t] = canon32(c0) | (canon32(c1) << 16);
         }
+    }
+}
+
+// ml_kem.c:580 PolyAddition / :599 PolySubtraction, element-wise on 12-bit coefficients (8 per thread).  Restated literally:
+// the sum is reduced ((u + v) % q), the difference is `u < v ? q - (v - u) : u - v` kept in a 12-bit field -- it stays
+// unreduced when u - v >= q, like in the reference.  On the KEM path both are fused into their consumers (matvec_row_tail,
+// k_encrypt_v, k_decrypt); these kernels serve the stand-alone entry points.
+template <bool SUB>
+__global__ void __launch_bounds__(kPrimTPB) k_poly_addsub(long long nvec, const uint4 *__restrict__ u, const uint4 *__restrict__ v,
+                                                          uint4 *__restrict__ z) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+        const uint4 a4 = __ldg(u + i), b4 = __ldg(v + i);
+        const uint32_t a[4] = {a4.x, a4.y, a4.z, a4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
+        uint32_t o[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            uint32_t r[2];
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const uint32_t x = (a[k] >> (16 * h)) & 0xFFFu, y = (b[k] >> (16 * h)) & 0xFFFu;
+                r[h] = SUB ? ((x < y ? kQ - (y - x) : x - y) & 0xFFFu) : canon16(x + y);
+            }
+            o[k] = r[0] | (r[1] << 16);
+        }
+        z[i] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+}
+// ml_kem.c:618 VectorMultiply: w = sum over i < k of MultiplyNTTs(u[i], v[i]); one item per warp, operands any 12-bit value.
+__global__ void __launch_bounds__(kPrimTPB) k_vecmul_batch(int n, int k, const uint16_t *__restrict__ u, const uint16_t *__restrict__ v,
+                                                           uint16_t *__restrict__ w) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint2 gam[4];
+#pragma unroll
+    for (int r = 0; r < 4; r++) gam[r] = lane_gamma(lane + 32 * r);
+    for (long long p = (long long)blockIdx.x * (kPrimTPB / 32) + warp; p < n; p += (long long)gridDim.x * (kPrimTPB / 32)) {
+        uint32_t acc[8];
+#pragma unroll
+        for (int r = 0; r < 8; r++) acc[r] = 0;
+        for (int j = 0; j < k; j++) {
+            const uint32_t *uw = reinterpret_cast<const uint32_t *>(u + 256 * (p * k + j)), *vw = reinterpret_cast<const uint32_t *>(v + 256 * (p * k + j));
+#pragma unroll
+            for (int r = 0; r < 4; r++) {
+                const uint32_t a = __ldg(uw + lane + 32 * r), b = __ldg(vw + lane + 32 * r);
+                uint32_t c0 = 0, c1 = 0;  // every product is reduced before it is added (MultiplyNTTs then PolyAddition)
+                basemul_acc(c0, c1, a & 0xFFFu, (a >> 16) & 0xFFFu, b & 0xFFFu, (b >> 16) & 0xFFFu, gam[r]);
+                acc[2 * r] += canon32(c0);
+                acc[2 * r + 1] += canon32(c1);
+            }
+        }
+        uint32_t *ww = reinterpret_cast<uint32_t *>(w + 256 * p);
+#pragma unroll
+        for (int r = 0; r < 4; r++) ww[lane + 32 * r] = canon16(acc[2 * r]) | (canon16(acc[2 * r + 1]) << 16);
     }
 }
 

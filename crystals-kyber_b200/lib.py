@@ -63,6 +63,9 @@ SIGNATURES = {
     "mlkem_b200_ntt_batch": (C.c_int, [C.c_size_t, _P16, _P16, _PO]),
     "mlkem_b200_intt_batch": (C.c_int, [C.c_size_t, _P16, _P16, _PO]),
     "mlkem_b200_multiply_ntts_batch": (C.c_int, [C.c_size_t, _P16, _P16, _P16, _PO]),
+    "mlkem_b200_poly_add_batch": (C.c_int, [C.c_size_t, _P16, _P16, _P16, _PO]),
+    "mlkem_b200_poly_sub_batch": (C.c_int, [C.c_size_t, _P16, _P16, _P16, _PO]),
+    "mlkem_b200_vector_multiply_batch": (C.c_int, [C.c_int, C.c_size_t, _P16, _P16, _P16, _PO]),
     "mlkem_b200_sample_ntt_batch": (C.c_int, [C.c_size_t, _P8, _P16, _P8, _PO]),
     "mlkem_b200_cbd_batch": (C.c_int, [C.c_int, C.c_size_t, _P8, _P16, _PO]),
     "mlkem_b200_prf_cbd_batch": (C.c_int, [C.c_int, C.c_size_t, _P8, _P8, _P16, _PO]),

@@ -214,6 +214,14 @@ int mlkem_b200_intt_batch(size_t n, const uint16_t *f_hat, uint16_t *f, const ml
 int mlkem_b200_multiply_ntts_batch(size_t n, const uint16_t *f_hat, const uint16_t *g_hat, uint16_t *h_hat,
                                    const mlkem_b200_opts *opts);
 
+/* PolyAddition, ml_kem.c:580: (u + v) mod q coefficient-wise; PolySubtraction, ml_kem.c:599: u < v ? q - (v - u) : u - v,
+ * kept in 12 bits (unreduced when u - v >= q, like the reference).  n polynomials each. */
+int mlkem_b200_poly_add_batch(size_t n, const uint16_t *u, const uint16_t *v, uint16_t *z, const mlkem_b200_opts *opts);
+int mlkem_b200_poly_sub_batch(size_t n, const uint16_t *u, const uint16_t *v, uint16_t *z, const mlkem_b200_opts *opts);
+/* VectorMultiply, ml_kem.c:618: w = sum_{i<k} MultiplyNTTs(u[i], v[i]).  u, v: n x k x 256, w: n x 256; 1 <= k <= 16. */
+int mlkem_b200_vector_multiply_batch(int k, size_t n, const uint16_t *u, const uint16_t *v, uint16_t *w,
+                                     const mlkem_b200_opts *opts);
+
 /* ---- samplers -------------------------------------------------------------------------------------- */
 
 /* SampleNTT, ml_kem.c:189.  seeds: n x 34.  a_hat: n x 256.  seeds_after (may be NULL): n x 34, the caller's

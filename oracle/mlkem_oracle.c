@@ -663,6 +663,18 @@ ORC_API void orc_multiply_ntts_batch(size_t n, const uint16_t *f, const uint16_t
 #pragma omp parallel for schedule(static)
     for (long long i = 0; i < (long long)n; i++) orc_multiply_ntts(f + i * ORC_N, g + i * ORC_N, h + i * ORC_N);
 }
+ORC_API void orc_poly_add_batch(size_t n, const uint16_t *u, const uint16_t *v, uint16_t *z) {
+#pragma omp parallel for schedule(static)
+    for (long long i = 0; i < (long long)n; i++) orc_poly_add(u + i * ORC_N, v + i * ORC_N, z + i * ORC_N);
+}
+ORC_API void orc_poly_sub_batch(size_t n, const uint16_t *u, const uint16_t *v, uint16_t *z) {
+#pragma omp parallel for schedule(static)
+    for (long long i = 0; i < (long long)n; i++) orc_poly_sub(u + i * ORC_N, v + i * ORC_N, z + i * ORC_N);
+}
+ORC_API void orc_vector_multiply_batch(size_t n, unsigned k, const uint16_t *u, const uint16_t *v, uint16_t *w) {
+#pragma omp parallel for schedule(static)
+    for (long long i = 0; i < (long long)n; i++) orc_vector_multiply(u + i * k * ORC_N, v + i * k * ORC_N, k, w + i * ORC_N);
+}
 ORC_API void orc_sample_ntt_batch(size_t n, const uint8_t *seeds34, uint16_t *a) {
 #pragma omp parallel for schedule(static)
     for (long long i = 0; i < (long long)n; i++) {

@@ -150,6 +150,20 @@ class Oracle(_Lib):
     def multiply_ntts(self, f, g):
         return self._polys("multiply_ntts_batch", f, g)
 
+    def poly_add(self, u, v):
+        return self._polys("poly_add_batch", u, v)
+
+    def poly_sub(self, u, v):
+        return self._polys("poly_sub_batch", u, v)
+
+    def vector_multiply(self, u, v, k):
+        uu, pu = _u16(u)
+        vv, pv = _u16(v)
+        n = uu.size // (256 * k)
+        out = np.empty((n, 256), np.uint16)
+        self.fn("vector_multiply_batch")(C.c_size_t(n), C.c_uint(k), pu, pv, out.ctypes.data_as(C.POINTER(C.c_uint16)))
+        return out
+
     def sample_ntt(self, seeds34):
         s, ps = _u8(seeds34)
         n = s.size // 34
@@ -367,6 +381,13 @@ class Reference(_Lib):
 
     def poly_sub(self, f, g):
         return self._poly("poly_sub", f, g)
+
+    def vector_multiply(self, u, v, k):
+        _, pu = _u16(u)
+        _, pv = _u16(v)
+        out = np.empty(256, np.uint16)
+        self.fn("vector_multiply")(C.c_uint(k), pu, pv, out.ctypes.data_as(C.POINTER(C.c_uint16)))
+        return out
 
     def basecase_multiply(self, a0, a1, b0, b1, gamma):
         out = (C.c_uint16 * 2)()

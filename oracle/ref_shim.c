@@ -155,6 +155,19 @@ REF_API void ref_poly_sub(const uint16_t u[256], const uint16_t v[256], uint16_t
     from_ui(o, 256, z);
     free(o); free(a); free(b);
 }
+/* ml_kem.c:618 VectorMultiply on k polynomials each (u, v: k x 256 contiguous). */
+REF_API void ref_vector_multiply(unsigned k, const uint16_t *u, const uint16_t *v, uint16_t w[256]) {
+    union integer *up[16], *vp[16];
+    if (k > 16) return;
+    for (unsigned i = 0; i < k; i++) {
+        up[i] = to_ui(u + 256 * i, 256);
+        vp[i] = to_ui(v + 256 * i, 256);
+    }
+    union integer *o = VectorMultiply(up, vp, k);
+    from_ui(o, 256, w);
+    free(o);
+    for (unsigned i = 0; i < k; i++) { free(up[i]); free(vp[i]); }
+}
 REF_API void ref_PRF(const uint8_t s[32], uint8_t b, unsigned eta, uint8_t *out) {
     union byte *S = to_ub(s, 32), B;
     B.e = 0;

@@ -12,6 +12,8 @@ Kept apart from make_golden.py so that the round-1 fixtures stay byte-identical.
                    with zeta overflows a signed int (:366-368).  The two builds DISAGREE; one input with both outputs is
                    recorded as evidence that there is no reference behaviour to reproduce.
   decaps_random    Decaps_internal / PKE_Decrypt on decapsulation keys made of random bytes (s^, t^ coefficients >= q, D4).
+  addsub, vector_multiply
+                   PolyAddition / PolySubtraction (ml_kem.c:580, :599) incl. 12-bit operands, VectorMultiply (:618), k = 2, 3, 4.
 """
 import hashlib
 import json
@@ -70,6 +72,24 @@ def main():
             mp = r.pke_decrypt(ps, dk[: sz["dk_pke"]].tobytes(), c.tobytes())
             dec.append({"set": ps, "dk": dk.tobytes().hex(), "c": c.tobytes().hex(), "K": K.hex(), "m": mp.hex()})
     v["decaps_random"] = dec
+    # PolyAddition / PolySubtraction (ml_kem.c:580, :599) on 12-bit operands, VectorMultiply (:618) for k = 2, 3, 4
+    ring = []
+    for t in range(4):
+        u = rng.integers(0, 4096 if t >= 2 else 3329, 256, dtype=np.uint16)
+        w = rng.integers(0, 4096 if t >= 2 else 3329, 256, dtype=np.uint16)
+        a, b = r.poly_add(u, w), r.poly_sub(u, w)
+        assert (a == rg.poly_add(u, w)).all() and (b == rg.poly_sub(u, w)).all()
+        ring.append({"u": u.tobytes().hex(), "v": w.tobytes().hex(), "add": a.tobytes().hex(), "sub": b.tobytes().hex()})
+    v["addsub"] = ring
+    vm = []
+    for k in (2, 3, 4):
+        for hi in (3329, 4096):
+            u = rng.integers(0, hi, (k, 256), dtype=np.uint16)
+            w = rng.integers(0, 3329, (k, 256), dtype=np.uint16)
+            o = r.vector_multiply(u, w, k)
+            assert (o == rg.vector_multiply(u, w, k)).all()
+            vm.append({"k": k, "u": u.tobytes().hex(), "v": w.tobytes().hex(), "w": o.tobytes().hex()})
+    v["vector_multiply"] = vm
     out = os.path.join(ROOT, "tests", "golden", "ref_vectors_r02.json")
     json.dump(v, open(out, "w"), indent=0, sort_keys=True)
     print("wrote", out, os.path.getsize(out), "bytes", hashlib.sha256(open(out, "rb").read()).hexdigest()[:16])

@@ -1052,3 +1052,35 @@ def test_concurrent_host_threads(mlkem, oracle):
     for i in range(4):
         c, K, Kd = results[i]
         assert first_mismatch(c, want[i][0]) == -1 and first_mismatch(K, want[i][1]) == -1 and first_mismatch(Kd, want[i][1]) == -1
+
+
+def test_poly_add_sub_vector_multiply(mlkem, oracle, ref_vectors, ref_vectors_r02):
+    """The stand-alone PolyAddition / PolySubtraction / VectorMultiply entry points (ml_kem.c:580, :599, :618): reference
+    vectors, then random batches against the oracle, 12-bit operands included (the difference stays unreduced when
+    u - v >= q, like in the reference)."""
+    import torch
+
+    for rec in ref_vectors["ring"]:
+        f, g = h2a(rec["f"], np.uint16), h2a(rec["g"], np.uint16)
+        assert (mlkem.poly_add(f % 3329, g)[0] == h2a(rec["add"], np.uint16)).all()
+        assert (mlkem.poly_sub(f % 3329, g)[0] == h2a(rec["sub"], np.uint16)).all()
+    for rec in ref_vectors_r02["addsub"]:
+        u, v = h2a(rec["u"], np.uint16), h2a(rec["v"], np.uint16)
+        assert (mlkem.poly_add(u, v)[0] == h2a(rec["add"], np.uint16)).all()
+        assert (mlkem.poly_sub(u, v)[0] == h2a(rec["sub"], np.uint16)).all()
+    for rec in ref_vectors_r02["vector_multiply"]:
+        u, v = h2a(rec["u"], np.uint16), h2a(rec["v"], np.uint16)
+        assert (mlkem.vector_multiply(u, v, rec["k"])[0] == h2a(rec["w"], np.uint16)).all()
+    rng = np.random.default_rng(580)
+    for n in (1, 33, 5000):
+        u, v = rng_polys(rng, n, 4096), rng_polys(rng, n, 4096)
+        assert first_mismatch(mlkem.poly_add(u, v), oracle.poly_add(u, v)) == -1
+        got = mlkem.poly_sub(u, v)
+        assert first_mismatch(got, oracle.poly_sub(u, v)) == -1
+        if n > 1:
+            assert (got >= 3329).any()
+        for k in (2, 3, 4):
+            uu, vv = rng.integers(0, 4096, (n, k, 256), dtype=np.uint16), rng.integers(0, 3329, (n, k, 256), dtype=np.uint16)
+            want = oracle.vector_multiply(uu, vv, k)
+            assert first_mismatch(mlkem.vector_multiply(uu, vv, k), want) == -1
+            assert first_mismatch(mlkem.vector_multiply(torch.from_numpy(uu).cuda(), torch.from_numpy(vv).cuda(), k).cpu().numpy(), want) == -1
