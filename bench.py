@@ -66,7 +66,7 @@ def reference_pairs_per_s(threads: int, pairs_per_thread: int, steps: int, warmu
     out = {"cores": threads, "sample": f"{n} ML-KEM-768 encaps+decaps pairs per step on {threads} threads"}
     if os.path.exists(REF_SO):
         ref = Reference(REF_SO)
-        for _ in range(warmup):  # a warm-up step is one pair per thread (28 ms per operation: nothing to warm but the caches)
+        for _ in range(warmup):  # a warm-up step is one pair per thread (20 ms per operation: nothing to warm but the caches)
             ref.time_pairs(PS, ek[:threads], dk[:threads], m[:threads], threads)
         out["warmup_steps_run"] = warmup
         ts = [ref.time_pairs(PS, ek, dk, m, threads)[0] for _ in range(steps)]
@@ -106,7 +106,7 @@ def run_reference_arm(args):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    # 32 pairs per thread and step: about 2 s per step at 28 ms per operation, whatever the core count
+    # 32 pairs per thread and step: about 1.3 s per step at 20 ms per operation, whatever the core count
     r = reference_pairs_per_s(threads, 32, max(1, args.steps), max(0, args.warmup))
     emit({
         "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
@@ -694,7 +694,7 @@ def caller_view(kem):
                 lat[name].append(dt * 1e6)
     out = {"drop_in_api_latency_us": {k: {"median": statistics.median(v), "min": min(v)} for k, v in lat.items()},
            "drop_in_api_note": "include/ml_kem.h entry points, one operation per call: layout conversion + H2D + the kernel chain of one item "
-                               "+ D2H + synchronise; the reference takes ~28 ms per operation at -O2 (cpu_baseline)"}
+                               "+ D2H + synchronise; the reference takes about 20 ms per operation at -O2 (cpu_baseline.O2_1thread_pairs_per_s)"}
     rng = np.random.default_rng(7)
     nmax = 1 << 14
     d, z, m = (rng.integers(0, 256, (nmax, 32), dtype=np.uint8) for _ in range(3))
