@@ -30,5 +30,12 @@ for pat in 'k_sample_matvec<.*3, 2, 2, 10, 4>, 1>' 'k_sample_matvec<.*3, 2, 2, 1
            'k_encaps_HG<.*3, 2, 2, 10, 4>' 'k_decaps_J_select<.*3, 2, 2, 10, 4>, 21' 'k_ntt_batch' 'k_intt_batch' 'k_mulntt_batch'; do
     python3 tools/sass_static.py crystals-kyber_b200/libmlkem_b200.so "$pat"
 done
+echo
+echo "# loop bodies (tools/sass_loop.py): the Keccak loop holds TWO rounds = 244 LOP3 + 116 SHF, i.e. 122 LOP3 + 58 SHF = 180 alu-pipe"
+echo "# instructions per round; in the fused kernel: the Keccak loop, the three-block sampling loop around it (both parser variants),"
+echo "# and phase 2 (one row per iteration)"
+python3 tools/sass_loop.py crystals-kyber_b200/libmlkem_b200.so 'k_decaps_G<.*3, 2, 2, 10, 4>'
+python3 tools/sass_loop.py crystals-kyber_b200/libmlkem_b200.so 'k_sample_matvec<.*3, 2, 2, 10, 4>, 1>'
+python3 tools/sass_loop.py crystals-kyber_b200/libmlkem_b200.so 'k_matvec_table<.*3, 2, 2, 10, 4>, 1>'
 } > $hist
 echo "wrote $hist"
