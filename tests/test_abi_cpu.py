@@ -92,6 +92,17 @@ def test_no_cpu_fallback(lib):
 
     with pytest.raises(ck.MlKemB200Error):
         ck.MLKEM().keygen(768, np.zeros((1, 32), np.uint8), np.zeros((1, 32), np.uint8))
+    # round-2 entry points: a key table cannot be built, the cell-layout calls and the copy probe refuse as well
+    handle = C.c_void_p(123)
+    dk = np.zeros((1, 2400), np.uint8)
+    assert lib.mlkem_b200_keys_load(768, 1, C.c_void_p(dk.ctypes.data), None, None, C.byref(handle)) == -10 and not handle.value
+    with pytest.raises(ck.MlKemB200Error):
+        ck.MLKEM().keys_load(768, dk=dk)
+    cells = np.zeros((1, 2400), np.uint32)
+    with pytest.raises(ck.MlKemB200Error):
+        ck.MLKEM().decaps_cells(768, cells, np.zeros((1, 1088), np.uint32))
+    assert lib.mlkem_b200_keys_count(None) == 0
+    lib.mlkem_b200_keys_free(None)  # a no-op
 
 
 def test_product_does_not_import_oracle():
@@ -144,6 +155,16 @@ def test_arithmetic_lemmas():
         want = (((xr % u(q)) << np.uint64(dd)) + u(1664)) // u(q) % u(1 << dd)
         exact = (mulhi((xr << np.uint64(dd)) + u(1664), M) % u(1 << dd) == want).all()
         assert exact == (dd <= 5)
+    # the literal NTT butterfly for inputs >= q (ct_bfly_exact): Shoup product with the 16-bit quotient, one conditional
+    # subtraction, for every 12-bit operand and every zeta; and canon16 on sums below 4096 + q
+    zetas = np.array([pow(17, int(f"{i:07b}"[::-1], 2), q) for i in range(128)], dtype=np.uint64)
+    bb = np.arange(4096, dtype=np.uint64)[:, None]
+    wy = (zetas << np.uint64(16)) // u(q)
+    r = bb * zetas - ((bb * wy) >> np.uint64(16)) * u(q)
+    assert (r < 2 * q).all() and (np.where(r >= q, r - u(q), r) == bb * zetas % u(q)).all()
+    xs = np.arange(4096 + q, dtype=np.uint64)
+    b16 = xs - ((xs * u(40317)) >> np.uint64(27)) * u(q)  # barrett16: result in [0, q]
+    assert (b16 <= q).all() and (np.where(b16 >= q, b16 - u(q), b16) == xs % u(q)).all()
     # nibble j of a word by multiply (2^(28-4j)) and multiply-high (2^4)
     w = rng.integers(0, 1 << 32, 4096, dtype=np.uint64)
     for j in range(8):
