@@ -695,6 +695,22 @@ def caller_view(kem):
     out = {"drop_in_api_latency_us": {k: {"median": statistics.median(v), "min": min(v)} for k, v in lat.items()},
            "drop_in_api_note": "include/ml_kem.h entry points, one operation per call: layout conversion + H2D + the kernel chain of one item "
                                "+ D2H + synchronise; the reference takes about 20 ms per operation at -O2 (cpu_baseline.O2_1thread_pairs_per_s)"}
+    # is a batch of one launch-bound?  sum of the kernels' own durations (event hooks) against the wall time of the calls
+    one = [np.zeros((1, w), np.uint8) for w in (32, 32, 32)]
+    ek1, dk1 = kem.keygen(PS, one[0], one[1])
+    kem.encaps(PS, ek1, one[2])
+    kem.profile(True)
+    t0 = time.perf_counter()
+    for _ in range(10):
+        c1, K1 = kem.encaps(PS, ek1, one[2])
+        kem.decaps(PS, dk1, c1)
+    wall_us = (time.perf_counter() - t0) / 10 * 1e6
+    kem.profile(False)
+    rep = kem.profile_report()
+    kern_us = sum(v["ms"] for v in rep.values()) / 10 * 1e3
+    out["batch_of_one"] = {"wall_us_per_encaps_plus_decaps": wall_us, "kernel_us": kern_us, "launches": sum(v["launches"] for v in rep.values()) // 10,
+                           "note": "kernel_us = sum of the kernels' own durations (CUDA events around every launch, which add their own overhead to the "
+                                   "wall time here); the rest is launch gaps, the pageable copies and the synchronisation"}
     rng = np.random.default_rng(7)
     nmax = 1 << 14
     d, z, m = (rng.integers(0, 256, (nmax, 32), dtype=np.uint8) for _ in range(3))
