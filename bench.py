@@ -186,7 +186,8 @@ def main():
     ap.add_argument("--e2e-log2-items", type=int, default=None, help="items per GPU for the host-buffer leg (default: same)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
-    ap.add_argument("--no-wc-inputs", action="store_true", help="e2e input buffers in ordinary pinned memory instead of write-combined")
+    ap.add_argument("--wc-inputs", action="store_true",
+                    help="e2e input buffers in write-combined pinned memory where the box grants it (default: ordinary pinned memory)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -314,12 +315,13 @@ def main():
     wc_allocs, wc_bytes = [], [0, 0]  # write-combined / ordinary pinned bytes of the e2e input buffers
 
     def pinned_copy(t):
-        """Host copy of a device tensor in an INPUT buffer of the e2e legs: pinned and, unless --no-wc-inputs, write-combined
-        (mlkem_b200_host_alloc_wc).  The CPU only ever fills these buffers; write-combined pages are not snooped when the GPU
-        reads them, which is worth nothing on one GPU and 7 % (H2D alone) to 44 % (both directions busy) of the box's aggregate
-        copy rate with eight (tools/pcie_bw.py, profiles/pcie_bw_r02_8gpu.json)."""
+        """Host copy of a device tensor in an INPUT buffer of the e2e legs: pinned, and with --wc-inputs write-combined
+        (mlkem_b200_host_alloc_wc) where the box grants it.  The CPU only ever fills these buffers; write-combined pages are not
+        snooped when the GPU reads them, which is worth nothing on one GPU and 7 % (H2D alone) to 44 % (both directions busy) of
+        the box's aggregate copy rate with eight (tools/pcie_bw.py, profiles/pcie_bw_r02_8gpu.json) -- but such mappings are a
+        limited resource (8 ranks x 20 GB were refused), so the default is ordinary pinned memory."""
         nbytes = t.numel() * t.element_size()
-        ptr = None if args.no_wc_inputs else lib.mlkem_b200_host_alloc_wc(nbytes)
+        ptr = lib.mlkem_b200_host_alloc_wc(nbytes) if args.wc_inputs else None
         if ptr:
             wc_allocs.append(ptr)
             wc_bytes[0] += nbytes
@@ -395,7 +397,7 @@ def main():
     e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "items_per_gpu": ne,
            "ms_per_step": 1e3 * e2e_s / steps, "h2d_GBps_per_gpu": h2d * steps / e2e_s / 1e9,
            "input_buffers": {"write_combined_bytes": wc_bytes[0], "pinned_bytes": wc_bytes[1],
-                             "note": "input buffers are write-combined (mlkem_b200_host_alloc_wc) where the box grants it, else ordinary pinned memory"},
+                             "note": "--wc-inputs: write-combined (mlkem_b200_host_alloc_wc) where the box grants it; default ordinary pinned memory"},
            "path": "mlkem_b200_encaps_batch + mlkem_b200_decaps_batch with MLKEM_B200_MEM_HOST (pinned buffers), distinct keys per item; the two "
                    "calls of a step are issued with MLKEM_B200_FLAG_ASYNC and followed by one mlkem_b200_synchronize",
            "blocking_calls": {"value": world * ne * steps / e2e_sync_s, "unit": UNIT, "ms_per_step": 1e3 * e2e_sync_s / steps,

@@ -692,12 +692,19 @@ int mlkem_b200_synchronize(int device, void *stream) {
 }
 void *mlkem_b200_host_alloc(size_t bytes) {
     void *p = nullptr;
-    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) return nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) {
+        cudaGetLastError();  // a failed allocation must not linger as the "last error" of the next kernel launch
+        return nullptr;
+    }
     return p;
 }
 void *mlkem_b200_host_alloc_wc(size_t bytes) {
     void *p = nullptr;
-    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable | cudaHostAllocWriteCombined) != cudaSuccess) return nullptr;
+    // write-combined mappings are a limited resource (8 processes x 20 GB did not fit on the 8-GPU box): callers fall back
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable | cudaHostAllocWriteCombined) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
     return p;
 }
 void mlkem_b200_host_free(void *p) {
