@@ -988,8 +988,14 @@ __global__ void __launch_bounds__(256) k_matrix_seeds(int n, const uint8_t *__re
 // u rows of K-PKE.Encrypt from the table (ml_kem.c:854-896): persistent warps, warp = one (item, row); the K matrix
 // polynomials of the row come from HBM / L2 with coalesced 32-bit loads (a coefficient pair per lane and load), the
 // vector, noise codes and ciphertext row are fetched one row ahead like in the fused kernel.
+#ifndef MLKEM_B200_MATTABLE_PREFETCH
+#define MLKEM_B200_MATTABLE_PREFETCH 1  // 1: operands of the next row in a second register set (118 registers, 16 warps per SM)
+#endif                                  // 0: loaded at the top of the row, latency left to occupancy (MLKEM_B200_MATTABLE_BLOCKS per SM)
+#ifndef MLKEM_B200_MATTABLE_BLOCKS
+#define MLKEM_B200_MATTABLE_BLOCKS 1
+#endif
 template <class P, int MODE>
-__global__ void __launch_bounds__(kMatTableTPB) k_matvec_table(MatvecArgs g, const uint16_t *__restrict__ table) {
+__global__ void __launch_bounds__(kMatTableTPB, MLKEM_B200_MATTABLE_BLOCKS) k_matvec_table(MatvecArgs g, const uint16_t *__restrict__ table) {
     static_assert(MODE != kModeKeyGen, "the table is kept in Encrypt order");
     constexpr int K = P::K, NW = kMatTableTPB / 32;
     __shared__ __align__(16) uint8_t s_warp[NW * kMatvecWarpBytes];
@@ -1001,10 +1007,11 @@ __global__ void __launch_bounds__(kMatTableTPB) k_matvec_table(MatvecArgs g, con
     const int rows = g.n * K, stride = gridDim.x * NW;
     int gg = blockIdx.x * NW + warp;
     MatvecOperands<P> nx;
-    matvec_prefetch<P, MODE>(nx, g, gg < rows ? gg : -1, lane);
+    if (MLKEM_B200_MATTABLE_PREFETCH) matvec_prefetch<P, MODE>(nx, g, gg < rows ? gg : -1, lane);
     constexpr int kCmpWords = MatvecOperands<P>::kCmpWords;
 #pragma unroll 1
     for (; gg < rows; gg += stride) {
+        if (!MLKEM_B200_MATTABLE_PREFETCH) matvec_prefetch<P, MODE>(nx, g, gg, lane);
         const int item = gg / K, row = gg - item * K;
         const uint32_t *arow = reinterpret_cast<const uint32_t *>(table + ((size_t)key_row(g.keys, item) * K + row) * K * 256);
         uint32_t aw[4 * K];
@@ -1021,7 +1028,7 @@ __global__ void __launch_bounds__(kMatTableTPB) k_matvec_table(MatvecArgs g, con
         for (int i = 0; i < kCmpWords; i++) cmpw[i] = nx.cmp[i];
 #pragma unroll
         for (int i = 0; i < 4; i++) ev4[i] = 0;
-        matvec_prefetch<P, MODE>(nx, g, gg + stride < rows ? gg + stride : -1, lane);
+        if (MLKEM_B200_MATTABLE_PREFETCH) matvec_prefetch<P, MODE>(nx, g, gg + stride < rows ? gg + stride : -1, lane);
         uint32_t acc[8];
 #pragma unroll
         for (int r = 0; r < 8; r++) acc[r] = 0;
