@@ -286,6 +286,29 @@ def main():
     clocks = sampler.summary(t_wall0, t_wall1)
     value = world * n * steps / (ms * 1e-3)
 
+    # ---- the two operations on their own (Encaps/s, Decaps/s and pairs/s = 1 / (1/E + 1/D)), device-resident, per GPU
+    def timed_device(fn, reps=3):
+        fn()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        a0.record(stream)
+        for _ in range(reps):
+            fn()
+        a1.record(stream)
+        torch.cuda.synchronize()
+        return a0.elapsed_time(a1) / reps * 1e-3
+
+    def only_encaps():
+        if lib.mlkem_b200_encaps_batch(PS, n, P(ek), P(m), P(c), P(K), C.byref(o_dev)):
+            raise RuntimeError(lib.mlkem_b200_last_error().decode())
+
+    def only_decaps():
+        if lib.mlkem_b200_decaps_batch(PS, n, P(dk), P(c_t), P(Kd), C.byref(o_dev)):
+            raise RuntimeError(lib.mlkem_b200_last_error().decode())
+
+    t_enc, t_dec = timed_device(only_encaps), timed_device(only_decaps)
+    per_op = {"encaps_per_s_per_gpu": n / t_enc, "decaps_per_s_per_gpu": n / t_dec, "pairs_per_s_per_gpu_from_the_two": n / (t_enc + t_dec)}
+
     # ---- per-kernel durations: the same steps again with the chunks serialised on one stream (in the timed region
     # above, kernels of different chunks overlap on two streams, so a kernel's own duration cannot be read there)
     kem.set_streams(1)
@@ -549,7 +572,7 @@ def main():
                                "(BASELINE configs[3]); 1 op = 1 encaps + 1 decaps",
                    "items_per_gpu": n, "distinct_keys": n, "tamper": "i % 10 == 3", "sharding": f"contiguous index shards x{world}, no collective",
                    "cache": "working set 20 GB per GPU >> 126 MB L2, no flush needed"},
-        "e2e": e2e, "e2e_keyed": e2e_keyed, "cross_n_digest": digest,
+        "per_operation": per_op, "e2e": e2e, "e2e_keyed": e2e_keyed, "cross_n_digest": digest,
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
         "kernel_ms_per_step": {k: v["ms"] / steps for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])},
         "serialized_ms_per_step": serial_ms / steps,

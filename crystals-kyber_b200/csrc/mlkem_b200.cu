@@ -596,7 +596,7 @@ int drive(const mlkem_b200_opts *o, size_t n, size_t ws_per_item, std::vector<Bu
         std::lock_guard<std::mutex> lock(g_mutex);
         for (int s = s0; s < s0 + nslots; s++) {
             if (int rc = ensure_buffer(&ctx->ws[s], &ctx->ws_bytes[s], chunk * ws_per_item + kWsSlack, ctx->ev_slot[s])) return rc;
-            if (int rc = ensure_buffer(&ctx->io[s], &ctx->io_bytes[s], chunk * io_per_item + 256 * bufs.size(), ctx->ev_slot[s])) return rc;
+            if (int rc = ensure_buffer(&ctx->io[s], &ctx->io_bytes[s], chunk * io_per_item + 512 * bufs.size(), ctx->ev_slot[s])) return rc;
         }
     }
     for (int s = s0; s < s0 + nslots; s++) CU(cudaStreamWaitEvent(ctx->stream[s], ctx->ev_slot[s], 0));

@@ -73,7 +73,8 @@ typedef struct mlkem_b200_opts {
  *   MLKEM_B200_STREAMS     internal streams the chunks of a device-memory call take turns on [4]; read once at load time,
  *                          mlkem_b200_set_streams() overrides it
  *   MLKEM_B200_HOST_CHUNK  items per staged chunk of a host-memory call [65536]
- *   MLKEM_B200_HOST_SLOTS  staging slots (H2D / kernels / D2H overlap) of a host-memory call [3] */
+ *   MLKEM_B200_HOST_SLOTS  staging slots (H2D / kernels / D2H overlap) of a host-memory call [3]; consecutive host-memory
+ *                          calls alternate between two such groups of slots */
 
 /* FIPS 203 mode.  The reference deviates from FIPS 203: its PRF and J are SHAKE128
  * and its ByteDecode12 never reduces, so the modulus check of KEM_Encaps cannot fail (D4).  With this flag PRF and J are

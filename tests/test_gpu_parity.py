@@ -1084,3 +1084,20 @@ def test_poly_add_sub_vector_multiply(mlkem, oracle, ref_vectors, ref_vectors_r0
             want = oracle.vector_multiply(uu, vv, k)
             assert first_mismatch(mlkem.vector_multiply(uu, vv, k), want) == -1
             assert first_mismatch(mlkem.vector_multiply(torch.from_numpy(uu).cuda(), torch.from_numpy(vv).cuda(), k).cpu().numpy(), want) == -1
+
+
+def test_config2_4096_polynomials_vs_live_reference(mlkem, reference):
+    """4 096 of the 2^20 pairs against tier 1, the compiled reference itself
+    (NTT ml_kem.c:287, MultiplyNTTs :415, InverseNTT :336), when oracle/_ref travelled to the box."""
+    rng = np.random.default_rng(20261018)
+    f = rng.integers(0, 3329, (1 << 20, 256), dtype=np.uint16)[777_000 : 777_000 + 4096]
+    g = rng.integers(0, 3329, (1 << 20, 256), dtype=np.uint16)[777_000 : 777_000 + 4096]
+    fh, gh = mlkem.ntt(f), mlkem.ntt(g)
+    hh = mlkem.multiply_ntts(fh, gh)
+    h = mlkem.intt(hh)
+    for i in range(4096):
+        rf, rg = reference.ntt(f[i]), reference.ntt(g[i])
+        assert (fh[i] == rf).all() and (gh[i] == rg).all(), i
+        rh = reference.multiply_ntts(rf, rg)
+        assert (hh[i] == rh).all(), i
+        assert (h[i] == reference.intt(rh)).all(), i
