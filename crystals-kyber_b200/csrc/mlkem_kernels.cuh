@@ -10,6 +10,8 @@
 //     the warps of the block then multiply them with the vector, accumulate, (inverse-)transform, add the noise,
 //     compress and pack -- the matrix never exists in HBM.  The 2.7 % of rows that own a sponge needing a fourth
 //     block go to a list that k_sample_matvec_list works off with the general sampler.
+//   * keys that are resident on the device (mlkem_b200_keys) are addressed through a per-item index (KeySel); with an
+//     expanded key table the matrix is sampled once per KEY and k_matvec_table reads it back instead.
 //
 // All byte buffers are dense and item-major (item i of an array with per-item size S starts at i*S);
 // every per-item size on this path is a multiple of 16 bytes, so with 16-byte aligned bases every item,
@@ -1068,13 +1070,6 @@ struct EncVArgs {
     const uint8_t *cmp;
     uint32_t *flags;
 };
-
-// Copy `bytes` (multiple of 16) from global to this warp's shared staging area with 128-bit accesses.
-__device__ __forceinline__ void stage_row(uint8_t *dst, const uint8_t *src, int bytes, int lane) {
-    const uint4 *s4 = reinterpret_cast<const uint4 *>(src);
-    uint4 *d4 = reinterpret_cast<uint4 *>(dst);
-    for (int i = lane; i < bytes / 16; i += 32) d4[i] = __ldg(s4 + i);
-}
 
 // Bulk asynchronous global -> shared copies (cp.async.bulk, the 1-D form of the TMA engine, completion signalled on an
 // mbarrier): the persistent warps of k_encrypt_v / k_decrypt fetch the inputs of their NEXT item while they work on the

@@ -254,7 +254,7 @@ def test_kem_with_lowered_group_limit(oracle, ps):
 
 
 def test_kem_chunked_host_pipeline(oracle):
-    """Host-memory path with several chunks alternating between the two pipeline slots."""
+    """Host-memory path with several chunks rotating over the staging slots."""
     import crystals_kyber_b200 as ck
 
     gpu = ck.MLKEM(chunk_items=96)
