@@ -590,6 +590,9 @@ __device__ __forceinline__ void sample_ntt_thread(const Lane rho[4], uint32_t &b
 #endif
 template <bool CHECKED>
 __device__ __forceinline__ void parse_chunk3(const uint32_t w[7], uint32_t &addr, uint32_t end_addr) {
+#ifndef MLKEM_B200_PARSE_ALU_ADDR
+    const uint32_t one = c_pow2[0], two = c_pow2[1];  // values the compiler cannot see through
+#endif
 #pragma unroll
     for (int m = 0; m < 16; m++) {  // candidate m = bits [12 m, 12 m + 12): d1 / d2 of group m / 2 (ml_kem.c:208-209)
         const int bit = 12 * m, wi = bit >> 5, sh = bit & 31;
@@ -600,11 +603,25 @@ __device__ __forceinline__ void parse_chunk3(const uint32_t w[7], uint32_t &addr
         const bool ok = t < (kQ << 20);  // d < q  (:211, :216)
         MLKEM_CHECK_SLOT_STORE(addr, CHECKED ? end_addr : end_addr - 2)
         asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"((uint16_t)(t >> 20)) : "memory");
+#ifndef MLKEM_B200_PARSE_ALU_ADDR
+        // The position advances by a PREDICATED multiply-add (1 * 2 + addr, both factors opaque to the compiler: IMAD, fma pipe, one
+        // issue cycle) instead of a predicated add (VIADD, alu pipe, two); in the checked block the two conditions meet in one
+        // predicate (setp.and), where the compiler's own code spent a SEL on them.  Inline PTX because nvcc turns the C form into
+        // SEL + IMAD.IADD.  1 704 -> 1 594 instructions in the sampling loop, fused kernel 9.015 -> 8.964 ms per 2^20 Encaps
+        // (-DMLKEM_B200_PARSE_ALU_ADDR restores the old form).
+        if (CHECKED)
+            asm volatile("{.reg .pred p; setp.lt.u32 p, %1, %2; setp.lt.and.u32 p, %0, %3, p; @p mad.lo.u32 %0, %4, %5, %0;}"
+                         : "+r"(addr) : "r"(t), "r"(kQ << 20), "r"(end_addr), "r"(one), "r"(two));
+        else
+            asm volatile("{.reg .pred p; setp.lt.u32 p, %1, %2; @p mad.lo.u32 %0, %3, %4, %0;}" : "+r"(addr) : "r"(t), "r"(kQ << 20), "r"(one), "r"(two));
+        (void)ok;
+#else
         if (CHECKED) {
             if (ok && addr < end_addr) addr += 2;  // j < N  (:203, :216)
         } else {
             if (ok) addr += 2;
         }
+#endif
     }
 }
 template <bool CHECKED>  // false: blocks 1 and 2 (cannot fill the slot), true: block 3
@@ -825,6 +842,8 @@ __device__ __forceinline__ void matvec_finish_rows(const MatvecArgs &g, uint32_t
     // iteration that uses them left 32 % of the phase-2 warp time in long-scoreboard stalls: consumers of early loads
     // also wait for later loads that share their scoreboard.)
     constexpr int kCmpWords = MatvecOperands<P>::kCmpWords;
+    // (Measured and rejected, round 2: two operand sets that swap roles every row -- the loop unrolled by two -- instead of
+    // one set copied over per row: 15 instructions less per row, 147 registers, twice the code: 9.63 vs 9.02 ms per 2^20 Encaps.)
 #pragma unroll 1
     for (int grp = warp; grp < 32; grp += K) {
         const int gg = s_gg[grp];
