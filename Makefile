@@ -8,7 +8,7 @@ PKG     := crystals-kyber_b200
 CSRC    := $(PKG)/csrc
 LIB     := $(PKG)/libmlkem_b200.so
 
-all: lib tools oracle
+all: lib tools examples oracle
 
 lib: $(LIB)
 
@@ -35,6 +35,12 @@ build/keccak_bench: $(CSRC)/keccak_bench.cu
 	mkdir -p build
 	$(NVCC) $(ARCH) -O3 -lineinfo -o $@ $<
 
+# plain-C users of the batched ABI (gcc, no CUDA headers): compiled by `make` so that include/mlkem_b200.h stays valid C
+examples: build/keyed_server
+build/keyed_server: examples/keyed_server.c include/mlkem_b200.h $(LIB)
+	mkdir -p build
+	gcc -std=c99 -Wall -Wextra -O1 -Iinclude $< -L$(PKG) -lmlkem_b200 -Wl,-rpath,'$$ORIGIN/../$(PKG)' -o $@
+
 oracle: lib
 	$(MAKE) -C oracle
 	$(MAKE) -C oracle drivers
@@ -43,4 +49,4 @@ clean:
 	rm -f $(LIB) build/microbench build/keccak_bench build/coissue_bench
 	$(MAKE) -C oracle clean
 
-.PHONY: all lib exp tools oracle clean
+.PHONY: all lib exp tools examples oracle clean

@@ -53,6 +53,18 @@ def test_reference_header_symbols_exported(lib):
     assert C.c_int.in_dll(lib, "ml_errno").value == 0
 
 
+def test_batched_header_is_valid_c99():
+    """include/mlkem_b200.h is a C header (cgo / JNI / plain C callers): gcc -std=c99 must accept it, and the plain-C example
+    that uses the keyed entry points must compile against it."""
+    import subprocess
+
+    src = '#include "mlkem_b200.h"\nint main(void) { mlkem_b200_opts o = {0, MLKEM_B200_MEM_HOST, 0, 0, 0, MLKEM_B200_FLAG_ASYNC}; return o.device; }\n'
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), "-x", "c", "-"],
+                   input=src.encode(), check=True)
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "examples", "keyed_server.c")], check=True)
+
+
 def test_sizes_match_reference_formulas(lib):
     for ps, (k, du, dv) in {512: (2, 10, 4), 768: (3, 10, 4), 1024: (4, 11, 5)}.items():
         assert lib.mlkem_b200_ek_bytes(ps) == 384 * k + 32       # ml_kem.c:730

@@ -341,6 +341,12 @@ def test_fips_mode(oracle, ps):
     assert gpu.kem_encaps(ps, ek_bad)[0] == -4
     assert gpu.kem_encaps(ps, ek[:3])[0] == 0
     assert ck.MLKEM().kem_encaps(ps, ek_bad)[0] == 0
+    # the keyed path in FIPS mode (table from seeds, expanded matrices): same outputs as the unkeyed FIPS calls
+    table = gpu.keys_load(ps, seeds=(d, z), expand=True)
+    ck_, Kk = gpu.encaps_keyed(table, None, m)
+    assert (ck_ == c).all() and (Kk == K).all()
+    assert (gpu.decaps_keyed(table, None, bad) == Kd).all()
+    table.free()
     if ps in (768, 1024):
         mlkem_mod = pytest.importorskip("cryptography.hazmat.primitives.asymmetric.mlkem")
         Priv = mlkem_mod.MLKEM768PrivateKey if ps == 768 else mlkem_mod.MLKEM1024PrivateKey
@@ -1101,3 +1107,21 @@ def test_config2_4096_polynomials_vs_live_reference(mlkem, reference):
         rh = reference.multiply_ntts(rf, rg)
         assert (hh[i] == rh).all(), i
         assert (h[i] == reference.intt(rh)).all(), i
+
+
+def test_plain_c_example_prints_the_survey_kat(mlkem):
+    """examples/keyed_server.c: the batched ABI used from C99 (gcc, no CUDA headers) -- KeyGen, a resident expanded key
+    table from the seeds, keyed Encaps / Decaps.  Its output must be the ML-KEM-768 KAT of SURVEY.md 8(c) (the compiled
+    reference's K and K_rej for d = 00..1f, z = 20..3f, m = 40..5f)."""
+    import os
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "build", "keyed_server")
+    if not os.path.exists(exe):
+        subprocess.run(["make", "-C", root, "examples"], check=True, stdout=subprocess.DEVNULL)
+    out = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=120)
+    assert out.returncode == 0, out.stderr
+    lines = dict(l.split(" = ") for l in out.stdout.decode().strip().split("\n"))
+    assert lines["K    "] == "ca49ed38f11d513390bb0db10b9bf900eb6ce82f1ca0c71acca7947ad0dd2c37"
+    assert lines["K_rej"] == "1ff209d0da6ec725d8513af357049d0cb065caa7fd3fd2b038aa4c2487e962b3"
