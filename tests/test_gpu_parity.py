@@ -1125,3 +1125,36 @@ def test_plain_c_example_prints_the_survey_kat(mlkem):
     lines = dict(l.split(" = ") for l in out.stdout.decode().strip().split("\n"))
     assert lines["K    "] == "ca49ed38f11d513390bb0db10b9bf900eb6ce82f1ca0c71acca7947ad0dd2c37"
     assert lines["K_rej"] == "1ff209d0da6ec725d8513af357049d0cb065caa7fd3fd2b038aa4c2487e962b3"
+
+
+def test_copy_probe_and_write_combined_buffers(mlkem):
+    """mlkem_b200_copy_probe (the copy-only denominator of bench.py's e2e) and mlkem_b200_host_alloc_wc: the probe moves the
+    buffers of a host-memory call through the staging pipeline without kernels; a write-combined input buffer behaves like
+    any other input of a real call."""
+    import ctypes as C
+
+    from crystals_kyber_b200.lib import MEM_DEVICE, MEM_HOST, Opts
+
+    lib = mlkem.lib
+    n, item = 100_000, 1088
+    src = lib.mlkem_b200_host_alloc_wc(n * item) or lib.mlkem_b200_host_alloc(n * item)
+    dst = lib.mlkem_b200_host_alloc(n * 32)
+    assert src and dst
+    ip, ib = (C.c_void_p * 1)(src), (C.c_size_t * 1)(item)
+    op, ob = (C.c_void_p * 1)(dst), (C.c_size_t * 1)(32)
+    o = Opts(0, MEM_HOST, None, 0, 0, 0)
+    assert lib.mlkem_b200_copy_probe(n, 1, ip, ib, 1, op, ob, C.byref(o)) == 0
+    assert lib.mlkem_b200_copy_probe(n, 1, ip, ib, 0, None, None, C.byref(o)) == 0
+    od = Opts(0, MEM_DEVICE, None, 0, 0, 0)
+    assert lib.mlkem_b200_copy_probe(n, 1, ip, ib, 1, op, ob, C.byref(od)) == -11  # host memory only
+    # a real call reading its ciphertexts from the (write-combined) buffer
+    rng = np.random.default_rng(4)
+    d, z, m = (rng.integers(0, 256, (64, 32), dtype=np.uint8) for _ in range(3))
+    ek, dk = mlkem.keygen(768, d, z)
+    c, K = mlkem.encaps(768, ek, m)
+    C.memmove(src, c.ctypes.data, c.nbytes)
+    Kd = np.zeros((64, 32), np.uint8)
+    assert lib.mlkem_b200_decaps_batch(768, 64, C.c_void_p(dk.ctypes.data), C.c_void_p(src), C.c_void_p(Kd.ctypes.data), C.byref(o)) == 0
+    assert (Kd == K).all()
+    lib.mlkem_b200_host_free(src)
+    lib.mlkem_b200_host_free(dst)
