@@ -83,6 +83,15 @@ def reference_pairs_per_s(threads: int, pairs_per_thread: int, steps: int, warmu
         if detail:
             t1, _, _ = ref.time_pairs(PS, ek[:4], dk[:4], m[:4], 1)
             out["O2_1thread_pairs_per_s"] = 4 / t1
+            # the three operations on their own through the reference's *_internal functions, and KeyGen on all threads
+            tk, ek4, dk4 = ref.time_keygen(PS, d[:4], z[:4], 1)
+            te, c4, K4 = ref.time_encaps(PS, ek[:4], m[:4], 1)
+            td, Kd4 = ref.time_decaps(PS, dk[:4], c4, 1)
+            assert (ek4 == ek[:4]).all() and (dk4 == dk[:4]).all() and (Kd4 == K4).all(), "reference and oracle disagree"
+            tka, _, _ = ref.time_keygen(PS, d[: 8 * threads], z[: 8 * threads], threads)
+            out["O2_1thread_per_operation"] = {"keygen_per_s": 4 / tk, "encaps_per_s": 4 / te, "decaps_per_s": 4 / td,
+                                               "sample": "4 calls each of KeyGen_internal / Encaps_internal / Decaps_internal (-O2), one thread"}
+            out["keygen_per_s_all_threads"] = 8 * threads / tka
             f = rng.integers(0, 3329, 256, dtype=np.uint16)
             g = rng.integers(0, 3329, 256, dtype=np.uint16)
             tn, ti, tm = ref.time_ring(f, g, 2000)  # ml_kem.c:287, :336, :415 -- 2 000 calls each, one thread
@@ -584,7 +593,8 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         r = reference_pairs_per_s(os.cpu_count() or 1, 32, 1, 1, detail=True)
         line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "build", "makefile_flags_1thread_pairs_per_s",
-                                                  "O2_1thread_pairs_per_s", "ring_1thread") if k in r}
+                                                  "O2_1thread_pairs_per_s", "O2_1thread_per_operation",
+                                                  "keygen_per_s_all_threads", "ring_1thread") if k in r}
     if rank == 0:
         emit(line)
     if dist is not None:

@@ -25,6 +25,7 @@ def main():
     ap.add_argument("--max-log2", type=int, default=24)
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--set", type=int, default=768)
+    ap.add_argument("--no-cpu-reference", action="store_true", help="skip the reference's own CPU figure (last line, rank 0)")
     args = ap.parse_args()
 
     import torch
@@ -88,8 +89,33 @@ def main():
                               "decaps_per_s": B / (best["decaps"] * 1e-3), "ms": best}), flush=True)
         del d, z, m, ek, dk, c, K, Kd
         torch.cuda.empty_cache()
+    if rank == 0 and not args.no_cpu_reference:
+        print(json.dumps(cpu_reference(ps)), flush=True)
     if dist is not None:
         dist.destroy_process_group()
+
+
+def cpu_reference(ps, per_thread=8):
+    """BASELINE configs[4] asks for the host-core CPU reference beside the sweep: full KEM round trips per second of the
+    unmodified reference (oracle/_ref, built by oracle/Makefile) on all host threads, on a bounded sample -- the
+    reference's time per item does not depend on the batch size."""
+    import numpy as np
+
+    from oracle.oracle import REF_SO, Reference, build
+
+    build()
+    if not os.path.exists(REF_SO):
+        return {"cpu_reference": None, "why": "oracle/_ref did not travel"}
+    ref = Reference(REF_SO)
+    threads = os.cpu_count() or 1
+    n = threads * per_thread
+    rng = np.random.default_rng(20261018)
+    d, z, m = (rng.integers(0, 256, (n, 32), dtype=np.uint8) for _ in range(3))
+    tk, ek, dk = ref.time_keygen(ps, d, z, threads)
+    tp, _, _ = ref.time_pairs(ps, ek, dk, m, threads)
+    return {"cpu_reference": f"ML-KEM-{ps} full KEM (KeyGen+Encaps+Decaps), the unmodified reference at gcc -O2", "cores": threads,
+            "sample": f"{n} round trips on {threads} threads", "round_trips_per_s": n / (tk + tp), "keygen_per_s": n / tk,
+            "encaps_plus_decaps_pairs_per_s": n / tp}
 
 
 if __name__ == "__main__":

@@ -712,13 +712,14 @@ void mlkem_b200_host_free(void *p) {
 }
 void mlkem_b200_release(int device) {
     if (device < 0 || device >= kMaxDevices) return;
-    std::lock_guard<std::mutex> lock(g_mutex);
     DeviceCtx &c = g_ctx[device];
+    // lock order everywhere: misc_mutex (public-wrapper batches) -> call_mutex (drive) -> g_mutex (buffer growth)
+    std::lock_guard<std::mutex> misc_lock(c.misc_mutex);
+    std::lock_guard<std::mutex> call_lock(c.call_mutex);
+    std::lock_guard<std::mutex> lock(g_mutex);
     if (!c.ready) return;
     DeviceGuard guard;
     if (guard.enter(device)) return;
-    std::lock_guard<std::mutex> call_lock(c.call_mutex);
-    std::lock_guard<std::mutex> misc_lock(c.misc_mutex);
     cudaDeviceSynchronize();
     // the workspaces hold secret-dependent intermediates (sigma, s^ / e^, m', K' || r') and staged keys: wipe, then free
     auto wipe_free = [](void *&p, size_t &bytes) {
@@ -857,15 +858,29 @@ static int with_entropy(const mlkem_b200_opts *o, size_t bytes, F call) {
     return call(lease.ptr);
 }
 
+// The public-wrapper batches read results (status words) or wipe inputs (seeds) on the host right after their inner calls:
+// they are synchronous whatever the caller's flags say.
+struct SyncOpts {
+    mlkem_b200_opts v;
+    const mlkem_b200_opts *p;
+    explicit SyncOpts(const mlkem_b200_opts *o) : v(o ? *o : mlkem_b200_opts{-1, MLKEM_B200_MEM_HOST, nullptr, 0, 0, 0}), p(o ? &v : nullptr) {
+        v.flags &= ~MLKEM_B200_FLAG_ASYNC;
+    }
+};
+
 extern "C" {
 
-int mlkem_b200_kem_keygen_batch(int set, size_t n, uint8_t *ek, uint8_t *dk, const mlkem_b200_opts *o) {
+int mlkem_b200_kem_keygen_batch(int set, size_t n, uint8_t *ek, uint8_t *dk, const mlkem_b200_opts *opts) {
+    const SyncOpts so(opts);
+    const mlkem_b200_opts *o = so.p;
     if (!mlkem_b200_ek_bytes(set)) return MLKEM_B200_ERR_PARAM;
     if (n == 0) return MLKEM_B200_OK;
     return with_entropy(o, 64 * n, [&](uint8_t *seeds) { return mlkem_b200_keygen_batch(set, n, seeds, seeds + 32 * n, ek, dk, o); });
 }
 
-int mlkem_b200_kem_encaps_batch(int set, size_t n, const uint8_t *ek, size_t ek_len, uint8_t *c, uint8_t *K, const mlkem_b200_opts *o) {
+int mlkem_b200_kem_encaps_batch(int set, size_t n, const uint8_t *ek, size_t ek_len, uint8_t *c, uint8_t *K, const mlkem_b200_opts *opts) {
+    const SyncOpts so(opts);
+    const mlkem_b200_opts *o = so.p;
     unsigned want = mlkem_b200_ek_bytes(set);
     if (!want) return MLKEM_B200_ERR_PARAM;
     if (ek_len != want) return MLKEM_B200_ERR_LENGTH;  // type check, ml_kem.c:1267
@@ -911,14 +926,21 @@ int mlkem_b200_kem_encaps_batch(int set, size_t n, const uint8_t *ek, size_t ek_
 }
 
 int mlkem_b200_kem_decaps_batch(int set, size_t n, const uint8_t *dk, size_t dk_len, const uint8_t *c, size_t c_len, uint8_t *K,
-                                int32_t *status, const mlkem_b200_opts *o) {
+                                int32_t *status, const mlkem_b200_opts *opts) {
+    const SyncOpts so(opts);
+    const mlkem_b200_opts *o = so.p;
     if (!mlkem_b200_ek_bytes(set)) return MLKEM_B200_ERR_PARAM;
     if (c_len != mlkem_b200_ct_bytes(set)) return MLKEM_B200_ERR_LENGTH;   // ml_kem.c:1321
     if (dk_len != mlkem_b200_dk_bytes(set)) return MLKEM_B200_ERR_LENGTH;  // ml_kem.c:1329
     if (!status) return MLKEM_B200_ERR_ARG;
     if (int rc = mlkem_b200_check_dk_batch(set, n, dk, status, o)) return rc;  // hash check, ml_kem.c:1336-1350
     if (int rc = mlkem_b200_decaps_batch(set, n, dk, c, K, o)) return rc;
+    if (n == 0) return MLKEM_B200_OK;
     if (o && o->mem == MLKEM_B200_MEM_DEVICE) {
+        int dev;
+        DeviceCtx *ctx;
+        DeviceGuard guard;  // the stream belongs to opts->device, which need not be the calling thread's current device
+        if (int rc = acquire(o, &dev, &ctx, guard)) return rc;
         cudaStream_t st = static_cast<cudaStream_t>(o->stream);
         LAUNCH(k_mask_keys, cdiv(n, kHashTPB), kHashTPB, 0, st, (int)n, (const int *)status, K);
     } else {
@@ -1111,7 +1133,9 @@ int mlkem_b200_hash_batch(int which, size_t n, size_t len, const uint8_t *in, ui
 // ceil(nbits/8) bytes per message, item-major).  Host memory only: this is the reference's general SHA-3
 // front-end, not part of the KEM hot path.
 int mlkem_b200_sha3_bits_batch(size_t n, const uint8_t *msgs, size_t nbits, const uint8_t sfx[4], unsigned c, size_t d, uint8_t *out,
-                               const mlkem_b200_opts *o) {
+                               const mlkem_b200_opts *opts) {
+    const SyncOpts so(opts);  // pads into, and reads the digests from, temporary host vectors
+    const mlkem_b200_opts *o = so.p;
     if (c == 0 || c >= 1600 || (1600 - c) % 64 != 0 || d == 0 || !sfx || !out || (nbits && !msgs)) return MLKEM_B200_ERR_ARG;
     if (o && o->mem == MLKEM_B200_MEM_DEVICE) return MLKEM_B200_ERR_ARG;
     if (n == 0) return MLKEM_B200_OK;
@@ -1339,12 +1363,20 @@ int mlkem_b200_keys_load(int set, size_t n_keys, const uint8_t *dk, int32_t *sta
     // the hash check of KEM_Decaps (ml_kem.c:1336-1350), once per key instead of once per ciphertext; status is HOST memory
     mlkem_b200_opts od{(*out)->device, MLKEM_B200_MEM_DEVICE, nullptr, 0, 0, 0};
     int32_t *d_status = nullptr;
-    DeviceGuard guard;
-    if (int r = guard.enter((*out)->device)) return r;
-    CU(cudaMalloc(&d_status, 4 * n_keys));
-    rc = mlkem_b200_check_dk_batch(set, n_keys, (*out)->dk, d_status, &od);
-    if (!rc && cudaMemcpy(status, d_status, 4 * n_keys, cudaMemcpyDeviceToHost) != cudaSuccess) rc = MLKEM_B200_ERR_CUDA;
-    cudaFree(d_status);
+    auto check = [&]() -> int {
+        DeviceGuard guard;
+        if (int r = guard.enter((*out)->device)) return r;
+        CU(cudaMalloc(&d_status, 4 * n_keys));
+        int r = mlkem_b200_check_dk_batch(set, n_keys, (*out)->dk, d_status, &od);
+        if (!r && cudaMemcpy(status, d_status, 4 * n_keys, cudaMemcpyDeviceToHost) != cudaSuccess) r = MLKEM_B200_ERR_CUDA;
+        cudaFree(d_status);
+        return r;
+    };
+    rc = check();
+    if (rc) {  // an error leaves no table behind (a FAILED hash check is not an error: status says which keys)
+        keys_destroy(*out);
+        *out = nullptr;
+    }
     return rc;
 }
 

@@ -85,7 +85,9 @@ typedef struct mlkem_b200_opts {
 /* Host-memory calls only: return as soon as the copies and kernels are enqueued on the library's streams instead of
  * waiting for the results.  The buffers must be pinned (mlkem_b200_host_alloc) and stay untouched until
  * mlkem_b200_synchronize(device, NULL) returns.  Consecutive asynchronous calls pipeline through the staging slots:
- * the device-to-host tail of one overlaps the host-to-device head of the next. */
+ * the device-to-host tail of one overlaps the host-to-device head of the next.  Ignored by the calls that use their results
+ * on the host before they return: the public-wrapper batches (mlkem_b200_kem_*_batch), mlkem_b200_sha3_bits_batch and the
+ * set-up calls mlkem_b200_keys_*. */
 #define MLKEM_B200_FLAG_ASYNC 2
 /* mlkem_b200_keys_load / _load_ek / _from_seeds only: also keep the expanded matrix A^ of every key in the table
  * (At[row][col] = SampleNTT(rho || row || col), ml_kem.c:817-823; k*k*512 bytes per key, 4.6 KB at ML-KEM-768).  The matrix
@@ -101,7 +103,7 @@ int mlkem_b200_synchronize(int device, void *stream);
 void *mlkem_b200_host_alloc(size_t bytes);        /* pinned host memory (cudaHostAlloc) */
 void *mlkem_b200_host_alloc_wc(size_t bytes);     /* the same, write-combined: for INPUT buffers the CPU only ever fills sequentially */
 void mlkem_b200_host_free(void *p);
-void mlkem_b200_release(int device);              /* drop the cached workspace of a device */
+void mlkem_b200_release(int device);              /* wait for the device, wipe and drop its cached workspaces (key tables stay) */
 
 /* Sizes of a parameter set (512 / 768 / 1024), 0 for an unknown set.  ml_kem.c:730-731,1050,1105 */
 unsigned mlkem_b200_ek_bytes(int param_set);
@@ -135,7 +137,7 @@ typedef struct mlkem_b200_keys mlkem_b200_keys;
 
 /* n_keys decapsulation keys (n_keys x (768k+96) bytes, host or device memory per opts->mem).  status (HOST memory, may
  * be NULL): the dk hash check of KEM_Decaps (ml_kem.c:1336-1350) once per key, status[i] = 0 or -5; failing keys are
- * loaded all the same (Decaps_internal does not validate either). */
+ * loaded all the same (Decaps_internal does not validate either).  On an error return *out is NULL: no table is left behind. */
 int mlkem_b200_keys_load(int param_set, size_t n_keys, const uint8_t *dk, int32_t *status, const mlkem_b200_opts *opts,
                          mlkem_b200_keys **out);
 /* n_keys encapsulation keys only (n_keys x (384k+32) bytes): a table for mlkem_b200_encaps_keyed_batch. */

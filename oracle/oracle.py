@@ -535,6 +535,27 @@ class Reference(_Lib):
                                                dk.ctypes.data_as(C.POINTER(C.c_uint8)))
         return float(t), ek, dk
 
+    def time_encaps(self, ps, ek, m, threads):
+        sz = sizes(ps)
+        ek, pe = _u8(ek)
+        m, pm = _u8(m)
+        n = m.size // 32
+        c = np.empty((n, sz["c"]), np.uint8)
+        K = np.empty((n, 32), np.uint8)
+        t = self.fn("time_encaps", C.c_double)(C.c_int(ps), C.c_size_t(n), C.c_int(threads), pe, pm,
+                                               c.ctypes.data_as(C.POINTER(C.c_uint8)),
+                                               K.ctypes.data_as(C.POINTER(C.c_uint8)))
+        return float(t), c, K
+
+    def time_decaps(self, ps, dk, c, threads):
+        dk, pd = _u8(dk)
+        c, pc = _u8(c)
+        n = c.size // sizes(ps)["c"]
+        K = np.empty((n, 32), np.uint8)
+        t = self.fn("time_decaps", C.c_double)(C.c_int(ps), C.c_size_t(n), C.c_int(threads), pd, pc,
+                                               K.ctypes.data_as(C.POINTER(C.c_uint8)))
+        return float(t), K
+
     def time_ring(self, f, g, reps):
         _, pf = _u16(f)
         _, pg = _u16(g)

@@ -1158,3 +1158,78 @@ def test_copy_probe_and_write_combined_buffers(mlkem):
     assert (Kd == K).all()
     lib.mlkem_b200_host_free(src)
     lib.mlkem_b200_host_free(dst)
+
+
+def test_public_wrappers_are_synchronous_whatever_the_flags(oracle):
+    """The batched public wrappers read status words and wipe their seed buffers on the host right after their inner calls, and
+    the SHA-3 front-end pads into temporary host vectors: MLKEM_B200_FLAG_ASYNC in the caller's options must not reach those
+    inner calls (the results below would be read, or the seeds wiped, before the copies ran)."""
+    import crystals_kyber_b200 as ck
+
+    gpu = ck.MLKEM()
+    gpu.flags |= 2  # MLKEM_B200_FLAG_ASYNC
+    n = 70_000  # two staged chunks per inner call
+    ek, dk = gpu.kem_keygen(768, n)
+    assert len({bytes(r) for r in ek[::997, -32:]}) == len(ek[::997])
+    assert [oracle.check_decaps_input(768, dk[i].tobytes(), 1088) for i in (0, n // 2, n - 1)] == [0, 0, 0]
+    rc, c, K = gpu.kem_encaps(768, ek)
+    assert rc == 0
+    bad_dk = dk.copy()
+    bad_dk[n - 1, 1152 + 5] ^= 1
+    rc, Kd, status = gpu.kem_decaps(768, bad_dk, c)
+    assert rc == 0 and status[n - 1] == -5 and (status[: n - 1] == 0).all()
+    assert (Kd[n - 1] == 0).all() and (Kd[: n - 1] == K[: n - 1]).all()
+    sl = slice(n - 300, n - 1)
+    assert (oracle.decaps(768, dk[sl], c[sl]) == K[sl]).all()
+    bits = np.unpackbits(np.frombuffer(b"abc", np.uint8), bitorder="little")
+    got = gpu.sha3_bits([bits], [0, 1, 0, 0], 512, 256)
+    assert np.packbits(got[0], bitorder="little").tobytes() == hashlib.sha3_256(b"abc").digest()
+
+
+def test_public_wrapper_decaps_on_device_memory(mlkem, oracle):
+    """mlkem_b200_kem_decaps_batch with device pointers: the hash check, Decaps_internal and the masking of failed items all run on
+    the caller's stream of the device the options name; an empty batch is a no-op."""
+    import ctypes as C
+
+    import torch
+
+    from crystals_kyber_b200.lib import MEM_DEVICE, Opts
+
+    rng = np.random.default_rng(11)
+    n = 513
+    d, z, m = (rng.integers(0, 256, (n, 32), dtype=np.uint8) for _ in range(3))
+    ek, dk = oracle.keygen(768, d, z)
+    c, K = oracle.encaps(768, ek, m)
+    bad_dk = dk.copy()
+    bad_dk[100, 2400 - 64] ^= 0x80  # the stored hash of item 100
+    t_dk, t_c = torch.from_numpy(bad_dk).cuda(), torch.from_numpy(c).cuda()
+    t_K = torch.full((n, 32), 0xAA, dtype=torch.uint8, device="cuda")
+    t_st = torch.full((n,), 7, dtype=torch.int32, device="cuda")
+    s = torch.cuda.Stream()
+    o = Opts(0, MEM_DEVICE, s.cuda_stream, 0, 0, 0)
+    P = lambda t: C.c_void_p(t.data_ptr())
+    lib = mlkem.lib
+    s.wait_stream(torch.cuda.current_stream())
+    assert lib.mlkem_b200_kem_decaps_batch(768, n, P(t_dk), 2400, P(t_c), 1088, P(t_K), P(t_st), C.byref(o)) == 0
+    assert lib.mlkem_b200_kem_decaps_batch(768, 0, P(t_dk), 2400, P(t_c), 1088, P(t_K), P(t_st), C.byref(o)) == 0
+    s.synchronize()
+    st, Kd = t_st.cpu().numpy(), t_K.cpu().numpy()
+    assert st[100] == -5 and (np.delete(st, 100) == 0).all()
+    assert (Kd[100] == 0).all() and (np.delete(Kd, 100, 0) == np.delete(K, 100, 0)).all()
+
+
+def test_keys_load_reports_the_hash_check_per_key(mlkem, oracle):
+    """mlkem_b200_keys_load(status): a key whose stored hash is wrong is reported (-5) and loaded all the same -- Decaps_internal
+    does not validate either (ml_kem.c:1136) -- and the keyed call on it equals the unkeyed call."""
+    rng = np.random.default_rng(12)
+    nk, n = 5, 64
+    d, z, m = (rng.integers(0, 256, (n, 32), dtype=np.uint8) for _ in range(3))
+    ek, dk = oracle.keygen(768, d[:nk], z[:nk])
+    dk = dk.copy()
+    dk[3, 2400 - 64 + 7] ^= 2
+    table, status = mlkem.keys_load(768, dk=dk, return_status=True)
+    assert list(status) == [0, 0, 0, -5, 0]
+    idx = (np.arange(n) % nk).astype(np.uint32)
+    c, K = oracle.encaps(768, ek[idx], m)
+    assert (mlkem.decaps_keyed(table, idx, c) == oracle.decaps(768, dk[idx], c)).all()
+    table.free()
