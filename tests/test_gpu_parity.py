@@ -1233,3 +1233,18 @@ def test_keys_load_reports_the_hash_check_per_key(mlkem, oracle):
     c, K = oracle.encaps(768, ek[idx], m)
     assert (mlkem.decaps_keyed(table, idx, c) == oracle.decaps(768, dk[idx], c)).all()
     table.free()
+
+
+def test_unmodified_sha_testing_driver_linked_against_the_library(mlkem, sha_examples, tmp_path):
+    """The reference's twelfth driver, Test_Archive/SHA/SHA_Testing.c (makefile target test05), compiled UNMODIFIED against
+    include/sha3.h and linked with libmlkem_b200.so instead of sha3.o, under the reference's own test flow (sha_testing.sh,
+    restated in tests/sha_flow.py and pinned on the reference's test05 by tests/test_oracle.py): all 16 NIST example files,
+    byte-aligned or not, hash to the expected values -- every sponge on the GPU (sha3_b -> mlkem_b200_sha3_bits_batch)."""
+    import os
+
+    import sha_flow
+
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "drivers", "SHA_Testing")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/drivers/SHA_Testing not built (needs /root/reference at build time)")
+    assert len(sha_flow.run(exe, sha_examples["examples"], str(tmp_path))) == 16
