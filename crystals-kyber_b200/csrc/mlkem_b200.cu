@@ -39,6 +39,12 @@ int initial_streams() {
     return v < 1 ? kDevSlots : (v > kDevSlots ? kDevSlots : v);
 }
 std::atomic<int> g_streams{initial_streams()};
+// Batches of at most this many items run their long hash chains (H(ek), J(z || c)) with one sponge per WARP instead of one per
+// thread: latency instead of throughput.  MLKEM_B200_WARP_HASH_MAX = 0 switches the warp form off.
+int warp_hash_max() {
+    static const int v = env_int("MLKEM_B200_WARP_HASH_MAX", kWarpHashMaxItems);
+    return v;
+}
 
 #define CU(call)                                                                                              \
     do {                                                                                                      \
@@ -88,6 +94,7 @@ inline void prof_end(cudaStream_t st, ProfEntry &pe, bool on) {
     } while (0)
 
 inline unsigned cdiv(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
+inline unsigned warp_hash_grid(int n) { return cdiv((size_t)n, kWarpHashTPB / 32); }
 // grid of the persistent warp-per-item kernels: enough blocks to fill the machine several times over, then grid-stride
 inline unsigned warp_grid(size_t items, int warps_per_block) {
     size_t blocks = (items + warps_per_block - 1) / warps_per_block;
@@ -420,14 +427,16 @@ int enqueue_keygen(cudaStream_t st, Arena &ws, int n, const uint8_t *d, const ui
     a.out2 = full ? dk + 384 * K : nullptr;
     a.out2_stride = dk_stride;
     if (int rc = launch_matvec<P, kModeKeyGen>(st, ws, a)) return rc;
-    if (full) LAUNCH((k_keygen_H<P>), cdiv(n, kHashTPB), kHashTPB, 0, st, n, ek, z, dk);
+    if (full && n <= warp_hash_max()) LAUNCH((k_keygen_H_warp<P>), warp_hash_grid(n), kWarpHashTPB, 0, st, n, ek, z, dk);
+    else if (full) LAUNCH((k_keygen_H<P>), cdiv(n, kHashTPB), kHashTPB, 0, st, n, ek, z, dk);
     return 0;
 }
 
 template <class P>
 int enqueue_encaps(cudaStream_t st, Arena &ws, int n, const uint8_t *ek, const uint8_t *m, uint8_t *c, uint8_t *Kout, int group_limit, bool fips) {
     uint8_t *r = ws.take<uint8_t>((size_t)n * 32);
-    LAUNCH((k_encaps_HG<P>), cdiv(n, kHashTPB), kHashTPB, 0, st, n, ek, m, Kout, r);
+    if (n <= warp_hash_max()) LAUNCH((k_encaps_HG_warp<P>), warp_hash_grid(n), kWarpHashTPB, 0, st, n, ek, m, Kout, r);
+    else LAUNCH((k_encaps_HG<P>), cdiv(n, kHashTPB), kHashTPB, 0, st, n, ek, m, Kout, r);
     return enqueue_encrypt<P>(st, ws, n, ek, P::EK, KeySel{}, m, r, 32, c, nullptr, nullptr, group_limit, fips);
 }
 
@@ -452,6 +461,11 @@ int enqueue_decaps(cudaStream_t st, Arena &ws, int n, const uint8_t *dk, KeySel 
     LAUNCH((k_decaps_G<P>), cdiv(n, kHashTPB), kHashTPB, 0, st, n, mp, dk, keys, Kr);
     // c' = K-PKE.Encrypt(ek_pke, m', r') compared on the fly (ml_kem.c:1206-1215)
     if (int rc = enqueue_encrypt<P>(st, ws, n, dk + 384 * K, P::DK, keys, mp, Kr + 32, 64, nullptr, c, flags, group_limit, fips, matrix)) return rc;
+    if (n <= warp_hash_max()) {
+        if (!fips) LAUNCH((k_decaps_J_select_warp<P>), warp_hash_grid(n), kWarpHashTPB, 0, st, n, dk, keys, c, Kr, flags, Kout);
+        else LAUNCH((k_decaps_J_select_warp<P, kRateSha3_256>), warp_hash_grid(n), kWarpHashTPB, 0, st, n, dk, keys, c, Kr, flags, Kout);
+        return 0;
+    }
     if (!fips) LAUNCH((k_decaps_J_select<P>), cdiv(n, kHashTPB), kHashTPB, 0, st, n, dk, keys, c, Kr, flags, Kout);
     else LAUNCH((k_decaps_J_select<P, kRateSha3_256>), cdiv(n, kHashTPB), kHashTPB, 0, st, n, dk, keys, c, Kr, flags, Kout);
     return 0;
@@ -792,7 +806,8 @@ int mlkem_b200_decaps_batch(int set, size_t n, const uint8_t *dk, const uint8_t 
 
 int mlkem_b200_check_dk_batch(int set, size_t n, const uint8_t *dk, int32_t *status, const mlkem_b200_opts *o) {
     DISPATCH_SET(set, return drive(o, n, 0, {{dk, nullptr, P::DK}, {nullptr, status, 4}}, [=](cudaStream_t st, Arena &, int cn, void **p, size_t) {
-                     LAUNCH((k_check_dk_hash<P>), cdiv(cn, kHashTPB), kHashTPB, 0, st, cn, (const uint8_t *)p[0], (int *)p[1]);
+                     if (cn <= warp_hash_max()) LAUNCH((k_check_dk_hash_warp<P>), warp_hash_grid(cn), kWarpHashTPB, 0, st, cn, (const uint8_t *)p[0], (int *)p[1]);
+                     else LAUNCH((k_check_dk_hash<P>), cdiv(cn, kHashTPB), kHashTPB, 0, st, cn, (const uint8_t *)p[0], (int *)p[1]);
                      return 0;
                  }));
     return MLKEM_B200_ERR_PARAM;

@@ -268,6 +268,98 @@ __device__ __forceinline__ Lane load_lane(const uint8_t *p) {  // p must be 8-by
 __device__ __forceinline__ void store_lane(uint8_t *p, Lane v) { *reinterpret_cast<uint2 *>(p) = make_uint2(v.lo, v.hi); }
 
 // ------------------------------------------------------------------------------------------------
+// 2b. Keccak-f[1600], one sponge per WARP: the latency form, for small batches
+// ------------------------------------------------------------------------------------------------
+// One sponge per thread is the throughput form: 4 320 dependent-issue instructions per permutation, 4.4 us on a warp that has a
+// scheduler to itself.  A batch of one (what a caller of the reference's KEM_Encaps / KEM_Decaps gets) spends most of its time
+// in such chains -- H(ek) alone is 9 permutations one after the other -- with 31 lanes of the warp idle.  Here lane l < 25
+// holds state lane A[x][y], l = x + 5 y, as two registers, and the round's neighbours come by shuffle: theta's column
+// parities from the four other lanes of the column (then C[x-1] and C[x+1] from row 0), rho as a funnel shift by the lane's
+// own offset, pi as one permuting shuffle, chi from the two next lanes of the row; 18 SHFL + ~16 alu instructions per round
+// instead of 180, a dependent chain of four shuffle latencies.  Lanes 25..31 carry zeros and shuffle from themselves.
+// (tests/test_abi_cpu.py::test_warp_keccak_model pins this index arithmetic against hashlib with a numpy model of the 32 lanes.)
+struct WarpSponge {
+    int s5, s10, s15, s20;  // the other four lanes of this lane's column
+    int xm, xp;             // row-0 lanes holding C[x-1] and C[x+1]
+    int pi;                 // source of this lane after rho: B[y][2x+3y] = A[x][y] read backwards
+    int c1, c2;             // the next two lanes of this lane's row
+    uint32_t shift;         // rho offset mod 32
+    bool swap, first;       // rho offset >= 32; lane 0 (iota)
+};
+__device__ __forceinline__ WarpSponge warp_sponge_init(int lane) {
+    // rho offsets by lane index x + 5 y (sha3.c:53-87 computes them from the (t+1)(t+2)/2 walk): the same constants as the
+    // rotl64<> amounts of keccak_f1600 above, packed four per word
+    constexpr uint32_t kRho[7] = {0u | 1u << 8 | 62u << 16 | 28u << 24,  27u | 36u << 8 | 44u << 16 | 6u << 24,  55u | 20u << 8 | 3u << 16 | 10u << 24,
+                                  43u | 25u << 8 | 39u << 16 | 41u << 24, 45u | 15u << 8 | 21u << 16 | 8u << 24, 18u | 2u << 8 | 61u << 16 | 56u << 24,
+                                  14u};
+    WarpSponge w;
+    const bool act = lane < 25;
+    const int x = lane % 5, y = lane / 5;
+    w.s5 = act ? (lane + 5) % 25 : lane;
+    w.s10 = act ? (lane + 10) % 25 : lane;
+    w.s15 = act ? (lane + 15) % 25 : lane;
+    w.s20 = act ? (lane + 20) % 25 : lane;
+    w.xm = act ? (x + 4) % 5 : lane;
+    w.xp = act ? (x + 1) % 5 : lane;
+    w.pi = act ? (x + 3 * y) % 5 + 5 * x : lane;
+    w.c1 = act ? 5 * y + (x + 1) % 5 : lane;
+    w.c2 = act ? 5 * y + (x + 2) % 5 : lane;
+    uint32_t word = 0;
+#pragma unroll
+    for (int k = 0; k < 7; k++) word = (lane >> 2) == k ? kRho[k] : word;
+    const uint32_t rot = act ? (word >> (8 * (lane & 3))) & 63u : 0u;
+    w.shift = rot & 31u;
+    w.swap = (rot & 32u) != 0;
+    w.first = lane == 0;
+    return w;
+}
+__device__ __forceinline__ Lane shfl_lane(Lane v, int src) {
+    return Lane{__shfl_sync(kFullMask, v.lo, src), __shfl_sync(kFullMask, v.hi, src)};
+}
+// sha3.c:207 Keccak_f on the state spread over the warp; every lane of the warp must call it.
+__device__ __forceinline__ void keccak_f1600_warp(Lane &a, const WarpSponge &w) {
+#pragma unroll 2
+    for (int rnd = 0; rnd < 24; rnd++) {
+        const Lane c = xor5(a, shfl_lane(a, w.s5), shfl_lane(a, w.s10), shfl_lane(a, w.s15), shfl_lane(a, w.s20));  // theta, sha3.c:15
+        a = xor3(a, shfl_lane(c, w.xm), rotl64<1>(shfl_lane(c, w.xp)));
+        const uint32_t lo = w.swap ? a.hi : a.lo, hi = w.swap ? a.lo : a.hi;                                       // rho, sha3.c:53
+        a.hi = __funnelshift_l(lo, hi, w.shift);
+        a.lo = __funnelshift_l(hi, lo, w.shift);
+        const Lane b = shfl_lane(a, w.pi);                                                                          // pi, sha3.c:88
+        a = chi3(b, shfl_lane(b, w.c1), shfl_lane(b, w.c2));                                                        // chi, sha3.c:116
+        const uint2 rc = c_keccak_rc[rnd];                                                                          // iota, sha3.c:182
+        a.lo ^= w.first ? rc.x : 0u;
+        a.hi ^= w.first ? rc.y : 0u;
+    }
+}
+// The warp form of sponge_absorb_words: `word(i)` is evaluated by lane (i mod RATE) only.  Returns this lane's state lane
+// after the last absorbing permutation: lanes 0 .. RATE-1 hold the first output block.
+template <int RATE, typename F>
+__device__ __forceinline__ Lane warp_sponge_absorb_words(int lane, const WarpSponge &w, int nwords, uint32_t sfx, F word) {
+    Lane a{0u, 0u};
+    int base = 0;
+    for (; base + RATE <= nwords; base += RATE) {
+        if (lane < RATE) {
+            const Lane v = word(base + lane);
+            a.lo ^= v.lo;
+            a.hi ^= v.hi;
+        }
+        keccak_f1600_warp(a, w);
+    }
+    const int rem = nwords - base;  // 0 .. RATE-1 words in the final block, then the suffix and the pad (sha3.c:226)
+    if (lane < rem) {
+        const Lane v = word(base + lane);
+        a.lo ^= v.lo;
+        a.hi ^= v.hi;
+    } else if (lane == rem) {
+        a.lo ^= sfx;
+    }
+    if (lane == RATE - 1) a.hi ^= 0x80000000u;
+    keccak_f1600_warp(a, w);
+    return a;
+}
+
+// ------------------------------------------------------------------------------------------------
 // 3. Polynomials, one per warp
 // ------------------------------------------------------------------------------------------------
 // Register layouts for the 256 coefficients of one polynomial held by a warp, 8 per lane

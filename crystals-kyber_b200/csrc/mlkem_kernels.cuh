@@ -276,6 +276,89 @@ __global__ void __launch_bounds__(kHashTPB) k_decaps_J_select(int n, const uint8
     }
 }
 
+// -------------------------------------------------------------------------------------------------
+// The same hash kernels with one item per WARP (keccak_f1600_warp): small batches, where the chains of dependent
+// permutations -- 9 for H(ek), 7 for J(z || c) at ML-KEM-768 -- are latency, not throughput.  The host picks these when the
+// batch has at most kWarpHashMaxItems items (MLKEM_B200_WARP_HASH_MAX); results are identical.
+// -------------------------------------------------------------------------------------------------
+constexpr int kWarpHashTPB = 128;        // 4 items per block
+constexpr int kWarpHashMaxItems = 1024;  // one warp per item costs ~8 x the issue slots of one thread per item: past ~2 000 items the
+                                         // thread form is faster again
+
+// SHA3-256 over P::EK bytes at `ek`: lanes 0..3 of the result hold the digest words.
+template <class P>
+__device__ __forceinline__ Lane warp_hash_H_ek(const uint8_t *ek, int lane, const WarpSponge &w) {
+    return warp_sponge_absorb_words<kRateSha3_256>(lane, w, P::EK / 8, kSfxHash, [&](int i) { return load_lane(ek + 8 * i); });
+}
+// SHA3-512 over x || y, x = 32 bytes in memory, y = the words held by lanes 0..3 of `y03`: lanes 0..7 hold the digest words.
+__device__ __forceinline__ Lane warp_hash_G_64(const uint8_t *x, Lane y03, int lane, const WarpSponge &w) {
+    const Lane y = shfl_lane(y03, (lane - 4) & 31);  // lanes 4..7 take y[0..3]
+    Lane a{0u, 0u};
+    if (lane < 4) a = load_lane(x + 8 * lane);
+    else if (lane < 8) a = y;
+    else if (lane == 8) a = Lane{kSfxHash, 0x80000000u};  // 64-byte message: suffix and pad share lane 8 = RATE - 1
+    keccak_f1600_warp(a, w);
+    return a;
+}
+
+template <class P>
+__global__ void __launch_bounds__(kWarpHashTPB) k_keygen_H_warp(int n, const uint8_t *__restrict__ ek, const uint8_t *__restrict__ z,
+                                                                uint8_t *__restrict__ dk) {
+    const int lane = threadIdx.x & 31, i = blockIdx.x * (kWarpHashTPB / 32) + (threadIdx.x >> 5);
+    if (i >= n) return;  // warp-uniform
+    const WarpSponge w = warp_sponge_init(lane);
+    const Lane h = warp_hash_H_ek<P>(ek + (size_t)P::EK * i, lane, w);
+    uint8_t *tail = dk + (size_t)P::DK * i + 768 * P::K + 32;  // dk tail = H(ek) || z, ml_kem.c:1064-1077
+    if (lane < 4) store_lane(tail + 8 * lane, h);
+    else if (lane < 8) store_lane(tail + 8 * lane, load_lane(z + 32 * (size_t)i + 8 * (lane - 4)));
+}
+
+template <class P>
+__global__ void __launch_bounds__(kWarpHashTPB) k_encaps_HG_warp(int n, const uint8_t *__restrict__ ek, const uint8_t *__restrict__ m,
+                                                                 uint8_t *__restrict__ Kout, uint8_t *__restrict__ r) {
+    const int lane = threadIdx.x & 31, i = blockIdx.x * (kWarpHashTPB / 32) + (threadIdx.x >> 5);
+    if (i >= n) return;
+    const WarpSponge w = warp_sponge_init(lane);
+    const Lane h = warp_hash_H_ek<P>(ek + (size_t)P::EK * i, lane, w);   // ml_kem.c:1108
+    const Lane a = warp_hash_G_64(m + 32 * (size_t)i, h, lane, w);       // (K, r) = G(m || h), ml_kem.c:1116-1124
+    if (lane < 4) store_lane(Kout + 32 * (size_t)i + 8 * lane, a);
+    else if (lane < 8) store_lane(r + 32 * (size_t)i + 8 * (lane - 4), a);
+}
+
+template <class P>
+__global__ void __launch_bounds__(kWarpHashTPB) k_check_dk_hash_warp(int n, const uint8_t *__restrict__ dk, int *__restrict__ status) {
+    const int lane = threadIdx.x & 31, i = blockIdx.x * (kWarpHashTPB / 32) + (threadIdx.x >> 5);
+    if (i >= n) return;
+    const WarpSponge w = warp_sponge_init(lane);
+    const uint8_t *base = dk + (size_t)P::DK * i;
+    const Lane h = warp_hash_H_ek<P>(base + 384 * P::K, lane, w);
+    bool diff = false;
+    if (lane < 4) {
+        const Lane s = load_lane(base + 768 * P::K + 32 + 8 * lane);
+        diff = ((s.lo ^ h.lo) | (s.hi ^ h.hi)) != 0;
+    }
+    const bool any = __any_sync(kFullMask, diff);
+    if (lane == 0) status[i] = any ? -5 : 0;
+}
+
+template <class P, int RATE = kRateShake128>
+__global__ void __launch_bounds__(kWarpHashTPB) k_decaps_J_select_warp(int n, const uint8_t *__restrict__ dk, KeySel keys, const uint8_t *__restrict__ c,
+                                                                       const uint8_t *__restrict__ Kr, const uint32_t *__restrict__ flags,
+                                                                       uint8_t *__restrict__ Kout) {
+    const int lane = threadIdx.x & 31, i = blockIdx.x * (kWarpHashTPB / 32) + (threadIdx.x >> 5);
+    if (i >= n) return;
+    const WarpSponge w = warp_sponge_init(lane);
+    const uint8_t *z = dk + (size_t)P::DK * key_row(keys, i) + 768 * P::K + 64;
+    const uint8_t *ci = c + (size_t)P::C * i;
+    const Lane a = warp_sponge_absorb_words<RATE>(lane, w, 4 + P::C / 8, kSfxXof,
+                                                  [&](int t) { return t < 4 ? load_lane(z + 8 * t) : load_lane(ci + 8 * (t - 4)); });
+    const uint32_t mask = flags[i] ? 0xFFFFFFFFu : 0u;  // branch-free select, as in k_decaps_J_select
+    if (lane < 4) {
+        const Lane kp = load_lane(Kr + 64 * (size_t)i + 8 * lane);
+        store_lane(Kout + 32 * (size_t)i + 8 * lane, Lane{(a.lo & mask) | (kp.lo & ~mask), (a.hi & mask) | (kp.hi & ~mask)});
+    }
+}
+
 // Generic batched hash over equal-length messages, length a multiple of 8 bytes.  RATE (lanes) and the suffix select the
 // function, OUTW the output lanes: H = <17, 4> + 0x06, G = <9, 8> + 0x06, J = <21, 4> + 0x1F (the host maps `which` to these).
 template <int RATE, int OUTW>

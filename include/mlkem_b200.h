@@ -74,7 +74,10 @@ typedef struct mlkem_b200_opts {
  *                          mlkem_b200_set_streams() overrides it
  *   MLKEM_B200_HOST_CHUNK  items per staged chunk of a host-memory call [65536]
  *   MLKEM_B200_HOST_SLOTS  staging slots (H2D / kernels / D2H overlap) of a host-memory call [3]; consecutive host-memory
- *                          calls alternate between two such groups of slots */
+ *                          calls alternate between two such groups of slots
+ *   MLKEM_B200_WARP_HASH_MAX  chunks of at most this many items run their long hash chains (H(ek), G(m || h), J(z || c), the dk
+ *                          hash check) with one sponge per warp instead of one per thread [1024]: the latency form, 13-21 % off a
+ *                          batch of one (profiles/latency_r02_warp_hash_ab.jsonl); 0 = one sponge per thread everywhere */
 
 /* FIPS 203 mode.  The reference deviates from FIPS 203: its PRF and J are SHAKE128
  * and its ByteDecode12 never reduces, so the modulus check of KEM_Encaps cannot fail (D4).  With this flag PRF and J are

@@ -193,3 +193,22 @@ def test_algorithmic_work_model_matches_the_scope_table():
     ops = wl.op_counts(3, 2, 10, 4)
     assert (ops["keygen"], ops["encaps"], ops["decaps"]) == (232_224, 250_624, 267_200)
     assert ops["encaps"] + ops["decaps"] == 517_824 and ops["matvec_encrypt"] == 151_968
+
+
+def test_warp_keccak_model():
+    """The one-sponge-per-warp Keccak of the small-batch hash kernels (keccak_f1600_warp, mlkem_device.cuh): a numpy model of its
+    32 lanes -- same shuffle sources, rho offsets, funnel-shift rotate and pad placement -- reproduces hashlib's SHA3-256,
+    SHA3-512, SHAKE128 and SHAKE256 on ML-KEM-sized messages, and the rho constants packed in the CUDA source are the model's."""
+    import re
+
+    import warp_keccak_model as model
+
+    assert model.check_against_hashlib()
+    src = open(os.path.join(ROOT, "crystals-kyber_b200", "csrc", "mlkem_device.cuh")).read()
+    body = re.search(r"constexpr uint32_t kRho\[7\] = \{(.*?)\};", src, re.S).group(1)
+    words = [eval(w.replace("u", "")) for w in body.replace("\n", " ").split(",")]  # "27u | 36u << 8 | ..." -> int
+    assert len(words) == 7
+    assert [(words[l >> 2] >> (8 * (l & 3))) & 63 for l in range(25)] == model.RHO
+    # the shuffle sources the kernel computes, restated from the source text's formulas, are permutations of the 25 lanes
+    for name in ("s5", "s10", "s15", "s20", "pi_src"):
+        assert sorted(getattr(model, name)[:25]) == list(range(25)), name

@@ -1248,3 +1248,33 @@ def test_unmodified_sha_testing_driver_linked_against_the_library(mlkem, sha_exa
     if not os.path.exists(exe):
         pytest.skip("oracle/_ref/drivers/SHA_Testing not built (needs /root/reference at build time)")
     assert len(sha_flow.run(exe, sha_examples["examples"], str(tmp_path))) == 16
+
+
+@pytest.mark.parametrize("ps", SETS)
+def test_small_batches_hash_with_one_sponge_per_warp(mlkem, oracle, ps):
+    """Batches of at most 1024 items run H(ek), G(m || h), J(z || c) and the dk hash check with one sponge per WARP
+    (keccak_f1600_warp: the latency form), larger ones with one per thread; both sides of the switch give the oracle's bytes."""
+    rng = np.random.default_rng(21 + ps)
+    n = 1500
+    d, z, m = (rng.integers(0, 256, (n, 32), dtype=np.uint8) for _ in range(3))
+    oek, odk = oracle.keygen(ps, d, z)
+    oc, oK = oracle.encaps(ps, oek, m)
+    ct = oc.copy()
+    ct[::7, 5] ^= 1  # every seventh ciphertext tampered: J(z || c) is selected there
+    oKd = oracle.decaps(ps, odk, ct)
+    bad_dk = odk.copy()
+    bad_dk[3, -40] ^= 0x10  # inside the stored H(ek) of item 3
+    for cut in (1, 5, 1000, 1024, 1025, n):
+        mlkem.profile(True)
+        ek, dk = mlkem.keygen(ps, d[:cut], z[:cut])
+        c, K = mlkem.encaps(ps, ek, m[:cut])
+        Kd = mlkem.decaps(ps, dk, ct[:cut])
+        st = mlkem.check_dk(ps, bad_dk[:cut])
+        mlkem.profile(False)
+        names = list(mlkem.profile_report())
+        assert any("_warp" in k for k in names) == (cut <= 1024), (cut, names)
+        assert (ek == oek[:cut]).all() and (dk == odk[:cut]).all(), cut
+        assert (c == oc[:cut]).all() and (K == oK[:cut]).all() and (Kd == oKd[:cut]).all(), cut
+        want = np.zeros(cut, np.int32)
+        want[3:4] = -5  # (no item 3 when cut <= 3)
+        assert (st == want).all(), cut
