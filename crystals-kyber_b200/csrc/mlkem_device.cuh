@@ -5,7 +5,8 @@
 //
 //   1. field arithmetic mod q = 3329 (Shoup multiplication by constants, Barrett for products),
 //   2. Keccak-f[1600] with one sponge per THREAD (25 lanes as 50 x 32-bit registers, funnel-shift
-//      rotates), plus absorb/squeeze helpers for SHA3-256 / SHA3-512 / SHAKE128,
+//      rotates), plus absorb/squeeze helpers for SHA3-256 / SHA3-512 / SHAKE128; and (2b) the same permutation with one
+//      sponge per WARP (state lanes spread over the lanes, neighbours by shuffle) for the hash chains of small batches,
 //   3. polynomial routines with one polynomial per WARP: NTT / inverse NTT (8 coefficients per lane,
 //      three register-local passes with two transposes through a swizzled shared-memory scratch, no
 //      shuffles), NTT-domain multiply-accumulate, Compress/Decompress and ByteEncode/ByteDecode.

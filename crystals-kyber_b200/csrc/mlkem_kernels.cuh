@@ -2,7 +2,8 @@
 //
 // Work decomposition (DESIGN.md has the full picture):
 //   * every Keccak sponge is run by ONE THREAD (state in registers); a warp therefore runs 32 sponges of
-//     the same kind in lock step.  Kernels are split by sponge kind so warps never mix roles.
+//     the same kind in lock step.  Kernels are split by sponge kind so warps never mix roles.  (Small batches are the
+//     exception: the k_*_warp hash kernels run one sponge per WARP, the latency form -- keccak_f1600_warp.)
 //   * every polynomial operation (NTT, inverse NTT, multiply-accumulate, compress, pack) is run by ONE
 //     WARP per polynomial, 8 coefficients per lane.
 //   * the matrix expansion is fused with its consumer: k_sample_matvec samples the k entries of one matrix
