@@ -27,7 +27,7 @@ hist=profiles/sass_hist_${tag}.txt
 echo "# cuobjdump -sass opcode histograms (static instruction counts), tools/sass_static.py"
 for pat in 'k_sample_matvec<.*3, 2, 2, 10, 4>, 1>' 'k_sample_matvec<.*3, 2, 2, 10, 4>, 2>' 'k_sample_matvec_list<.*3, 2, 2, 10, 4>, 1>' \
            'k_matvec_table<.*3, 2, 2, 10, 4>, 1>' 'k_decrypt<.*3, 2, 2, 10, 4>' 'k_encrypt_v<.*3, 2, 2, 10, 4>, false' 'k_noise<2, true, 21>' 'k_noise<2, false, 21>' \
-           'k_encaps_HG<.*3, 2, 2, 10, 4>' 'k_decaps_J_select<.*3, 2, 2, 10, 4>, 21' 'k_ntt_batch' 'k_intt_batch' 'k_mulntt_batch'; do
+           'k_encaps_HG<.*3, 2, 2, 10, 4>' 'k_decaps_J_select<.*3, 2, 2, 10, 4>, 21' 'k_encaps_HG_warp<.*3, 2, 2, 10, 4>' 'k_decaps_J_select_warp<.*3, 2, 2, 10, 4>, 21' 'k_ntt_batch' 'k_intt_batch' 'k_mulntt_batch'; do
     python3 tools/sass_static.py crystals-kyber_b200/libmlkem_b200.so "$pat"
 done
 echo
@@ -37,5 +37,7 @@ echo "# and phase 2 (one row per iteration)"
 python3 tools/sass_loop.py crystals-kyber_b200/libmlkem_b200.so 'k_decaps_G<.*3, 2, 2, 10, 4>'
 python3 tools/sass_loop.py crystals-kyber_b200/libmlkem_b200.so 'k_sample_matvec<.*3, 2, 2, 10, 4>, 1>'
 python3 tools/sass_loop.py crystals-kyber_b200/libmlkem_b200.so 'k_matvec_table<.*3, 2, 2, 10, 4>, 1>'
+echo "# one sponge per warp (small batches): the loop holds TWO rounds = 36 SHFL + 20 LOP3 + 8 SHF + 8 SEL"
+python3 tools/sass_loop.py crystals-kyber_b200/libmlkem_b200.so 'k_encaps_HG_warp<.*3, 2, 2, 10, 4>'
 } > $hist
 echo "wrote $hist"
