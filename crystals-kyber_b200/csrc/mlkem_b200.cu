@@ -313,7 +313,9 @@ int launch_matvec(cudaStream_t st, Arena &ws, MatvecArgs a) {
     static const int env_exp = env_int("MLKEM_B200_EXPERIMENT", 0);
     a.experiment = env_exp;
 #endif
-    if (a.group_limit >= 168) {
+    // A batch that fits one block (a batch of one, most of all) goes through the general kernel alone: the same results from
+    // one launch instead of a memset and two launches, and nothing to defer when there is no second wave of blocks to keep busy.
+    if (a.group_limit >= 168 && rows > 32) {
         a.defer_list = ws.take<int>(rows);
         a.defer_count = ws.take<int>(1);
         CU(cudaMemsetAsync(a.defer_count, 0, sizeof(int), st));
